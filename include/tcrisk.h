@@ -1,0 +1,183 @@
+/*
+ * tcrisk.h -- C ABI of the B200-native synthetic tropical-cyclone ensemble
+ * integrator (libtcrisk.so).
+ *
+ * The reference (linjonathan/tropical_cyclone_risk) has no FFI: its seam for the
+ * hot path is Python-level:
+ *
+ *   outer:  run_tracks(year, n_tracks, b) -> 9-tuple          util/compute.py:64,210
+ *   inner:  Coupled_FAST(...).init_fields / .gen_track        intensity/coupled_fast.py:19,217,229
+ *           BetaAdvectionTrack._env_winds                     track/bam_track.py:116
+ *           RectBivariateSpline(kx=1,ky=1).ev                 util/mat.py:142-153
+ *
+ * Every entry point below names the reference interface it replaces.  Plain C,
+ * caller-allocated buffers, int status return (0 = ok, <0 = error; text via
+ * tcr_last_error()).  No exceptions, no torch types.  One handle per device;
+ * calls on one handle must be serialised by the caller.  All kernels and copies
+ * are issued on the handle's stream (tcr_set_stream, default stream 0).
+ *
+ * Pointer arguments named h_* are HOST pointers; d_* are DEVICE pointers; the
+ * remaining data pointers are host pointers unless `on_device` says otherwise.
+ */
+#ifndef TCRISK_H
+#define TCRISK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCR_N_CH          20   /* channels per grid point in HBM (19 used + pad)        */
+#define TCR_N_FIELDS      19   /* fields supplied per month (layout.py FIELD_NAMES)     */
+#define TCR_N_INTERP_OUT  21   /* tcr_env_interp outputs: 19 fields, bathymetry, land   */
+#define TCR_N_BASINS       7   /* sorted basin ids AU EP NA NI SI SP WP (compute.py:87) */
+#define TCR_N_MASKS        8   /* 7 basin masks + the run basin's own mask (f_b)        */
+#define TCR_N_SERIES       4   /* Fourier series per storm = nWLvl (bam_track.py:60)    */
+#define TCR_N_HARM        15   /* harmonics per series (bam_track.py:112)               */
+#define TCR_N_PHASES      60
+
+/* storm status codes (scipy solve_ivp status + the reference's `None`) */
+#define TCR_STATUS_FINISHED   0   /* reached total_time                                  */
+#define TCR_STATUS_EVENT      1   /* terminal event tc_dissipates (coupled_fast.py:246)  */
+#define TCR_STATUS_FAILED    -1   /* step size underflow (scipy rk.py _step_impl)        */
+#define TCR_STATUS_VENT       2   /* gen_track returned None (coupled_fast.py:241-244)   */
+
+/* storm flag bits */
+#define TCR_FLAG_IS_TC   1u   /* util/compute.py:185-189 */
+#define TCR_FLAG_KEPT    2u   /* util/compute.py:205     */
+
+/* All physics / configuration constants the hot path reads from `namelist`
+ * (reference namelist.py:40-119) plus the fixed constants of coupled_fast.py:23-27,
+ * bam_track.py:52-60, constants.py:7.  Filled by params_from_namelist() in Python. */
+typedef struct tcr_params {
+    double dt_track;            /* namelist.output_interval_s               (bam_track.py:52)  */
+    double total_time;          /* total_track_time_days*86400              (bam_track.py:53)  */
+    double T_Fs;                /* namelist.T_days*86400                    (bam_track.py:56)  */
+    double max_step;            /* 86400                                    (coupled_fast.py:266) */
+    double rtol, atol;          /* 1e-3, 1e-6 (scipy solve_ivp defaults)                        */
+    double u_beta, v_beta;      /* namelist.py:77-78                                            */
+    double steering_coefs[2];   /* used when coupled_track == 0             (coupled_fast.py:191) */
+    double y_alpha[2], m_alpha[2], alpha_max[2], alpha_min[2];      /* namelist.py:73-76       */
+    double Ck;                  /* namelist.py:57                                               */
+    double epsilon, kappa, beta;/* 0.33, 0.1, 1-0.33-0.1                    (coupled_fast.py:25-27) */
+    double earth_R;             /* 6.3781e6                                 (constants.py:7)    */
+    double basin_bounds[4];     /* lon_min, lat_min, lon_max, lat_max       (basins.py:42-50)   */
+    double gen_lat_min, gen_lat_max;   /* 3|-45, 45|-3                      (compute.py:140-141) */
+    double lat_vort_fac;        /* namelist.py:89                                               */
+    double lat_vort_power[TCR_N_BASINS];   /* namelist.py:90-92, sorted basin order             */
+    double atm_bl_depth[TCR_N_BASINS];     /* namelist.py:85-86, sorted basin order             */
+    double seed_v_init;         /* namelist.py:80                                               */
+    double seed_v_2d_thresh;    /* namelist.py:81                                               */
+    double seed_v_thresh;       /* namelist.py:82                                               */
+    double seed_vmax_thresh;    /* namelist.py:83                                               */
+    double pi_gen_min;          /* 35 m/s                                   (compute.py:168)    */
+    double minit_amp, minit_center, minit_slope, minit_offset;  /* f_mInit  (namelist.py:94)    */
+    double fourier_amp[TCR_N_HARM];   /* sqrt(2/sum n^-3) * n^-1.5, n=1..15  (bam_track.py:28-29) */
+    int32_t n_steps;            /* int(total_time/dt_track)+1               (bam_track.py:54)   */
+    int32_t coupled_track;      /* namelist.py:72                                               */
+    int32_t max_redraws;        /* bound on the ocean-point redraw loop     (compute.py:146-148) */
+    int32_t reserved;
+} tcr_params;
+
+/* Work counters of one tcr_run_years call (all per year; arrays of n_years). */
+typedef struct tcr_year_stats {
+    int64_t attempts;          /* seed attempts consumed, i.e. i*+1 (compute.py:136 iterations)  */
+    int64_t counted_seeds;     /* sum of n_seeds                                                  */
+    int64_t integrated;        /* gen_track calls with attempt index <= i*                       */
+    int64_t storm_steps;       /* emitted samples of those calls (sum len(res.t))                */
+    int64_t kept_steps;        /* samples of the n_tracks kept storms                            */
+    int64_t rhs_evals;         /* dydt evaluations of those calls                                */
+    int64_t wasted_integrated; /* gen_track calls beyond i* (over-shoot of the last wave)        */
+    int64_t wasted_steps;      /* their samples                                                  */
+    int32_t n_kept;            /* == n_tracks on success                                         */
+    int32_t n_waves;
+} tcr_year_stats;
+
+typedef struct tcr_handle tcr_handle;
+
+/* ---- life cycle ----------------------------------------------------------------------- */
+/* replaces: Coupled_FAST.__init__ constants + namelist reads (coupled_fast.py:19-32)       */
+int tcr_create(int device, const tcr_params* p, tcr_handle** out);
+int tcr_destroy(tcr_handle* h);
+const char* tcr_last_error(void);
+/* issue all subsequent work of `h` on this cudaStream_t (pass torch's current stream)     */
+int tcr_set_stream(tcr_handle* h, void* cuda_stream);
+int tcr_synchronize(tcr_handle* h);
+int tcr_version(void);
+
+/* ---- static fields -------------------------------------------------------------------- */
+/* replaces: geo.read_bathy / geo.read_land (intensity/geo.py:9-33): basin-cropped,
+ * ascending axes; int16 bathymetry [nlat_b][nlon_b], int8 land [nlat_l][nlon_l].          */
+int tcr_upload_static(tcr_handle* h,
+                      int nlat_b, int nlon_b, const double* lat_b, const double* lon_b, const int16_t* bathy,
+                      int nlat_l, int nlon_l, const double* lat_l, const double* lon_l, const int8_t* land);
+/* replaces: f_basins[...] / f_b = mat.interp2_fx(land/<id>.nc) (util/compute.py:87-97):
+ * masks uint8 [TCR_N_MASKS][nlat_m][nlon_m]; planes 0..6 sorted basin ids, plane 7 = run basin */
+int tcr_upload_masks(tcr_handle* h, int nlat_m, int nlon_m, const double* lat_m, const double* lon_m,
+                     const uint8_t* masks);
+
+/* ---- monthly environment tables ------------------------------------------------------- */
+/* replaces: BetaAdvectionTrack._load_wnd_stat + Coupled_FAST.init_fields for one month
+ * (track/bam_track.py:76-91, intensity/coupled_fast.py:217-225).  All fields share one
+ * basin-cropped ascending grid.  tcr_alloc_tables sizes the HBM arena for n_ym months
+ * (index ym = year_slot*12 + month-1); tcr_upload_month interleaves 19 float32 planes
+ * [nlat][nlon] into the [nlat][nlon][20] record layout on the device.                      */
+int tcr_alloc_tables(tcr_handle* h, int n_ym, int nlat, int nlon, const double* lat, const double* lon);
+int tcr_upload_month(tcr_handle* h, int ym, const float* const* fields /*[TCR_N_FIELDS]*/);
+/* same, source planes already in HBM as one contiguous [19][nlat][nlon] float32 block       */
+int tcr_upload_month_dev(tcr_handle* h, int ym, const float* d_planes);
+
+/* ---- stand-alone bilinear sampler (roofline kernel) ----------------------------------- */
+/* replaces: RectBivariateSpline(kx=1,ky=1).ev on every field (util/mat.py:142-153,
+ * bam_track.py:93-108, coupled_fast.py:35-58,125-126).  out[n][21] float64.                */
+int tcr_env_interp(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon, const double* lat,
+                   double* out, int on_device);
+
+/* ---- integrate given seeds ------------------------------------------------------------ */
+/* replaces: Coupled_FAST.gen_track (coupled_fast.py:229-267) + the per-candidate post-
+ * processing of run_tracks (compute.py:178-206: TC criteria, env-wind recompute, vmax).
+ * phases[n][4][15] are the uniform random phases of gen_f (bam_track.py:27).
+ * Outputs (any may be NULL): track [n][n_steps][4] = lon,lat,v,m ; env [n][n_steps][4];
+ * vmax [n][n_steps] (NaN padded past n_time); n_time, status, nfev, flags [n].             */
+int tcr_integrate(tcr_handle* h, int64_t n,
+                  const int32_t* ym, const double* lon0, const double* lat0,
+                  const double* v0, const double* m0, const double* h_bl, const double* phases,
+                  double* track, double* env, double* vmax,
+                  int32_t* n_time, int32_t* status, int32_t* nfev, uint32_t* flags,
+                  int on_device);
+
+/* ---- whole years: seeding + integration + ordered selection ---------------------------- */
+/* replaces: run_tracks(year, n_tracks, b) for n_years years at once (util/compute.py:64-210).
+ * Year y uses tables ym = ym_base[y] .. ym_base[y]+11 and Philox key (run_seed, year_key[y]).
+ * Seed attempts are indexed 0,1,2,... per year; rank r of `world` integrates the attempts it
+ * owns and the first n_tracks kept storms in attempt order are returned.
+ * Outputs per year y (row-major, year-major): lon/lat/v/m/vmax [n_years][n_tracks][n_steps],
+ * env [n_years][n_tracks][n_steps][4], tc_month [n_years][n_tracks] (double, 1..12),
+ * tc_basin [n_years][n_tracks] (index into sorted ids), n_seeds [n_years][7][12] (double).
+ * Data outputs are host or device pointers per `on_device`; stats is always a host pointer. */
+int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int32_t* year_key,
+                  uint32_t run_seed, int n_tracks,
+                  double* lon, double* lat, double* v, double* m, double* vmax, double* env,
+                  double* tc_month, int32_t* tc_basin, double* n_seeds,
+                  tcr_year_stats* stats, int on_device);
+
+/* seeding only: evaluate attempts [k0, k0+n) of one year -> per-attempt records (test hook
+ * for util/compute.py:136-175).  code: 0 = not a seed, 1 = counted (PI <= 35), 2 = passed,
+ * 3 = redraw bound hit.  Host pointers.                                                     */
+int tcr_seed_attempts(tcr_handle* h, int ym_base, int32_t year_key, uint32_t run_seed,
+                      int64_t k0, int64_t n,
+                      int32_t* code, int32_t* basin, int32_t* month,
+                      double* lon, double* lat, double* v0, double* m0, double* pi_gen);
+
+/* tuning knobs (0 keeps the default): persistent CTAs per SM / threads per CTA of the
+ * integrate kernel, candidate rows per wave, wave over-subscription factor (x1000)          */
+int tcr_set_tuning(tcr_handle* h, int ctas_per_sm, int threads_per_cta, int64_t max_wave_cands,
+                   int oversub_permille);
+/* number of kernels launched by this handle so far (bench.py's gpu_launches)               */
+int64_t tcr_launch_count(tcr_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCRISK_H */
