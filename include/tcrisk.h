@@ -22,6 +22,7 @@
 #ifndef TCRISK_H
 #define TCRISK_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -42,6 +43,12 @@ extern "C" {
 #define TCR_STATUS_EVENT      1   /* terminal event tc_dissipates (coupled_fast.py:246)  */
 #define TCR_STATUS_FAILED    -1   /* step size underflow (scipy rk.py _step_impl)        */
 #define TCR_STATUS_VENT       2   /* gen_track returned None (coupled_fast.py:241-244)   */
+
+/* Safety net absent from the reference: scipy's RK45 loops forever when the step size
+ * becomes NaN (a NaN genesis point) and crawls at 10 ulp(t) per step if error control
+ * collapses.  A storm whose step size is NaN, or that needs more than this many RK attempts,
+ * ends with TCR_STATUS_FAILED.  (Storms on real fields take 10-40 attempts.)                 */
+#define TCR_MAX_RK_ATTEMPTS 20000
 
 /* storm flag bits */
 #define TCR_FLAG_IS_TC   1u   /* util/compute.py:185-189 */
@@ -176,6 +183,14 @@ int tcr_set_tuning(tcr_handle* h, int ctas_per_sm, int threads_per_cta, int64_t 
                    int oversub_permille);
 /* number of kernels launched by this handle so far (bench.py's gpu_launches)               */
 int64_t tcr_launch_count(tcr_handle* h);
+/* tcr_env_interp implementation: 0 = per-lane LDG.128 gathers, 1 = TMA bulk copies
+ * (cp.async.bulk) of the cell records into shared memory behind an mbarrier pipeline        */
+int tcr_set_interp_variant(tcr_handle* h, int variant);
+/* page-locked host memory for the caller's input planes / result arrays (the reference's
+ * NumPy arrays of util/compute.py:126-133 become views of this block): makes the host<->device
+ * copies of tcr_upload_month / tcr_run_years run at PCIe speed                               */
+int tcr_host_alloc(size_t bytes, void** out);
+int tcr_host_free(void* p);
 
 #ifdef __cplusplus
 }

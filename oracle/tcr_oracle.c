@@ -515,7 +515,7 @@ int orc_gen_track(const tcr_params* p, const orc_env* e, const double* coef,
     orc_dydt(&s, t, y, f);
     double h_abs = orc_initial_step(&s, t, y, t_bound, max_step, f, rtol, atol);
     double g = orc_event(p, y);
-    int status = 100, t_eval_i = 0;
+    int status = 100, t_eval_i = 0, n_attempts = 0;
 
     while (status == 100) {
         /* ---- RungeKutta._step_impl ---- */
@@ -524,7 +524,7 @@ int orc_gen_track(const tcr_params* p, const orc_env* e, const double* coef,
         int accepted = 0, rejected = 0, failed = 0;
         double h = 0.0, t_new = t, y_new[4], f_new[4];
         while (!accepted) {
-            if (h_abs < min_step) { failed = 1; break; }
+            if (h_abs < min_step || tcr_isnan(h_abs) || ++n_attempts > TCR_MAX_RK_ATTEMPTS) { failed = 1; break; }
             h = h_abs;
             t_new = t + h;
             if (t_new - t_bound > 0.0) t_new = t_bound;

@@ -1,0 +1,957 @@
+/*
+ * tcr_kernels.cuh -- the CUDA kernels of the hot path (sm_100a).  See DESIGN.md for the
+ * kernel-by-kernel roofline and the thread mapping; reference anchors are given per kernel.
+ */
+#pragma once
+#include "tcr_device.cuh"
+
+#define TCR_FULL 0xffffffffu
+
+/* ======================================================================================== */
+/* table builders: planes -> cell records                                                    */
+/* ======================================================================================== */
+/* one month: planes [19][nlat][nlon] float32 -> rec [ncy][ncx][20] float4 (corner quads)      */
+__global__ void k_build_month(const float* __restrict__ planes, float4* __restrict__ rec, int nlat, int nlon)
+{
+    const int ncx = nlon - 1, ncy = nlat - 1;
+    const size_t total = (size_t)ncx * ncy * TCR_REC_F4;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int ch = (int)(idx % TCR_REC_F4);
+        size_t cell = idx / TCR_REC_F4;
+        int ix = (int)(cell % ncx), iy = (int)(cell / ncx);
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ch < TCR_N_FIELDS) {
+            const float* p = planes + (size_t)ch * nlat * nlon + (size_t)iy * nlon + ix;
+            r = make_float4(p[0], p[nlon], p[1], p[nlon + 1]);
+        }
+        rec[idx] = r;
+    }
+}
+
+__global__ void k_build_bathy(const int16_t* __restrict__ src, short4* __restrict__ rec, int nlat, int nlon)
+{
+    const int ncx = nlon - 1, ncy = nlat - 1;
+    const size_t total = (size_t)ncx * ncy;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int ix = (int)(idx % ncx), iy = (int)(idx / ncx);
+        const int16_t* p = src + (size_t)iy * nlon + ix;
+        rec[idx] = make_short4(p[0], p[nlon], p[1], p[nlon + 1]);
+    }
+}
+
+__global__ void k_build_land(const int8_t* __restrict__ src, char4* __restrict__ rec, int nlat, int nlon)
+{
+    const int ncx = nlon - 1, ncy = nlat - 1;
+    const size_t total = (size_t)ncx * ncy;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int ix = (int)(idx % ncx), iy = (int)(idx / ncx);
+        const int8_t* p = src + (size_t)iy * nlon + ix;
+        rec[idx] = make_char4(p[0], p[nlon], p[1], p[nlon + 1]);
+    }
+}
+
+/* masks u8 [8][nlat][nlon] -> rec [ncy][ncx][4 corners] of 8 bytes (byte b = mask plane b)    */
+__global__ void k_build_masks(const uint8_t* __restrict__ src, uint2* __restrict__ rec, int nlat, int nlon)
+{
+    const int ncx = nlon - 1, ncy = nlat - 1;
+    const size_t total = (size_t)ncx * ncy * 4;
+    const size_t plane = (size_t)nlat * nlon;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        int corner = (int)(idx & 3);
+        size_t cell = idx >> 2;
+        int ix = (int)(cell % ncx) + (corner >> 1), iy = (int)(cell / ncx) + (corner & 1);
+        uint32_t lo = 0, hi = 0;
+        for (int b = 0; b < 4; ++b) lo |= (uint32_t)src[b * plane + (size_t)iy * nlon + ix] << (8 * b);
+        for (int b = 0; b < 4; ++b) hi |= (uint32_t)src[(4 + b) * plane + (size_t)iy * nlon + ix] << (8 * b);
+        rec[idx] = make_uint2(lo, hi);
+    }
+}
+
+__global__ void k_build_axis(const double* __restrict__ ax, double2* __restrict__ out, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(ax[i], i + 1 < n ? 1.0 / (ax[i + 1] - ax[i]) : 0.0);
+}
+
+/* ======================================================================================== */
+/* stand-alone bilinear sampler (the HBM-roofline kernel)                                     */
+/* replaces RectBivariateSpline(kx=1,ky=1).ev on every field: util/mat.py:142-153,            */
+/* bam_track.py:93-108, coupled_fast.py:35-58,125-126.  out [n][21] float64.                   */
+/* ======================================================================================== */
+#define EI_TILE 256
+#define EI_ITEMS (EI_TILE * TCR_N_INTERP_OUT)
+
+struct EiLoc { const float4* rec; double w00, w01, w10, w11, bathy, land; };
+
+/* variant 0: per-lane LDG.128 of the record quads, flat (query, channel) item space so that
+ * both the record reads and the float64 output writes are fully coalesced                    */
+__global__ void __launch_bounds__(EI_TILE) k_env_interp(const __grid_constant__ TcrCtx cx, int64_t n,
+                                                        const int32_t* __restrict__ ym, const double* __restrict__ lon,
+                                                        const double* __restrict__ lat, double* __restrict__ out)
+{
+    __shared__ EiLoc loc[EI_TILE];
+    const int tid = threadIdx.x;
+    const int64_t q0 = (int64_t)blockIdx.x * EI_TILE;
+    const int nq = (int)min((int64_t)EI_TILE, n - q0);
+    if (tid < nq) {
+        const int64_t q = q0 + tid;
+        const double x = lon[q], y = lat[q];
+        TcrCell c;
+        tcr_cell_at(cx.tab.lon, cx.tab.lat, x, y, c);
+        EiLoc l;
+        l.rec = tcr_record(cx.tab, ym[q], c);
+        l.w00 = c.w00; l.w01 = c.w01; l.w10 = c.w10; l.w11 = c.w11;
+        l.bathy = tcr_bathy_at(cx.st, x, y);
+        l.land = tcr_land_at(cx.st, x, y);
+        loc[tid] = l;
+    }
+    __syncthreads();
+    double* o = out + q0 * TCR_N_INTERP_OUT;
+    const int n_items = nq * TCR_N_INTERP_OUT;
+    /* 21 items per thread, in 3 batches of 7 independent loads */
+#pragma unroll 1
+    for (int b = 0; b < 3; ++b) {
+        float4 r[7];
+        int qi[7], ch[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            int i = tid + (b * 7 + j) * EI_TILE;
+            qi[j] = i / TCR_N_INTERP_OUT;
+            ch[j] = i - qi[j] * TCR_N_INTERP_OUT;
+            r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_items && ch[j] < TCR_N_FIELDS) r[j] = __ldg(loc[qi[j]].rec + ch[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            int i = tid + (b * 7 + j) * EI_TILE;
+            if (i < n_items) {
+                const EiLoc& l = loc[qi[j]];
+                double v;
+                if (ch[j] < TCR_N_FIELDS)
+                    v = fma((double)r[j].w, l.w11, fma((double)r[j].z, l.w10, fma((double)r[j].y, l.w01, (double)r[j].x * l.w00)));
+                else
+                    v = (ch[j] == TCR_N_FIELDS) ? l.bathy : l.land;
+                __stcs(o + i, v);
+            }
+        }
+    }
+}
+
+/* variant 1: each query's 320-byte record is staged into shared memory by one TMA bulk copy
+ * (cp.async.bulk, SASS UBLKCP) completing on an mbarrier; the 21 outputs per query are then
+ * formed from shared memory.  One elected thread per query issues the copy.                  */
+__device__ __forceinline__ uint32_t tcr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tcr_mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tcr_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tcr_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tcr_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tcr_mbar_wait(uint64_t* bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(tcr_smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tcr_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tcr_smem_u32(dst)), "l"(src), "r"(bytes), "r"(tcr_smem_u32(bar)) : "memory");
+}
+
+#define EIT_TILE 128           /* queries per stage */
+#define EIT_STAGES 3
+struct EitLoc { double w00, w01, w10, w11, bathy, land; };
+
+__global__ void __launch_bounds__(EIT_TILE * 2) k_env_interp_tma(const __grid_constant__ TcrCtx cx, int64_t n,
+                                                                 const int32_t* __restrict__ ym, const double* __restrict__ lon,
+                                                                 const double* __restrict__ lat, double* __restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* stage_rec = reinterpret_cast<float4*>(smem_raw);                                   /* [S][TILE][20] */
+    EitLoc* stage_loc = reinterpret_cast<EitLoc*>(smem_raw + (size_t)EIT_STAGES * EIT_TILE * TCR_REC_F4 * 16);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_loc + EIT_STAGES * EIT_TILE);
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (n + EIT_TILE - 1) / EIT_TILE;
+    if (tid == 0) {
+        for (int s = 0; s < EIT_STAGES; ++s) tcr_mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    /* producer step for tile `tile` into stage s: threads 0..TILE-1 locate one query each and
+     * issue its bulk copy; thread 0 first posts the expected byte count                        */
+    auto produce = [&](int64_t tile, int s) {
+        const int64_t q0 = tile * EIT_TILE;
+        const int nq = (int)min((int64_t)EIT_TILE, n - q0);
+        if (tid == 0) tcr_mbar_expect_tx(bars + s, (uint32_t)nq * TCR_REC_F4 * 16);
+        __syncthreads();
+        if (tid < nq) {
+            const int64_t q = q0 + tid;
+            const double x = lon[q], y = lat[q];
+            TcrCell c;
+            tcr_cell_at(cx.tab.lon, cx.tab.lat, x, y, c);
+            tcr_bulk_g2s(stage_rec + ((size_t)s * EIT_TILE + tid) * TCR_REC_F4, tcr_record(cx.tab, ym[q], c),
+                         TCR_REC_F4 * 16, bars + s);
+            EitLoc l;
+            l.w00 = c.w00; l.w01 = c.w01; l.w10 = c.w10; l.w11 = c.w11;
+            l.bathy = tcr_bathy_at(cx.st, x, y);
+            l.land = tcr_land_at(cx.st, x, y);
+            stage_loc[s * EIT_TILE + tid] = l;
+        }
+    };
+
+    int64_t tile = blockIdx.x;
+    int it = 0;
+    /* prologue: fill STAGES-1 stages */
+    for (int s = 0; s < EIT_STAGES - 1; ++s) {
+        int64_t tl = tile + (int64_t)s * gridDim.x;
+        if (tl < n_tiles) produce(tl, s);
+    }
+    for (; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int s = it % EIT_STAGES;
+        const uint32_t phase = (uint32_t)(it / EIT_STAGES) & 1u;
+        /* refill the stage that was consumed in the previous iteration */
+        {
+            int64_t tl = tile + (int64_t)(EIT_STAGES - 1) * gridDim.x;
+            if (tl < n_tiles) produce(tl, (it + EIT_STAGES - 1) % EIT_STAGES);
+        }
+        __syncthreads();                       /* stage_loc[s] visible */
+        tcr_mbar_wait(bars + s, phase);
+        const int64_t q0 = tile * EIT_TILE;
+        const int nq = (int)min((int64_t)EIT_TILE, n - q0);
+        const int n_items = nq * TCR_N_INTERP_OUT;
+        double* o = out + q0 * TCR_N_INTERP_OUT;
+        const float4* recs = stage_rec + (size_t)s * EIT_TILE * TCR_REC_F4;
+        const EitLoc* locs = stage_loc + s * EIT_TILE;
+        for (int i = tid; i < n_items; i += blockDim.x) {
+            int qi = i / TCR_N_INTERP_OUT, ch = i - qi * TCR_N_INTERP_OUT;
+            const EitLoc& l = locs[qi];
+            double v;
+            if (ch < TCR_N_FIELDS) {
+                float4 r = recs[qi * TCR_REC_F4 + ch];
+                v = fma((double)r.w, l.w11, fma((double)r.z, l.w10, fma((double)r.y, l.w01, (double)r.x * l.w00)));
+            } else {
+                v = (ch == TCR_N_FIELDS) ? l.bathy : l.land;
+            }
+            __stcs(o + i, v);
+        }
+        __syncthreads();                       /* stage s free for the next refill */
+    }
+}
+
+/* ======================================================================================== */
+/* Fourier coefficients of a wave's storms                                                    */
+/* gen_f phases (bam_track.py:27) -> {A, B} = amp_k {cos, sin}(2 pi x): the angle-addition   */
+/* form of bam_track.py:28-31.  coef [n][60] double2.                                         */
+/* ======================================================================================== */
+__global__ void k_coef_from_phases(const __grid_constant__ TcrCtx cx, int64_t n, const double* __restrict__ phases,
+                                   double2* __restrict__ coef)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * TCR_N_PHASES) return;
+    int pair = (int)(idx % TCR_N_PHASES);
+    double s, c;
+    tcr_sincos2pi(phases[idx], &s, &c);
+    double amp = cx.p.fourier_amp[pair % TCR_N_HARM];
+    coef[idx] = make_double2(amp * c, amp * s);
+}
+
+__global__ void k_coef_from_philox(const __grid_constant__ TcrCtx cx, const unsigned int* __restrict__ n_slots,
+                                   const int64_t* __restrict__ slot_att, const int32_t* __restrict__ slot_key,
+                                   uint32_t run_seed, double2* __restrict__ coef)
+{
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t slot = idx / TCR_N_PHASES;
+    if (slot >= (int64_t)*n_slots) return;
+    int pair = (int)(idx - slot * TCR_N_PHASES);
+    double u[2];
+    tcr_draw2(run_seed, slot_key[slot], slot_att[slot], (uint32_t)(pair >> 1), 1u, u);
+    double s, c;
+    tcr_sincos2pi(u[pair & 1], &s, &c);
+    double amp = cx.p.fourier_amp[pair % TCR_N_HARM];
+    coef[idx] = make_double2(amp * c, amp * s);
+}
+
+/* ======================================================================================== */
+/* the integrator: Coupled_FAST.gen_track (coupled_fast.py:229-267) incl. scipy's RK45        */
+/* driver loop, t_eval dense output and the terminal event                                    */
+/* ======================================================================================== */
+struct IntegArgs {
+    int64_t n;                         /* number of storms (slots) if n_dev == NULL           */
+    const unsigned int* n_dev;         /* device-side count (run_years)                       */
+    const int32_t* ym;                 /* [n] table index                                     */
+    const double* lon0; const double* lat0; const double* v0; const double* m0; const double* h_bl;
+    const double2* coef;               /* [n][60]                                             */
+    double* track;                     /* [n][n_steps][4] lon,lat,v,m                         */
+    int32_t* n_time; int32_t* status; int32_t* nfev; uint32_t* flags;
+    unsigned long long* queue;         /* work counter, zeroed by the host                    */
+    int32_t* cand_list; unsigned int* cand_count;   /* TC candidates (NULL: not collected)    */
+    int lane_cap;                      /* lanes per warp that take storms (small batches)     */
+};
+
+enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
+
+/* Thread mapping: ONE STORM PER LANE, warps advance in lock-step MACRO STEPS of six RHS
+ * evaluations -- exactly one RK45 attempt (5 stages + the FSAL evaluation), accepted or
+ * rejected -- so the expensive RHS is always executed convergently and only the cheap
+ * per-stage bookkeeping is predicated.  A lane whose storm ended pops the next storm from
+ * the global queue and spends its macro step on the two initial-step evaluations
+ * (select_initial_step); the persistent loop ends when the queue is drained.  Storm state
+ * (y, K[7][4], step control) lives in registers for the storm's lifetime; the storm's 120
+ * Fourier coefficients live in shared memory; only emitted samples go to HBM.              */
+__global__ void __launch_bounds__(256, 1) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
+{
+    extern __shared__ __align__(16) double2 cf_s[];          /* [60][blockDim.x] */
+    const tcr_params& p = cx.p;
+    const int tid = threadIdx.x, lane = tid & 31, stride = blockDim.x;
+    double2* cf = cf_s + tid;
+    const int64_t n = A.n_dev ? (int64_t)*A.n_dev : A.n;
+    const int ns = p.n_steps;
+    const double t_bound = p.total_time, rtol = p.rtol, atol = p.atol, max_step = p.max_step;
+
+    int mode = M_IDLE;
+    bool drained = false;
+    int64_t sid = -1;
+    int ym = 0, nfev = 0, n_out = 0, status = 0, n_attempts = 0;
+    bool rejected = false, new_step = false, any_v = false;
+    double hbl = 0.0, t = 0.0, h = 0.0, h_abs = 0.0, t_new = 0.0, g = 0.0, min_step = 0.0;
+    double h0 = 0.0, d1 = 0.0;
+    double y[4] = {0, 0, 0, 0}, yn[4] = {0, 0, 0, 0};
+    double K0[4] = {0, 0, 0, 0}, K1[4] = {0, 0, 0, 0}, K2[4] = {0, 0, 0, 0}, K3[4] = {0, 0, 0, 0},
+           K4[4] = {0, 0, 0, 0}, K5[4] = {0, 0, 0, 0}, K6[4] = {0, 0, 0, 0};
+    double* trk = nullptr;
+
+    /* storm end: n_time / status / nfev / TC criteria (util/compute.py:185-189) */
+    auto finalize = [&](int st) {
+        A.n_time[sid] = n_out;
+        A.status[sid] = st;
+        A.nfev[sid] = (st == TCR_STATUS_VENT) ? 0 : nfev;
+        uint32_t fl = 0;
+        if (st != TCR_STATUS_VENT && n_out > 0) {
+            const double t2 = 2.0 * 24 * 60 * 60;
+            double v2d;
+            if (t2 >= tcr_node_time(cx, n_out - 1)) {
+                v2d = trk[(size_t)(n_out - 1) * 4 + 2];
+            } else {
+                int j = tcr_nodes_le(cx, t2, 1) - 1;
+                if (j > n_out - 2) j = n_out - 2;
+                double x0 = tcr_node_time(cx, j), x1 = tcr_node_time(cx, j + 1);
+                double vj = trk[(size_t)j * 4 + 2], vj1 = trk[(size_t)(j + 1) * 4 + 2];
+                double slope = (vj1 - vj) / (x1 - x0);
+                v2d = slope * (t2 - x0) + vj;
+            }
+            if (any_v && v2d >= p.seed_v_2d_thresh) fl = TCR_FLAG_IS_TC;
+        }
+        A.flags[sid] = fl;
+        if (fl && A.cand_list) A.cand_list[atomicAdd(A.cand_count, 1u)] = (int32_t)sid;
+        mode = M_IDLE;
+    };
+
+    for (;;) {
+        /* ---- macro-step boundary: open the next RK attempt (RungeKutta._step_impl) ---- */
+        if (mode == M_WAIT) { mode = M_RK; new_step = true; }
+        if (mode == M_RK) {
+            if (new_step) {
+                min_step = 10.0 * (tcr_bits2d(tcr_d2bits(t) + 1) - t);
+                if (h_abs > max_step) h_abs = max_step; else if (h_abs < min_step) h_abs = min_step;
+                rejected = false;
+                new_step = false;
+            }
+            if (h_abs < min_step || tcr_isnan(h_abs) || ++n_attempts > TCR_MAX_RK_ATTEMPTS) {
+                finalize(TCR_STATUS_FAILED);
+            } else {
+                h = h_abs;
+                t_new = t + h;
+                if (t_new - t_bound > 0.0) t_new = t_bound;
+                h = t_new - t;
+                h_abs = fabs(h);
+            }
+        }
+
+#pragma unroll 1
+        for (int slot = 0; slot < 6; ++slot) {
+            /* ---- idle lanes take the next storm from the queue ---- */
+            if (slot < 5 && !drained) {
+                const unsigned need = __ballot_sync(TCR_FULL, mode == M_IDLE && lane < A.lane_cap);
+                if (need) {
+                    const int cnt = __popc(need), leader = __ffs(need) - 1;
+                    unsigned long long base = 0;
+                    if (lane == leader) base = atomicAdd(A.queue, (unsigned long long)cnt);
+                    base = __shfl_sync(TCR_FULL, base, leader);
+                    if ((need >> lane) & 1u) {
+                        const int64_t my = (int64_t)base + __popc(need & ((1u << lane) - 1u));
+                        if (my < n) {
+                            sid = my;
+                            ym = A.ym[sid];
+                            y[0] = A.lon0[sid]; y[1] = A.lat0[sid]; y[2] = A.v0[sid]; y[3] = A.m0[sid];
+                            hbl = A.h_bl[sid];
+                            const double2* src = A.coef + (size_t)sid * TCR_N_PHASES;
+#pragma unroll 4
+                            for (int j = 0; j < TCR_N_PHASES; ++j) cf[j * stride] = __ldg(src + j);
+                            trk = A.track + (size_t)sid * ns * 4;
+                            nfev = 0; n_out = 0; n_attempts = 0; any_v = false; t = 0.0; status = 100;
+                            mode = M_INIT0;
+                        }
+                    }
+                    if ((int64_t)base + cnt >= n) drained = true;
+                }
+            }
+            if (slot == 0 && __ballot_sync(TCR_FULL, mode != M_IDLE) == 0u) return;   /* warp-uniform */
+
+            /* ---- evaluation point of this slot ---- */
+            double te = 0.0, ye[4] = {0, 0, 0, 0};
+            bool ev = false;
+            if (mode == M_RK) {
+                ev = true;
+                switch (slot) {
+                case 0:
+                    te = t + RK_C1 * h;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(K0[i] * RK_A10, h, y[i]);
+                    break;
+                case 1:
+                    te = t + RK_C2 * h;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(K1[i], RK_A21, K0[i] * RK_A20), h, y[i]);
+                    break;
+                case 2:
+                    te = t + RK_C3 * h;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(K2[i], RK_A32, fma(K1[i], RK_A31, K0[i] * RK_A30)), h, y[i]);
+                    break;
+                case 3:
+                    te = t + RK_C4 * h;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        ye[i] = fma(fma(K3[i], RK_A43, fma(K2[i], RK_A42, fma(K1[i], RK_A41, K0[i] * RK_A40))), h, y[i]);
+                    break;
+                case 4:
+                    te = t + 1.0 * h;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        ye[i] = fma(fma(K4[i], RK_A54, fma(K3[i], RK_A53, fma(K2[i], RK_A52, fma(K1[i], RK_A51, K0[i] * RK_A50)))), h, y[i]);
+                    break;
+                default:
+                    te = t + h;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        yn[i] = fma(h, fma(K5[i], RK_B5, fma(K4[i], RK_B4, fma(K3[i], RK_B3, fma(K2[i], RK_B2, K0[i] * RK_B0)))), y[i]);
+                        ye[i] = yn[i];
+                    }
+                    break;
+                }
+            } else if (mode == M_INIT0) {
+                ev = true; te = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ye[i] = y[i];
+            } else if (mode == M_INIT1) {
+                ev = true; te = 0.0 + h0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ye[i] = yn[i];
+            }
+
+            double dy[4] = {0, 0, 0, 0};
+            TcrRhsAux aux = {0, 0, 0};
+            if (ev) { tcr_rhs(cx, ym, cf, stride, hbl, te, ye, dy, aux); ++nfev; }
+
+            /* ---- consume ---- */
+            if (mode == M_RK) {
+                switch (slot) {
+                case 0: K1[0] = dy[0]; K1[1] = dy[1]; K1[2] = dy[2]; K1[3] = dy[3]; break;
+                case 1: K2[0] = dy[0]; K2[1] = dy[1]; K2[2] = dy[2]; K2[3] = dy[3]; break;
+                case 2: K3[0] = dy[0]; K3[1] = dy[1]; K3[2] = dy[2]; K3[3] = dy[3]; break;
+                case 3: K4[0] = dy[0]; K4[1] = dy[1]; K4[2] = dy[2]; K4[3] = dy[3]; break;
+                case 4: K5[0] = dy[0]; K5[1] = dy[1]; K5[2] = dy[2]; K5[3] = dy[3]; break;
+                default: K6[0] = dy[0]; K6[1] = dy[1]; K6[2] = dy[2]; K6[3] = dy[3]; break;
+                }
+            } else if (mode == M_INIT0) {
+                /* ventilation pre-check (coupled_fast.py:238-244); the evaluation at (0, y0) is
+                 * also f0 of the integration, so it is only counted when the storm is integrated */
+                bool vent = false;
+                if (aux.vpot > 0.0) {
+                    double vent_index = aux.S_free * aux.chi / aux.vpot;
+                    if (vent_index >= 1.0) vent = true;
+                }
+                if (vent) {
+                    finalize(TCR_STATUS_VENT);
+                } else {
+                    /* select_initial_step, first half (scipy/integrate/_ivp/common.py) */
+                    double sa[4], sb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        K0[i] = dy[i];
+                        double scale = atol + fabs(y[i]) * rtol;
+                        sa[i] = y[i] / scale; sb[i] = dy[i] / scale;
+                    }
+                    double d0 = tcr_rms4(sa);
+                    d1 = tcr_rms4(sb);
+                    if (d0 < 1e-5 || d1 < 1e-5) h0 = 1e-6; else h0 = 0.01 * d0 / d1;
+                    if (t_bound < h0) h0 = t_bound;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) yn[i] = fma(h0, K0[i], y[i]);
+                    mode = M_INIT1;
+                }
+            } else if (mode == M_INIT1) {
+                double sc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double scale = atol + fabs(y[i]) * rtol;
+                    sc[i] = (dy[i] - K0[i]) / scale;
+                }
+                double d2 = tcr_rms4(sc) / h0, h1;
+                if (d1 <= 1e-15 && d2 <= 1e-15) { h1 = h0 * 1e-3; if (h1 < 1e-6) h1 = 1e-6; }
+                else h1 = tcr_pow(0.01 / (d2 > d1 ? d2 : d1), 0.2);
+                double hh = 100.0 * h0;
+                if (h1 < hh) hh = h1;
+                if (t_bound < hh) hh = t_bound;
+                if (max_step < hh) hh = max_step;
+                h_abs = hh;
+                g = tcr_event(p, y);
+                mode = M_WAIT;
+            }
+        }
+
+        /* ---- end of the RK attempt: error control, events, dense output ---- */
+        if (mode == M_RK) {
+            double en[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double ay = fabs(y[i]), an = fabs(yn[i]);
+                double mx = (tcr_isnan(ay) || tcr_isnan(an)) ? NAN : (ay > an ? ay : an);
+                double scale = atol + mx * rtol;
+                double e = fma(K6[i], RK_E6, fma(K5[i], RK_E5, fma(K4[i], RK_E4, fma(K3[i], RK_E3, fma(K2[i], RK_E2, K0[i] * RK_E0)))));
+                en[i] = (e * h) / scale;
+            }
+            const double err = tcr_rms4(en);
+            if (err < 1.0) {
+                double factor;
+                if (err == 0.0) factor = 10.0;
+                else { factor = 0.9 * tcr_pow(err, -0.2); if (10.0 < factor) factor = 10.0; }
+                if (rejected && 1.0 < factor) factor = 1.0;
+                h_abs *= factor;
+                /* accepted */
+                const double t_old = t;
+                if (t_new - t_bound >= 0.0) status = TCR_STATUS_FINISHED;
+                const double g_new = tcr_event(p, yn);
+                const bool active = ((g <= 0.0) && (g_new >= 0.0)) || ((g >= 0.0) && (g_new <= 0.0));
+                double t_emit = t_new;
+                if (active) { status = TCR_STATUS_EVENT; if (g == 0.0) t_emit = t_old; }
+                g = g_new;
+                /* t_eval sampling through the dense output */
+                const int i_new = tcr_nodes_le(cx, t_emit, n_out);
+                if (i_new > n_out) {
+                    double Q1[4], Q2[4], Q3[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        Q1[i] = fma(K6[i], RK_P61, fma(K5[i], RK_P51, fma(K4[i], RK_P41, fma(K3[i], RK_P31, fma(K2[i], RK_P21, K0[i] * RK_P01)))));
+                        Q2[i] = fma(K6[i], RK_P62, fma(K5[i], RK_P52, fma(K4[i], RK_P42, fma(K3[i], RK_P32, fma(K2[i], RK_P22, K0[i] * RK_P02)))));
+                        Q3[i] = fma(K6[i], RK_P63, fma(K5[i], RK_P53, fma(K4[i], RK_P43, fma(K3[i], RK_P33, fma(K2[i], RK_P23, K0[i] * RK_P03)))));
+                    }
+                    const double hd = t_new - t_old;
+                    for (int k = n_out; k < i_new; ++k) {
+                        double x = (tcr_node_time(cx, k) - t_old) / hd;
+                        double p2 = x * x, p3 = p2 * x, p4 = p3 * x;
+                        double o[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            double acc = (K0[i] * 1.0) * x;
+                            acc = fma(Q1[i], p2, acc);
+                            acc = fma(Q2[i], p3, acc);
+                            acc = fma(Q3[i], p4, acc);
+                            o[i] = fma(hd, acc, y[i]);
+                        }
+                        double2* dst = reinterpret_cast<double2*>(trk + (size_t)k * 4);
+                        dst[0] = make_double2(o[0], o[1]);
+                        dst[1] = make_double2(o[2], o[3]);
+                        if (o[2] >= p.seed_v_thresh) any_v = true;
+                    }
+                    n_out = i_new;
+                }
+                t = t_new;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { y[i] = yn[i]; K0[i] = K6[i]; }
+                new_step = true;
+                if (status != 100) finalize(status);
+            } else {
+                double fac = 0.9 * tcr_pow(err, -0.2);
+                if (!(fac > 0.2)) fac = 0.2;
+                h_abs *= fac;
+                rejected = true;
+            }
+        }
+    }
+}
+
+/* ======================================================================================== */
+/* post-processing of a candidate: env-wind recompute (util/compute.py:201-202), translation  */
+/* speed (util/sphere.py:58-83), axi_to_max_wind (wind/tc_wind.py:6-21), nanmax(vmax) >= 18   */
+/* (util/compute.py:205).  One CTA per storm; lanes stride over the output samples.           */
+/* ======================================================================================== */
+struct PostArgs {
+    int64_t n;                          /* storms if list == NULL */
+    const int32_t* list; const unsigned int* list_count;
+    const int32_t* ym; const double2* coef; const double* track;
+    const int32_t* n_time; const int32_t* status;
+    double* env;                        /* [n][n_steps][4] */
+    double* vmax;                       /* [n][n_steps]    */
+    uint32_t* flags;
+};
+
+__global__ void __launch_bounds__(128) k_postprocess(const __grid_constant__ TcrCtx cx, const PostArgs A)
+{
+    __shared__ double2 cfs[TCR_N_PHASES];
+    __shared__ unsigned long long best_bits;
+    __shared__ int have;
+    const tcr_params& p = cx.p;
+    const int ns = p.n_steps;
+    const int64_t count = A.list ? (int64_t)*A.list_count : A.n;
+    for (int64_t item = blockIdx.x; item < count; item += gridDim.x) {
+        const int64_t sid = A.list ? (int64_t)A.list[item] : item;
+        const int nt = A.n_time[sid];
+        if (nt <= 0 || A.status[sid] == TCR_STATUS_VENT) continue;
+        __syncthreads();
+        if (threadIdx.x < TCR_N_PHASES) cfs[threadIdx.x] = A.coef[(size_t)sid * TCR_N_PHASES + threadIdx.x];
+        if (threadIdx.x == 0) { best_bits = 0ull; have = 0; }
+        __syncthreads();
+        const int ym = A.ym[sid];
+        const double* trk = A.track + (size_t)sid * ns * 4;
+        double* env = A.env + (size_t)sid * ns * 4;
+        double* vmx = A.vmax + (size_t)sid * ns;
+        for (int k = threadIdx.x; k < nt; k += blockDim.x) {
+            const double2 a = *reinterpret_cast<const double2*>(trk + (size_t)k * 4);
+            const double lon = a.x, lat = a.y;
+            const double v = trk[(size_t)k * 4 + 2];
+            const double tk = tcr_node_time(cx, k);
+            double w[4] = {0.0, 0.0, 0.0, 0.0};
+            if (!(tcr_isnan(lon) || tcr_isnan(tk))) {
+                TcrCell c;
+                tcr_cell_at(cx.tab.lon, cx.tab.lat, lon, lat, c);
+                tcr_env_winds_cell(cx, tcr_record(cx.tab, ym, c), c, cfs, 1, tk, w);
+            }
+            double2* ed = reinterpret_cast<double2*>(env + (size_t)k * 4);
+            ed[0] = make_double2(w[0], w[1]);
+            ed[1] = make_double2(w[2], w[3]);
+            double ut, vt;
+            if (nt <= 1) {
+                ut = vt = NAN;
+            } else {
+                double lon_m, lat_m, lon_p, lat_p;
+                if (k == 0) {
+                    const double2 b = *reinterpret_cast<const double2*>(trk + 4);
+                    lon_m = 2 * lon - b.x; lat_m = 2 * lat - b.y;
+                } else {
+                    const double2 b = *reinterpret_cast<const double2*>(trk + (size_t)(k - 1) * 4);
+                    lon_m = b.x; lat_m = b.y;
+                }
+                if (k == nt - 1) {
+                    const double2 b = *reinterpret_cast<const double2*>(trk + (size_t)(nt - 2) * 4);
+                    lon_p = 2 * lon - b.x; lat_p = 2 * lat - b.y;
+                } else {
+                    const double2 b = *reinterpret_cast<const double2*>(trk + (size_t)(k + 1) * 4);
+                    lon_p = b.x; lat_p = b.y;
+                }
+                double dlon = 0.5 * (tcr_sign(lon_p - lon_m) * tcr_haversine_km(p, lon_p, lat, lon_m, lat));
+                double dlat = 0.5 * (tcr_sign(lat_p - lat_m) * tcr_haversine_km(p, lon, lat_p, lon, lat_m));
+                ut = dlon * 1000.0 / p.dt_track;
+                vt = dlat * 1000.0 / p.dt_track;
+            }
+            double G = 0.8 + 0.35 * (1.0 + tcr_tanh((lat - 35.0) / 10.0));
+            if (1.0 < G) G = 1.0;
+            double u_shr = w[0] - w[2], v_shr = w[1] - w[3];
+            double U = G * ut + 0.1 * u_shr * v / 15.0;
+            double V = G * vt + 0.1 * v_shr * v / 15.0;
+            double mag_inc = sqrt(U * U + V * V);
+            double vm;
+            if (mag_inc == 0.0) {
+                vm = fabs(v);
+            } else {
+                double mag_fac = (v * 0.50) / mag_inc;
+                if (!tcr_isnan(mag_fac) && 1.0 < mag_fac) mag_fac = 1.0;
+                double ug = v * (U / mag_inc) + U * mag_fac;
+                double vg = v * (V / mag_inc) + V * mag_fac;
+                vm = sqrt(ug * ug + vg * vg);
+            }
+            vmx[k] = vm;
+            if (!tcr_isnan(vm)) {
+                /* vm >= 0: the bit pattern orders like the value */
+                atomicMax(&best_bits, (unsigned long long)tcr_d2bits(fabs(vm)));
+                have = 1;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t fl = A.flags[sid];
+            if ((fl & TCR_FLAG_IS_TC) && have && tcr_bits2d((int64_t)best_bits) >= p.seed_vmax_thresh) fl |= TCR_FLAG_KEPT;
+            A.flags[sid] = fl;
+        }
+    }
+}
+
+/* ======================================================================================== */
+/* seeding: one thread per attempt = one pass of `while not seed_passed` (compute.py:136-175) */
+/* Draw slots (stream 0): block 0 = (lon, lat), 1 = (month, low-latitude test), 2 = Box-      */
+/* Muller pair for v_init, 3.. = ocean-point redraws.                                         */
+/* ======================================================================================== */
+struct SeedArgs {
+    int n_years;
+    const int64_t* wave_off;            /* [n_years+1] prefix offsets of the years' attempt ranges */
+    const int64_t* k0;                  /* [n_years] first attempt index of each year's range      */
+    const int32_t* ym_base; const int32_t* year_key;
+    uint32_t run_seed;
+    /* per attempt (flat) */
+    int32_t* code; int32_t* basin; int32_t* month;
+    double* lon; double* lat; double* v0; double* m0; double* pi_gen;      /* may be NULL */
+    int32_t* att_slot;                  /* slot of an integrated attempt, -1 otherwise (may be NULL) */
+    /* per slot (compaction of code == 2 attempts; may be NULL) */
+    unsigned int* n_slots;
+    int32_t* s_ym; double* s_lon; double* s_lat; double* s_v0; double* s_m0; double* s_hbl;
+    int64_t* s_att; int32_t* s_key;
+};
+
+__device__ __forceinline__ double tcr_mask_at(const uint2 r[4], int b, const TcrCell& c)
+{
+    auto byte = [&](const uint2& q) { return (double)(((b < 4 ? q.x : q.y) >> (8 * (b & 3))) & 0xffu); };
+    return tcr_bilin_fitpack(byte(r[0]), byte(r[1]), byte(r[2]), byte(r[3]), c);
+}
+
+__device__ __forceinline__ void tcr_mask_cell(const TcrMasks& mk, double lon, double lat, TcrCell& c, uint2 r[4])
+{
+    tcr_cell_at(mk.lon, mk.lat, lon, lat, c);
+    const uint4* q = reinterpret_cast<const uint4*>(mk.rec + ((size_t)c.iy * mk.ncx + c.ix) * 4);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    r[0] = make_uint2(a.x, a.y); r[1] = make_uint2(a.z, a.w);
+    r[2] = make_uint2(b.x, b.y); r[3] = make_uint2(b.z, b.w);
+}
+
+__global__ void __launch_bounds__(256) k_seed(const __grid_constant__ TcrCtx cx, const SeedArgs A)
+{
+    const tcr_params& p = cx.p;
+    const int64_t total = A.wave_off[A.n_years];
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int code = -1;
+    int bi = 0, mon = 1, yr = 0;
+    int64_t k = 0;
+    double gen_lon = 0, gen_lat = 0, v0 = 0, m0 = 0, pi = 0;
+    if (idx < total) {
+        while (yr + 1 < A.n_years && idx >= A.wave_off[yr + 1]) ++yr;
+        k = A.k0[yr] + (idx - A.wave_off[yr]);
+        const int32_t key = A.year_key[yr];
+        const double* b = p.basin_bounds;
+        double u[2];
+        tcr_draw2(A.run_seed, key, k, 0, 0, u);
+        const double y_min = tcr_sin(TCR_DEG2RAD * p.gen_lat_min), y_max = tcr_sin(TCR_DEG2RAD * p.gen_lat_max);
+        gen_lon = b[0] + (b[2] - b[0]) * u[0];
+        gen_lat = tcr_asin(y_min + (y_max - y_min) * u[1]) * 180.0 / TCR_PI;
+        int redraw = 0;
+        bool exhausted = false;
+        TcrCell c;
+        uint2 r[4];
+        for (;;) {
+            tcr_mask_cell(cx.mk, gen_lon, gen_lat, c, r);
+            if (!(tcr_mask_at(r, 7, c) < 1e-2)) break;
+            if (redraw >= p.max_redraws) { exhausted = true; break; }
+            tcr_draw2(A.run_seed, key, k, 3u + (uint32_t)redraw, 0, u);
+            gen_lon = b[0] + (b[2] - b[0]) * u[0];
+            gen_lat = b[1] + (b[3] - b[1]) * u[1];
+            ++redraw;
+        }
+        tcr_draw2(A.run_seed, key, k, 1, 0, u);
+        mon = 1 + (int)floor(u[0] * 12.0);
+        const double r_lowlat = u[1];
+        double best = -INFINITY;
+        for (int i = 0; i < TCR_N_BASINS; ++i) {
+            double val = tcr_mask_at(r, i, c);
+            if (val > best) { best = val; bi = i; }
+        }
+        TcrCell ce;
+        tcr_cell_at(cx.tab.lon, cx.tab.lat, gen_lon, gen_lat, ce);
+        const float4* rec = tcr_record(cx.tab, A.ym_base[yr] + mon - 1, ce);
+        pi = tcr_bilin(__ldg(rec + CH_VPOT), ce);
+        double q = (fabs(gen_lat) - p.lat_vort_fac) / 12.0;
+        if (q < 0.0) q = 0.0;
+        if (q > 1.0) q = 1.0;
+        const double prob = tcr_pow(q, p.lat_vort_power[bi]);
+        tcr_draw2(A.run_seed, key, k, 2, 0, u);
+        double bs, bc;
+        tcr_sincos2pi(u[1], &bs, &bc);
+        const double randn = sqrt(-2.0 * tcr_log(1.0 - u[0])) * bc;
+        v0 = p.seed_v_init + randn;
+        const double rh = tcr_bilin(__ldg(rec + CH_RH), ce);
+        const double mi = p.minit_amp / (1.0 + tcr_exp(-(rh - p.minit_center) * p.minit_slope)) + p.minit_offset;
+        m0 = mi > 0.0 ? mi : 0.0;
+        if (exhausted) code = 3;
+        else if (best > 1e-3 && r_lowlat < prob) code = pi > p.pi_gen_min ? 2 : 1;
+        else code = 0;
+        A.code[idx] = code; A.basin[idx] = bi; A.month[idx] = mon;
+        if (A.lon) { A.lon[idx] = gen_lon; A.lat[idx] = gen_lat; A.v0[idx] = v0; A.m0[idx] = m0; A.pi_gen[idx] = pi; }
+    }
+    if (A.n_slots) {
+        /* warp-aggregated compaction of the attempts that go on to gen_track */
+        const unsigned pass = __ballot_sync(TCR_FULL, code == 2);
+        if (pass) {
+            const int lane = threadIdx.x & 31, leader = __ffs(pass) - 1;
+            unsigned int base = 0;
+            if (lane == leader) base = atomicAdd(A.n_slots, (unsigned int)__popc(pass));
+            base = __shfl_sync(TCR_FULL, base, leader);
+            if (code == 2) {
+                const unsigned int s = base + __popc(pass & ((1u << lane) - 1u));
+                A.s_ym[s] = A.ym_base[yr] + mon - 1;
+                A.s_lon[s] = gen_lon; A.s_lat[s] = gen_lat; A.s_v0[s] = v0; A.s_m0[s] = m0;
+                A.s_hbl[s] = p.atm_bl_depth[bi];
+                A.s_att[s] = k; A.s_key[s] = A.year_key[yr];
+                A.att_slot[idx] = (int32_t)s;
+            }
+        }
+        if (idx < total && code != 2) A.att_slot[idx] = -1;
+    }
+}
+
+/* ======================================================================================== */
+/* ordered selection: the sequential `while nt < n_tracks` semantics of compute.py:134-209    */
+/* over the indexed attempt stream.  One CTA per year.                  */
+/* ======================================================================================== */
+struct SelectArgs {
+    int n_tracks;
+    const int64_t* wave_off; const int64_t* k0;
+    const int32_t* code; const int32_t* basin; const int32_t* month; const int32_t* att_slot;
+    const int32_t* n_time; const int32_t* nfev; const uint32_t* flags;
+    int32_t* nt;                /* [n_years] kept so far (in/out)                              */
+    int32_t* row_slot;          /* [n_years][n_tracks] slot of a row assigned in THIS wave, else -1 */
+    double* tc_month; int32_t* tc_basin; double* n_seeds;    /* outputs (device)               */
+    tcr_year_stats* stats;      /* [n_years] device accumulators                               */
+};
+
+__global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int s_running, s_istar;
+    __shared__ unsigned long long s_acc[6];
+    __shared__ unsigned int s_hist[TCR_N_BASINS * 12];
+    const int yr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t off = A.wave_off[yr];
+    const int64_t W = A.wave_off[yr + 1] - off;
+    for (int r = tid; r < A.n_tracks; r += blockDim.x) A.row_slot[(size_t)yr * A.n_tracks + r] = -1;
+    if (W == 0) return;
+    const int nt0 = A.nt[yr];
+    const int want = A.n_tracks - nt0;
+    if (tid == 0) { s_running = 0; s_istar = -1; }
+    if (tid < 6) s_acc[tid] = 0ull;
+    for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    /* pass 1: rank the kept storms in attempt order, find i* = attempt of the want-th kept */
+    for (int64_t base = 0; base < W; base += blockDim.x) {
+        const int64_t i = base + tid;
+        int kept = 0, slot = -1;
+        if (i < W) {
+            slot = A.att_slot[off + i];
+            if (slot >= 0 && (A.flags[slot] & TCR_FLAG_KEPT)) kept = 1;
+        }
+        int incl = kept;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(TCR_FULL, incl, d); if (lane >= d) incl += v; }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int v = warp_tot[lane], s = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(TCR_FULL, s, d); if (lane >= d) s += u; }
+            warp_tot[lane] = s - v;
+        }
+        __syncthreads();
+        const int run0 = s_running;
+        const int rank = run0 + warp_tot[wid] + incl;             /* 1-based rank of this kept storm */
+        if (kept && rank <= want) {
+            const int row = nt0 + rank - 1;
+            A.row_slot[(size_t)yr * A.n_tracks + row] = slot;
+            A.tc_month[(size_t)yr * A.n_tracks + row] = (double)A.month[off + i];
+            A.tc_basin[(size_t)yr * A.n_tracks + row] = A.basin[off + i];
+            atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot]);
+            if (rank == want) s_istar = (int)i;
+        }
+        __syncthreads();
+        if (tid == blockDim.x - 1) s_running = rank;
+        __syncthreads();
+        if (s_istar >= 0) break;
+    }
+    const int64_t i_star = s_istar;
+    const int64_t last = i_star >= 0 ? i_star : W - 1;      /* attempts consumed: 0..last */
+    /* pass 2: counters over the consumed attempts */
+    unsigned long long counted = 0, integ = 0, steps = 0, rhs = 0, w_integ = 0, w_steps = 0;
+    for (int64_t i = tid; i < W; i += blockDim.x) {
+        const int code = A.code[off + i];
+        const int slot = A.att_slot[off + i];
+        if (i <= last) {
+            if (code == 1 || code == 2) { ++counted; atomicAdd(&s_hist[A.basin[off + i] * 12 + A.month[off + i] - 1], 1u); }
+            if (slot >= 0) { ++integ; steps += (unsigned long long)A.n_time[slot]; rhs += (unsigned long long)A.nfev[slot]; }
+        } else if (slot >= 0) { ++w_integ; w_steps += (unsigned long long)A.n_time[slot]; }
+    }
+    atomicAdd(&s_acc[0], counted); atomicAdd(&s_acc[1], integ); atomicAdd(&s_acc[2], steps);
+    atomicAdd(&s_acc[3], rhs); atomicAdd(&s_acc[5], (w_integ << 40) | w_steps);
+    __syncthreads();
+    for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x)
+        A.n_seeds[(size_t)yr * TCR_N_BASINS * 12 + i] += (double)s_hist[i];
+    if (tid == 0) {
+        tcr_year_stats& s = A.stats[yr];
+        const int got = min(want, s_running);
+        s.attempts = A.k0[yr] + last + 1;
+        s.counted_seeds += (int64_t)s_acc[0];
+        s.integrated += (int64_t)s_acc[1];
+        s.storm_steps += (int64_t)s_acc[2];
+        s.rhs_evals += (int64_t)s_acc[3];
+        s.kept_steps += (int64_t)s_acc[4];
+        s.wasted_integrated += (int64_t)(s_acc[5] >> 40);
+        s.wasted_steps += (int64_t)(s_acc[5] & ((1ull << 40) - 1));
+        s.n_kept = nt0 + got;
+        s.n_waves += 1;
+        A.nt[yr] = nt0 + got;
+    }
+}
+
+/* copy the rows assigned in this wave into the caller's 9-tuple layout (compute.py:126-133,
+ * 193-207), NaN-padded past n_time.  One warp per (year, row).                               */
+struct GatherArgs {
+    int n_years, n_tracks;
+    const int32_t* row_slot; const int32_t* n_time;
+    const double* track; const double* env; const double* vmax;
+    double* o_lon; double* o_lat; double* o_v; double* o_m; double* o_vmax; double* o_env;
+};
+
+__global__ void __launch_bounds__(256) k_gather(const __grid_constant__ TcrCtx cx, const GatherArgs A)
+{
+    const int ns = cx.p.n_steps;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (int64_t)A.n_years * A.n_tracks) return;
+    const int slot = A.row_slot[row];
+    if (slot < 0) return;
+    const int lane = threadIdx.x & 31;
+    const int nt = A.n_time[slot];
+    const double* trk = A.track + (size_t)slot * ns * 4;
+    const double* env = A.env + (size_t)slot * ns * 4;
+    const double* vmx = A.vmax + (size_t)slot * ns;
+    const size_t o = (size_t)row * ns;
+    for (int k = lane; k < ns; k += 32) {
+        double2 a = make_double2(NAN, NAN), b = a, e0 = a, e1 = a;
+        double vm = NAN;
+        if (k < nt) {
+            a = *reinterpret_cast<const double2*>(trk + (size_t)k * 4);
+            b = *reinterpret_cast<const double2*>(trk + (size_t)k * 4 + 2);
+            e0 = *reinterpret_cast<const double2*>(env + (size_t)k * 4);
+            e1 = *reinterpret_cast<const double2*>(env + (size_t)k * 4 + 2);
+            vm = vmx[k];
+        }
+        A.o_lon[o + k] = a.x; A.o_lat[o + k] = a.y; A.o_v[o + k] = b.x; A.o_m[o + k] = b.y;
+        A.o_vmax[o + k] = vm;
+        double2* eo = reinterpret_cast<double2*>(A.o_env + (o + k) * 4);
+        eo[0] = e0; eo[1] = e1;
+    }
+}

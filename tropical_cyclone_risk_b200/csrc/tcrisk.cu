@@ -1,0 +1,741 @@
+/*
+ * tcrisk.cu -- C ABI (include/tcrisk.h) of the B200-native tropical-cyclone ensemble integrator:
+ * device-memory management, table upload and the wave scheduler around the kernels of
+ * tcr_kernels.cuh.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (the
+ * arithmetic contract forbids implicit contraction; see include/tcr_libm.h).
+ */
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tcr_kernels.cuh"
+
+#define TCR_VERSION 100
+
+static thread_local std::string g_err;
+
+static int set_err(const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return set_err("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define CKK(h)                                                                                      \
+    do {                                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                                        \
+        if (e_ != cudaSuccess)                                                                      \
+            return set_err("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \
+        (h)->launches++;                                                                            \
+    } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e != cudaSuccess) { p = nullptr; return set_err("cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e)); }
+        bytes = need;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct AxisBuf {
+    DevBuf buf;
+    int n = 0;
+};
+
+/* scratch of tcr_run_years / tcr_integrate, grown on demand and kept in the handle */
+struct Workspace {
+    int64_t cap = 0;        /* slots == attempts per wave */
+    int ns = 0;
+    DevBuf code, basin, month, att_slot;                       /* per attempt */
+    DevBuf s_ym, s_lon, s_lat, s_v0, s_m0, s_hbl, s_att, s_key; /* per slot */
+    DevBuf n_time, status, nfev, flags, cand;
+    DevBuf coef, track, env, vmax;
+    DevBuf counters;       /* [0] queue (u64), [1] n_slots (u32 @+8), [2] cand_count (u32 @+12) */
+    DevBuf year_i64;       /* wave_off [ny+1], k0 [ny] */
+    DevBuf year_i32;       /* ym_base [ny], year_key [ny], nt [ny] */
+    DevBuf row_slot, stats;
+    DevBuf out;            /* device-side result block when the caller passes host pointers */
+    void release_all()
+    {
+        DevBuf* all[] = {&code, &basin, &month, &att_slot, &s_ym, &s_lon, &s_lat, &s_v0, &s_m0, &s_hbl, &s_att, &s_key,
+                         &n_time, &status, &nfev, &flags, &cand, &coef, &track, &env, &vmax, &counters, &year_i64,
+                         &year_i32, &row_slot, &stats, &out};
+        for (DevBuf* b : all) b->release();
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct tcr_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    TcrCtx ctx;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    /* tables */
+    DevBuf rec, stage;
+    AxisBuf ax_lon, ax_lat;
+    int nlat = 0, nlon = 0, n_ym = 0;
+    size_t month_f4 = 0;
+    /* static */
+    DevBuf bathy, land, masks;
+    AxisBuf ax_lon_b, ax_lat_b, ax_lon_l, ax_lat_l, ax_lon_m, ax_lat_m;
+    bool have_static = false, have_masks = false;
+    /* tuning */
+    int ctas_per_sm = 1, threads_per_cta = 224, oversub_permille = 1100, interp_variant = 0;
+    int64_t max_wave = 0;
+    Workspace ws;
+    void* pinned = nullptr;      /* small pinned read-back area */
+};
+
+static int make_axis(tcr_handle* h, const double* host, int n, AxisBuf& ab, TcrAxis& ax)
+{
+    if (n < 2) return set_err("axis needs at least 2 points (got %d)", n);
+    for (int i = 1; i < n; ++i)
+        if (!(host[i] > host[i - 1])) return set_err("axis must be strictly ascending (index %d)", i);
+    DevBuf tmp;
+    if (tmp.ensure(sizeof(double) * n)) return -1;
+    if (ab.buf.ensure(sizeof(double2) * n)) { tmp.release(); return -1; }
+    cudaError_t e = cudaMemcpyAsync(tmp.p, host, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        k_build_axis<<<(n + 255) / 256, 256, 0, h->stream>>>(tmp.as<double>(), ab.buf.as<double2>(), n);
+        e = cudaGetLastError();
+        h->launches++;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    tmp.release();
+    if (e != cudaSuccess) return set_err("axis upload failed: %s", cudaGetErrorString(e));
+    ab.n = n;
+    ax.a = ab.buf.as<double2>();
+    ax.n = n;
+    ax.lo = host[0];
+    ax.hi = host[n - 1];
+    ax.inv_d = (double)(n - 1) / (host[n - 1] - host[0]);
+    return 0;
+}
+
+static int grid_for(size_t total, int block, int num_sms)
+{
+    size_t g = (total + block - 1) / block;
+    size_t cap = (size_t)num_sms * 32;
+    return (int)std::max<size_t>(1, std::min(g, cap));
+}
+
+extern "C" {
+
+const char* tcr_last_error(void) { return g_err.c_str(); }
+int tcr_version(void) { return TCR_VERSION; }
+
+int tcr_create(int device, const tcr_params* p, tcr_handle** out)
+{
+    if (!p || !out) return set_err("tcr_create: null argument");
+    if (p->n_steps < 2) return set_err("tcr_create: n_steps must be >= 2");
+    int n_dev = 0;
+    CK(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return set_err("tcr_create: device %d not present (%d devices)", device, n_dev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return set_err("tcr_create: this library is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+    tcr_handle* h = new tcr_handle();
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    memset(&h->ctx, 0, sizeof h->ctx);
+    h->ctx.p = *p;
+    h->ctx.t_step = p->total_time / (double)(p->n_steps - 1);
+    if (cudaMallocHost(&h->pinned, 1 << 16) != cudaSuccess) { delete h; return set_err("cudaMallocHost failed"); }
+    *out = h;
+    return 0;
+}
+
+int tcr_destroy(tcr_handle* h)
+{
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->ws.release_all();
+    DevBuf* bufs[] = {&h->rec, &h->stage, &h->bathy, &h->land, &h->masks};
+    for (DevBuf* b : bufs) b->release();
+    AxisBuf* axs[] = {&h->ax_lon, &h->ax_lat, &h->ax_lon_b, &h->ax_lat_b, &h->ax_lon_l, &h->ax_lat_l, &h->ax_lon_m, &h->ax_lat_m};
+    for (AxisBuf* a : axs) a->buf.release();
+    if (h->pinned) cudaFreeHost(h->pinned);
+    delete h;
+    return 0;
+}
+
+int tcr_set_stream(tcr_handle* h, void* cuda_stream)
+{
+    if (!h) return set_err("null handle");
+    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return 0;
+}
+
+int tcr_synchronize(tcr_handle* h)
+{
+    if (!h) return set_err("null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int tcr_set_tuning(tcr_handle* h, int ctas_per_sm, int threads_per_cta, int64_t max_wave_cands, int oversub_permille)
+{
+    if (!h) return set_err("null handle");
+    if (ctas_per_sm > 0) h->ctas_per_sm = ctas_per_sm;
+    if (threads_per_cta > 0) {
+        if (threads_per_cta % 32 || threads_per_cta > 256) return set_err("threads_per_cta must be a multiple of 32, <= 256");
+        h->threads_per_cta = threads_per_cta;
+    }
+    if (max_wave_cands > 0) h->max_wave = max_wave_cands;
+    if (oversub_permille > 0) h->oversub_permille = oversub_permille;
+    return 0;
+}
+
+int tcr_set_interp_variant(tcr_handle* h, int variant)
+{
+    if (!h) return set_err("null handle");
+    if (variant < 0 || variant > 1) return set_err("interp variant must be 0 (LDG) or 1 (TMA bulk)");
+    h->interp_variant = variant;
+    return 0;
+}
+
+int64_t tcr_launch_count(tcr_handle* h) { return h ? h->launches : 0; }
+
+int tcr_host_alloc(size_t bytes, void** out)
+{
+    if (!out) return set_err("null argument");
+    CK(cudaMallocHost(out, bytes));
+    return 0;
+}
+
+int tcr_host_free(void* p)
+{
+    if (p) CK(cudaFreeHost(p));
+    return 0;
+}
+
+/* ---- static fields ------------------------------------------------------------------------- */
+int tcr_upload_static(tcr_handle* h, int nlat_b, int nlon_b, const double* lat_b, const double* lon_b, const int16_t* bathy,
+                      int nlat_l, int nlon_l, const double* lat_l, const double* lon_l, const int8_t* land)
+{
+    if (!h || !lat_b || !lon_b || !bathy || !lat_l || !lon_l || !land) return set_err("tcr_upload_static: null argument");
+    CK(cudaSetDevice(h->device));
+    TcrStatic& st = h->ctx.st;
+    if (make_axis(h, lon_b, nlon_b, h->ax_lon_b, st.lon_b) || make_axis(h, lat_b, nlat_b, h->ax_lat_b, st.lat_b) ||
+        make_axis(h, lon_l, nlon_l, h->ax_lon_l, st.lon_l) || make_axis(h, lat_l, nlat_l, h->ax_lat_l, st.lat_l))
+        return -1;
+    DevBuf tmp;
+    {
+        size_t n = (size_t)nlat_b * nlon_b, nc = (size_t)(nlat_b - 1) * (nlon_b - 1);
+        if (tmp.ensure(n * sizeof(int16_t)) || h->bathy.ensure(nc * sizeof(short4))) { tmp.release(); return -1; }
+        CK(cudaMemcpyAsync(tmp.p, bathy, n * sizeof(int16_t), cudaMemcpyHostToDevice, h->stream));
+        k_build_bathy<<<grid_for(nc, 256, h->num_sms), 256, 0, h->stream>>>(tmp.as<int16_t>(), h->bathy.as<short4>(), nlat_b, nlon_b);
+        CKK(h);
+        CK(cudaStreamSynchronize(h->stream));
+        st.bathy = h->bathy.as<short4>();
+        st.ncx_b = nlon_b - 1;
+    }
+    {
+        size_t n = (size_t)nlat_l * nlon_l, nc = (size_t)(nlat_l - 1) * (nlon_l - 1);
+        if (tmp.ensure(n) || h->land.ensure(nc * sizeof(char4))) { tmp.release(); return -1; }
+        CK(cudaMemcpyAsync(tmp.p, land, n, cudaMemcpyHostToDevice, h->stream));
+        k_build_land<<<grid_for(nc, 256, h->num_sms), 256, 0, h->stream>>>(tmp.as<int8_t>(), h->land.as<char4>(), nlat_l, nlon_l);
+        CKK(h);
+        CK(cudaStreamSynchronize(h->stream));
+        st.land = h->land.as<char4>();
+        st.ncx_l = nlon_l - 1;
+    }
+    tmp.release();
+    h->have_static = true;
+    return 0;
+}
+
+int tcr_upload_masks(tcr_handle* h, int nlat_m, int nlon_m, const double* lat_m, const double* lon_m, const uint8_t* masks)
+{
+    if (!h || !lat_m || !lon_m || !masks) return set_err("tcr_upload_masks: null argument");
+    CK(cudaSetDevice(h->device));
+    TcrMasks& mk = h->ctx.mk;
+    if (make_axis(h, lon_m, nlon_m, h->ax_lon_m, mk.lon) || make_axis(h, lat_m, nlat_m, h->ax_lat_m, mk.lat)) return -1;
+    DevBuf tmp;
+    size_t n = (size_t)TCR_N_MASKS * nlat_m * nlon_m, nc = (size_t)(nlat_m - 1) * (nlon_m - 1) * 4;
+    if (tmp.ensure(n) || h->masks.ensure(nc * sizeof(uint2))) { tmp.release(); return -1; }
+    CK(cudaMemcpyAsync(tmp.p, masks, n, cudaMemcpyHostToDevice, h->stream));
+    k_build_masks<<<grid_for(nc, 256, h->num_sms), 256, 0, h->stream>>>(tmp.as<uint8_t>(), h->masks.as<uint2>(), nlat_m, nlon_m);
+    CKK(h);
+    CK(cudaStreamSynchronize(h->stream));
+    tmp.release();
+    mk.rec = h->masks.as<uint2>();
+    mk.ncx = nlon_m - 1;
+    h->have_masks = true;
+    return 0;
+}
+
+/* ---- monthly tables ------------------------------------------------------------------------ */
+int tcr_alloc_tables(tcr_handle* h, int n_ym, int nlat, int nlon, const double* lat, const double* lon)
+{
+    if (!h || !lat || !lon) return set_err("tcr_alloc_tables: null argument");
+    if (n_ym < 1 || nlat < 2 || nlon < 2) return set_err("tcr_alloc_tables: bad shape");
+    CK(cudaSetDevice(h->device));
+    TcrTables& tb = h->ctx.tab;
+    if (make_axis(h, lon, nlon, h->ax_lon, tb.lon) || make_axis(h, lat, nlat, h->ax_lat, tb.lat)) return -1;
+    h->month_f4 = (size_t)(nlat - 1) * (nlon - 1) * TCR_REC_F4;
+    if (h->rec.ensure(h->month_f4 * sizeof(float4) * (size_t)n_ym)) return -1;
+    if (h->stage.ensure((size_t)TCR_N_FIELDS * nlat * nlon * sizeof(float))) return -1;
+    h->nlat = nlat; h->nlon = nlon; h->n_ym = n_ym;
+    tb.rec = h->rec.as<float4>();
+    tb.ncx = nlon - 1; tb.ncy = nlat - 1; tb.n_ym = n_ym;
+    return 0;
+}
+
+int tcr_upload_month_dev(tcr_handle* h, int ym, const float* d_planes)
+{
+    if (!h || !d_planes) return set_err("tcr_upload_month_dev: null argument");
+    if (!h->rec.p) return set_err("tcr_upload_month: call tcr_alloc_tables first");
+    if (ym < 0 || ym >= h->n_ym) return set_err("tcr_upload_month: ym %d out of range [0, %d)", ym, h->n_ym);
+    CK(cudaSetDevice(h->device));
+    k_build_month<<<grid_for(h->month_f4, 256, h->num_sms), 256, 0, h->stream>>>(
+        d_planes, h->rec.as<float4>() + h->month_f4 * (size_t)ym, h->nlat, h->nlon);
+    CKK(h);
+    return 0;
+}
+
+int tcr_upload_month(tcr_handle* h, int ym, const float* const* fields)
+{
+    if (!h || !fields) return set_err("tcr_upload_month: null argument");
+    if (!h->rec.p) return set_err("tcr_upload_month: call tcr_alloc_tables first");
+    CK(cudaSetDevice(h->device));
+    const size_t plane = (size_t)h->nlat * h->nlon;
+    bool contiguous = true;
+    for (int i = 0; i < TCR_N_FIELDS; ++i) {
+        if (!fields[i]) return set_err("tcr_upload_month: field %d is null", i);
+        if (i && fields[i] != fields[i - 1] + plane) contiguous = false;
+    }
+    float* st = h->stage.as<float>();
+    if (contiguous) {
+        CK(cudaMemcpyAsync(st, fields[0], plane * TCR_N_FIELDS * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    } else {
+        for (int i = 0; i < TCR_N_FIELDS; ++i)
+            CK(cudaMemcpyAsync(st + plane * i, fields[i], plane * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    }
+    return tcr_upload_month_dev(h, ym, st);
+}
+
+/* ---- stand-alone bilinear sampler ------------------------------------------------------------ */
+static int launch_env_interp(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon, const double* lat, double* out)
+{
+    if (h->interp_variant == 1) {
+        const size_t smem = (size_t)EIT_STAGES * EIT_TILE * (TCR_REC_F4 * 16 + sizeof(EitLoc)) + EIT_STAGES * sizeof(uint64_t);
+        CK(cudaFuncSetAttribute(k_env_interp_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int64_t tiles = (n + EIT_TILE - 1) / EIT_TILE;
+        int grid = (int)std::min<int64_t>(tiles, h->num_sms);
+        k_env_interp_tma<<<grid, EIT_TILE * 2, smem, h->stream>>>(h->ctx, n, ym, lon, lat, out);
+    } else {
+        int64_t tiles = (n + EI_TILE - 1) / EI_TILE;
+        k_env_interp<<<(unsigned)tiles, EI_TILE, 0, h->stream>>>(h->ctx, n, ym, lon, lat, out);
+    }
+    CKK(h);
+    return 0;
+}
+
+int tcr_env_interp(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon, const double* lat, double* out, int on_device)
+{
+    if (!h) return set_err("null handle");
+    if (n < 0) return set_err("tcr_env_interp: negative n");
+    if (n == 0) return 0;
+    if (!ym || !lon || !lat || !out) return set_err("tcr_env_interp: null argument");
+    if (!h->rec.p || !h->have_static) return set_err("tcr_env_interp: tables / static fields not uploaded");
+    if (n > (int64_t)2147483647 * EI_TILE) return set_err("tcr_env_interp: n too large");
+    CK(cudaSetDevice(h->device));
+    if (on_device) return launch_env_interp(h, n, ym, lon, lat, out);
+    DevBuf in, o;
+    if (in.ensure((size_t)n * 20) || o.ensure((size_t)n * TCR_N_INTERP_OUT * sizeof(double))) { in.release(); o.release(); return -1; }
+    double* d_lon = in.as<double>();
+    double* d_lat = d_lon + n;
+    int32_t* d_ym = reinterpret_cast<int32_t*>(d_lat + n);
+    /* ym is range-checked on the host path; device callers own their indices */
+    for (int64_t i = 0; i < n; ++i)
+        if (ym[i] < 0 || ym[i] >= h->n_ym) { in.release(); o.release(); return set_err("tcr_env_interp: ym[%lld]=%d out of range", (long long)i, ym[i]); }
+    int rc = 0;
+    cudaError_t e = cudaMemcpyAsync(d_lon, lon, n * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_lat, lat, n * 8, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ym, ym, n * 4, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) rc = launch_env_interp(h, n, d_ym, d_lon, d_lat, o.as<double>());
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(out, o.p, (size_t)n * TCR_N_INTERP_OUT * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(h->stream);
+    in.release(); o.release();
+    if (rc) return rc;
+    if (e != cudaSuccess) return set_err("tcr_env_interp: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+/* ---- workspace ----------------------------------------------------------------------------- */
+static size_t slot_bytes(int ns) { return 960 + (size_t)ns * 72 + 96; }
+
+static int ws_ensure(tcr_handle* h, int64_t cap, int n_years)
+{
+    Workspace& w = h->ws;
+    const int ns = h->ctx.p.n_steps;
+    if (w.ns != ns) { w.release_all(); w.ns = ns; }
+    if (cap > w.cap) {
+        const size_t c = (size_t)cap;
+        if (w.code.ensure(c * 4) || w.basin.ensure(c * 4) || w.month.ensure(c * 4) || w.att_slot.ensure(c * 4) ||
+            w.s_ym.ensure(c * 4) || w.s_lon.ensure(c * 8) || w.s_lat.ensure(c * 8) || w.s_v0.ensure(c * 8) ||
+            w.s_m0.ensure(c * 8) || w.s_hbl.ensure(c * 8) || w.s_att.ensure(c * 8) || w.s_key.ensure(c * 4) ||
+            w.n_time.ensure(c * 4) || w.status.ensure(c * 4) || w.nfev.ensure(c * 4) || w.flags.ensure(c * 4) ||
+            w.cand.ensure(c * 4) || w.coef.ensure(c * TCR_N_PHASES * sizeof(double2)) ||
+            w.track.ensure(c * ns * 32) || w.env.ensure(c * ns * 32) || w.vmax.ensure(c * ns * 8))
+            return -1;
+        w.cap = cap;
+    }
+    if (w.counters.ensure(64)) return -1;
+    const size_t ny = (size_t)std::max(n_years, 1);
+    if (w.year_i64.ensure((2 * ny + 1) * 8) || w.year_i32.ensure(3 * ny * 4) || w.stats.ensure(ny * sizeof(tcr_year_stats))) return -1;
+    return 0;
+}
+
+static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
+{
+    const int bd = h->threads_per_cta;
+    const size_t smem = (size_t)TCR_N_PHASES * bd * sizeof(double2);
+    if (smem > h->smem_optin) return set_err("integrate kernel needs %zu B shared memory, device allows %zu", smem, h->smem_optin);
+    CK(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int warps_per_cta = bd / 32;
+    int64_t max_ctas = (int64_t)h->num_sms * h->ctas_per_sm;
+    int64_t want_ctas = (n_upper + warps_per_cta - 1) / warps_per_cta;       /* one storm per warp at least */
+    int grid = (int)std::max<int64_t>(1, std::min(max_ctas, want_ctas));
+    int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
+    a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
+    k_integrate<<<grid, bd, smem, h->stream>>>(h->ctx, a);
+    CKK(h);
+    return 0;
+}
+
+/* ---- integrate given seeds ------------------------------------------------------------------ */
+int tcr_integrate(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon0, const double* lat0,
+                  const double* v0, const double* m0, const double* h_bl, const double* phases,
+                  double* track, double* env, double* vmax, int32_t* n_time, int32_t* status, int32_t* nfev,
+                  uint32_t* flags, int on_device)
+{
+    if (!h) return set_err("null handle");
+    if (n < 0) return set_err("tcr_integrate: negative n");
+    if (n == 0) return 0;
+    if (!ym || !lon0 || !lat0 || !v0 || !m0 || !h_bl || !phases) return set_err("tcr_integrate: null input");
+    if (!h->rec.p || !h->have_static) return set_err("tcr_integrate: tables / static fields not uploaded");
+    if (n > 0x7fffffff) return set_err("tcr_integrate: n too large");
+    CK(cudaSetDevice(h->device));
+    if (ws_ensure(h, n, 1)) return -1;
+    Workspace& w = h->ws;
+    const int ns = h->ctx.p.n_steps;
+    cudaStream_t s = h->stream;
+    const cudaMemcpyKind in_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (!on_device)
+        for (int64_t i = 0; i < n; ++i)
+            if (ym[i] < 0 || ym[i] >= h->n_ym) return set_err("tcr_integrate: ym[%lld]=%d out of range", (long long)i, ym[i]);
+    DevBuf ph;
+    if (ph.ensure((size_t)n * TCR_N_PHASES * 8)) return -1;
+    CK(cudaMemcpyAsync(w.s_ym.p, ym, n * 4, in_kind, s));
+    CK(cudaMemcpyAsync(w.s_lon.p, lon0, n * 8, in_kind, s));
+    CK(cudaMemcpyAsync(w.s_lat.p, lat0, n * 8, in_kind, s));
+    CK(cudaMemcpyAsync(w.s_v0.p, v0, n * 8, in_kind, s));
+    CK(cudaMemcpyAsync(w.s_m0.p, m0, n * 8, in_kind, s));
+    CK(cudaMemcpyAsync(w.s_hbl.p, h_bl, n * 8, in_kind, s));
+    CK(cudaMemcpyAsync(ph.p, phases, (size_t)n * TCR_N_PHASES * 8, in_kind, s));
+    CK(cudaMemsetAsync(w.counters.p, 0, 64, s));
+    CK(cudaMemsetAsync(w.track.p, 0xff, (size_t)n * ns * 32, s));
+    CK(cudaMemsetAsync(w.env.p, 0xff, (size_t)n * ns * 32, s));
+    CK(cudaMemsetAsync(w.vmax.p, 0xff, (size_t)n * ns * 8, s));
+    {
+        int64_t total = n * TCR_N_PHASES;
+        k_coef_from_phases<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->ctx, n, ph.as<double>(), w.coef.as<double2>());
+        CKK(h);
+    }
+    IntegArgs a;
+    memset(&a, 0, sizeof a);
+    a.n = n; a.n_dev = nullptr;
+    a.ym = w.s_ym.as<int32_t>(); a.lon0 = w.s_lon.as<double>(); a.lat0 = w.s_lat.as<double>();
+    a.v0 = w.s_v0.as<double>(); a.m0 = w.s_m0.as<double>(); a.h_bl = w.s_hbl.as<double>();
+    a.coef = w.coef.as<double2>(); a.track = w.track.as<double>();
+    a.n_time = w.n_time.as<int32_t>(); a.status = w.status.as<int32_t>(); a.nfev = w.nfev.as<int32_t>();
+    a.flags = w.flags.as<uint32_t>();
+    a.queue = w.counters.as<unsigned long long>();
+    a.cand_list = nullptr; a.cand_count = nullptr;
+    if (launch_integrate(h, a, n)) { ph.release(); return -1; }
+    PostArgs pa;
+    memset(&pa, 0, sizeof pa);
+    pa.n = n; pa.list = nullptr; pa.list_count = nullptr;
+    pa.ym = a.ym; pa.coef = a.coef; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
+    pa.env = w.env.as<double>(); pa.vmax = w.vmax.as<double>(); pa.flags = a.flags;
+    k_postprocess<<<(unsigned)std::min<int64_t>(n, (int64_t)h->num_sms * 16), 128, 0, s>>>(h->ctx, pa);
+    CKK(h);
+    const cudaMemcpyKind out_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (track) CK(cudaMemcpyAsync(track, w.track.p, (size_t)n * ns * 32, out_kind, s));
+    if (env) CK(cudaMemcpyAsync(env, w.env.p, (size_t)n * ns * 32, out_kind, s));
+    if (vmax) CK(cudaMemcpyAsync(vmax, w.vmax.p, (size_t)n * ns * 8, out_kind, s));
+    if (n_time) CK(cudaMemcpyAsync(n_time, w.n_time.p, n * 4, out_kind, s));
+    if (status) CK(cudaMemcpyAsync(status, w.status.p, n * 4, out_kind, s));
+    if (nfev) CK(cudaMemcpyAsync(nfev, w.nfev.p, n * 4, out_kind, s));
+    if (flags) CK(cudaMemcpyAsync(flags, w.flags.p, n * 4, out_kind, s));
+    CK(cudaStreamSynchronize(s));
+    ph.release();
+    return 0;
+}
+
+/* ---- seeding only (test hook) ---------------------------------------------------------------- */
+int tcr_seed_attempts(tcr_handle* h, int ym_base, int32_t year_key, uint32_t run_seed, int64_t k0, int64_t n,
+                      int32_t* code, int32_t* basin, int32_t* month, double* lon, double* lat, double* v0, double* m0,
+                      double* pi_gen)
+{
+    if (!h) return set_err("null handle");
+    if (n <= 0) return n < 0 ? set_err("negative n") : 0;
+    if (!code || !basin || !month || !lon || !lat || !v0 || !m0 || !pi_gen) return set_err("tcr_seed_attempts: null output");
+    if (!h->rec.p || !h->have_masks) return set_err("tcr_seed_attempts: tables / masks not uploaded");
+    if (ym_base < 0 || ym_base + 12 > h->n_ym) return set_err("tcr_seed_attempts: ym_base out of range");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    DevBuf ints, dbls, yr;
+    if (ints.ensure((size_t)n * 12) || dbls.ensure((size_t)n * 40) || yr.ensure(64)) { ints.release(); dbls.release(); yr.release(); return -1; }
+    int64_t hy[3] = {0, n, k0};
+    int32_t hk[2] = {ym_base, year_key};
+    CK(cudaMemcpyAsync(yr.p, hy, sizeof hy, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(yr.as<char>() + 32, hk, sizeof hk, cudaMemcpyHostToDevice, s));
+    SeedArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_years = 1;
+    a.wave_off = yr.as<int64_t>(); a.k0 = yr.as<int64_t>() + 2;
+    a.ym_base = reinterpret_cast<int32_t*>(yr.as<char>() + 32); a.year_key = a.ym_base + 1;
+    a.run_seed = run_seed;
+    a.code = ints.as<int32_t>(); a.basin = a.code + n; a.month = a.basin + n;
+    a.lon = dbls.as<double>(); a.lat = a.lon + n; a.v0 = a.lat + n; a.m0 = a.v0 + n; a.pi_gen = a.m0 + n;
+    k_seed<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->ctx, a);
+    CKK(h);
+    CK(cudaMemcpyAsync(code, a.code, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(basin, a.basin, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(month, a.month, n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(lon, a.lon, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(lat, a.lat, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(v0, a.v0, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(m0, a.m0, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(pi_gen, a.pi_gen, n * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    ints.release(); dbls.release(); yr.release();
+    return 0;
+}
+
+/* ---- whole years ----------------------------------------------------------------------------- */
+int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int32_t* year_key, uint32_t run_seed,
+                  int n_tracks, double* lon, double* lat, double* v, double* m, double* vmax, double* env,
+                  double* tc_month, int32_t* tc_basin, double* n_seeds, tcr_year_stats* stats, int on_device)
+{
+    if (!h) return set_err("null handle");
+    if (n_years <= 0 || n_tracks <= 0) return set_err("tcr_run_years: n_years and n_tracks must be positive");
+    if (!ym_base || !year_key || !lon || !lat || !v || !m || !vmax || !env || !tc_month || !tc_basin || !n_seeds)
+        return set_err("tcr_run_years: null argument");
+    if (!h->rec.p || !h->have_static || !h->have_masks) return set_err("tcr_run_years: tables / static fields / masks not uploaded");
+    for (int y = 0; y < n_years; ++y)
+        if (ym_base[y] < 0 || ym_base[y] + 12 > h->n_ym) return set_err("tcr_run_years: ym_base[%d] out of range", y);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const int ns = h->ctx.p.n_steps;
+    const size_t rows = (size_t)n_years * n_tracks;
+
+    /* wave capacity: bounded by a memory budget and by what the job can use */
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const size_t out_bytes = on_device ? 0 : rows * ns * 72 + rows * 12 + (size_t)n_years * 84 * 8;
+    size_t budget = std::min<size_t>((size_t)32 << 30, (free_b + h->ws.track.bytes + h->ws.env.bytes + h->ws.vmax.bytes + h->ws.coef.bytes) / 2);
+    if (budget > out_bytes) budget -= out_bytes;
+    int64_t cap = (int64_t)(budget / slot_bytes(ns));
+    if (h->max_wave > 0) cap = std::min(cap, h->max_wave);
+    cap = std::min<int64_t>(cap, std::max<int64_t>(65536, (int64_t)rows * 256));
+    cap = std::max<int64_t>(cap, 4096);
+    if (h->ws.ns == ns && h->ws.cap >= 4096 && h->ws.cap >= cap / 2) cap = h->ws.cap;      /* reuse, do not re-allocate */
+    if (ws_ensure(h, cap, n_years)) return -1;
+    Workspace& w = h->ws;
+    cap = w.cap;
+    if (w.row_slot.ensure(rows * 4)) return -1;
+
+    /* result block on the device */
+    double *d_lon, *d_lat, *d_v, *d_m, *d_vmax, *d_env, *d_month, *d_seeds;
+    int32_t* d_basin;
+    if (on_device) {
+        d_lon = lon; d_lat = lat; d_v = v; d_m = m; d_vmax = vmax; d_env = env; d_month = tc_month; d_basin = tc_basin; d_seeds = n_seeds;
+    } else {
+        if (w.out.ensure(out_bytes + 256)) return -1;
+        double* base = w.out.as<double>();
+        d_lon = base; d_lat = d_lon + rows * ns; d_v = d_lat + rows * ns; d_m = d_v + rows * ns; d_vmax = d_m + rows * ns;
+        d_env = d_vmax + rows * ns; d_month = d_env + rows * ns * 4; d_seeds = d_month + rows;
+        d_basin = reinterpret_cast<int32_t*>(d_seeds + (size_t)n_years * 84);
+    }
+    CK(cudaMemsetAsync(d_lon, 0xff, rows * ns * 8, s));
+    CK(cudaMemsetAsync(d_lat, 0xff, rows * ns * 8, s));
+    CK(cudaMemsetAsync(d_v, 0xff, rows * ns * 8, s));
+    CK(cudaMemsetAsync(d_m, 0xff, rows * ns * 8, s));
+    CK(cudaMemsetAsync(d_vmax, 0xff, rows * ns * 8, s));
+    CK(cudaMemsetAsync(d_env, 0xff, rows * ns * 32, s));
+    CK(cudaMemsetAsync(d_month, 0xff, rows * 8, s));
+    CK(cudaMemsetAsync(d_basin, 0xff, rows * 4, s));
+    CK(cudaMemsetAsync(d_seeds, 0, (size_t)n_years * 84 * 8, s));
+    CK(cudaMemsetAsync(w.stats.p, 0, (size_t)n_years * sizeof(tcr_year_stats), s));
+
+    int64_t* d_wave_off = w.year_i64.as<int64_t>();
+    int64_t* d_k0 = d_wave_off + n_years + 1;
+    int32_t* d_ym_base = w.year_i32.as<int32_t>();
+    int32_t* d_key = d_ym_base + n_years;
+    int32_t* d_nt = d_key + n_years;
+    CK(cudaMemcpyAsync(d_ym_base, ym_base, n_years * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_key, year_key, n_years * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d_nt, 0, n_years * 4, s));
+
+    std::vector<int64_t> k0(n_years, 0), W(n_years, 0), att_total(n_years, 0), hoff(2 * n_years + 1, 0);
+    std::vector<int32_t> nt(n_years, 0);
+    int32_t* pin_nt = reinterpret_cast<int32_t*>(h->pinned);
+    if ((size_t)n_years * 4 > (1 << 16)) return set_err("tcr_run_years: too many years in one call (%d)", n_years);
+
+    unsigned long long* d_queue = w.counters.as<unsigned long long>();
+    unsigned int* d_nslots = reinterpret_cast<unsigned int*>(d_queue + 1);
+    unsigned int* d_ncand = d_nslots + 1;
+
+    const int max_waves = 4096;
+    int wave = 0;
+    for (; wave < max_waves; ++wave) {
+        int n_active = 0;
+        for (int y = 0; y < n_years; ++y) if (nt[y] < n_tracks) ++n_active;
+        if (!n_active) break;
+        const int64_t per_year_cap = std::max<int64_t>(256, cap / n_active);
+        int64_t total = 0;
+        for (int y = 0; y < n_years; ++y) {
+            int64_t wy = 0;
+            if (nt[y] < n_tracks) {
+                const int64_t remaining = n_tracks - nt[y];
+                if (att_total[y] == 0) wy = std::max<int64_t>(2048, remaining * 32);
+                else if (nt[y] == 0) wy = W[y] * 4;
+                else {
+                    double rate = (double)nt[y] / (double)att_total[y];
+                    wy = (int64_t)std::ceil((double)remaining / rate * (h->oversub_permille / 1000.0)) + 256;
+                }
+                wy = std::min(wy, per_year_cap);
+            }
+            W[y] = wy;
+            hoff[y] = total;
+            total += wy;
+            hoff[n_years + 1 + y] = k0[y];
+        }
+        hoff[n_years] = total;
+        CK(cudaMemcpyAsync(d_wave_off, hoff.data(), (2 * n_years + 1) * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemsetAsync(w.counters.p, 0, 64, s));
+
+        SeedArgs sa;
+        memset(&sa, 0, sizeof sa);
+        sa.n_years = n_years; sa.wave_off = d_wave_off; sa.k0 = d_k0; sa.ym_base = d_ym_base; sa.year_key = d_key;
+        sa.run_seed = run_seed;
+        sa.code = w.code.as<int32_t>(); sa.basin = w.basin.as<int32_t>(); sa.month = w.month.as<int32_t>();
+        sa.att_slot = w.att_slot.as<int32_t>();
+        sa.n_slots = d_nslots;
+        sa.s_ym = w.s_ym.as<int32_t>(); sa.s_lon = w.s_lon.as<double>(); sa.s_lat = w.s_lat.as<double>();
+        sa.s_v0 = w.s_v0.as<double>(); sa.s_m0 = w.s_m0.as<double>(); sa.s_hbl = w.s_hbl.as<double>();
+        sa.s_att = w.s_att.as<int64_t>(); sa.s_key = w.s_key.as<int32_t>();
+        k_seed<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->ctx, sa);
+        CKK(h);
+        k_coef_from_philox<<<(unsigned)((total * TCR_N_PHASES + 255) / 256), 256, 0, s>>>(
+            h->ctx, d_nslots, sa.s_att, sa.s_key, run_seed, w.coef.as<double2>());
+        CKK(h);
+
+        IntegArgs a;
+        memset(&a, 0, sizeof a);
+        a.n = 0; a.n_dev = d_nslots;
+        a.ym = sa.s_ym; a.lon0 = sa.s_lon; a.lat0 = sa.s_lat; a.v0 = sa.s_v0; a.m0 = sa.s_m0; a.h_bl = sa.s_hbl;
+        a.coef = w.coef.as<double2>(); a.track = w.track.as<double>();
+        a.n_time = w.n_time.as<int32_t>(); a.status = w.status.as<int32_t>(); a.nfev = w.nfev.as<int32_t>();
+        a.flags = w.flags.as<uint32_t>();
+        a.queue = d_queue; a.cand_list = w.cand.as<int32_t>(); a.cand_count = d_ncand;
+        if (launch_integrate(h, a, total)) return -1;
+
+        PostArgs pa;
+        memset(&pa, 0, sizeof pa);
+        pa.n = 0; pa.list = w.cand.as<int32_t>(); pa.list_count = d_ncand;
+        pa.ym = a.ym; pa.coef = a.coef; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
+        pa.env = w.env.as<double>(); pa.vmax = w.vmax.as<double>(); pa.flags = a.flags;
+        k_postprocess<<<h->num_sms * 8, 128, 0, s>>>(h->ctx, pa);
+        CKK(h);
+
+        SelectArgs se;
+        memset(&se, 0, sizeof se);
+        se.n_tracks = n_tracks; se.wave_off = d_wave_off; se.k0 = d_k0;
+        se.code = sa.code; se.basin = sa.basin; se.month = sa.month; se.att_slot = sa.att_slot;
+        se.n_time = a.n_time; se.nfev = a.nfev; se.flags = a.flags;
+        se.nt = d_nt; se.row_slot = w.row_slot.as<int32_t>();
+        se.tc_month = d_month; se.tc_basin = d_basin; se.n_seeds = d_seeds;
+        se.stats = w.stats.as<tcr_year_stats>();
+        k_select<<<n_years, 1024, 0, s>>>(se);
+        CKK(h);
+
+        GatherArgs ga;
+        memset(&ga, 0, sizeof ga);
+        ga.n_years = n_years; ga.n_tracks = n_tracks; ga.row_slot = se.row_slot; ga.n_time = a.n_time;
+        ga.track = a.track; ga.env = pa.env; ga.vmax = pa.vmax;
+        ga.o_lon = d_lon; ga.o_lat = d_lat; ga.o_v = d_v; ga.o_m = d_m; ga.o_vmax = d_vmax; ga.o_env = d_env;
+        k_gather<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(h->ctx, ga);
+        CKK(h);
+
+        CK(cudaMemcpyAsync(pin_nt, d_nt, n_years * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int y = 0; y < n_years; ++y) {
+            if (W[y] > 0) {
+                nt[y] = pin_nt[y];
+                att_total[y] += W[y];
+                k0[y] += W[y];
+            }
+        }
+    }
+    bool complete = true;
+    for (int y = 0; y < n_years; ++y) if (nt[y] < n_tracks) complete = false;
+
+    if (!on_device) {
+        CK(cudaMemcpyAsync(lon, d_lon, rows * ns * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(lat, d_lat, rows * ns * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(v, d_v, rows * ns * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(m, d_m, rows * ns * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(vmax, d_vmax, rows * ns * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(env, d_env, rows * ns * 32, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(tc_month, d_month, rows * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(tc_basin, d_basin, rows * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(n_seeds, d_seeds, (size_t)n_years * 84 * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (stats) CK(cudaMemcpyAsync(stats, w.stats.p, (size_t)n_years * sizeof(tcr_year_stats), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (!complete) return set_err("tcr_run_years: wave limit reached before every year produced %d tracks", n_tracks);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,201 @@
+"""Host-side owner of one ``tcr_handle`` (one per GPU): uploads the prepared tables and calls the
+hot-path entry points of libtcrisk.so.  All arithmetic happens in the CUDA library; this class
+only marshals NumPy arrays (or raw device pointers) across the C ABI of include/tcrisk.h.
+"""
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib, layout
+from .params import TcrParams, TcrYearStats
+
+N_OUT = layout.N_INTERP_OUT
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def _arr(x, dtype):
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+class PinnedPool:
+    """NumPy views of page-locked host memory (tcr_host_alloc)."""
+
+    @staticmethod
+    def empty(shape, dtype):
+        lib = _lib.load()
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        _lib.check(lib.tcr_host_alloc(max(n, 1), C.byref(p)))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        weakref.finalize(buf, lib.tcr_host_free, p)
+        return a
+
+
+class Engine:
+    def __init__(self, params, device=0):
+        if not isinstance(params, TcrParams):
+            raise TypeError("params must be a TcrParams (params.params_from_namelist)")
+        self.lib = _lib.load()
+        self.p = params
+        self.n_steps = int(params.n_steps)
+        self._h = C.c_void_p()
+        _lib.check(self.lib.tcr_create(int(device), C.byref(params), C.byref(self._h)))
+        self.device = int(device)
+        self.n_ym = 0
+        self.grid = None
+
+    # -- life cycle ---------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            self.lib.tcr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr):
+        _lib.check(self.lib.tcr_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr))))
+
+    def synchronize(self):
+        _lib.check(self.lib.tcr_synchronize(self._h))
+
+    def set_tuning(self, ctas_per_sm=0, threads_per_cta=0, max_wave=0, oversub_permille=0):
+        _lib.check(self.lib.tcr_set_tuning(self._h, ctas_per_sm, threads_per_cta, max_wave, oversub_permille))
+
+    def set_interp_variant(self, variant):
+        _lib.check(self.lib.tcr_set_interp_variant(self._h, int(variant)))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.tcr_launch_count(self._h))
+
+    # -- uploads ------------------------------------------------------------------------------
+    def upload_static(self, st):
+        """st: dict from fields.prepare_static (basin-cropped bathymetry / land + axes)."""
+        lat_b, lon_b = _arr(st["lat_b"], np.float64), _arr(st["lon_b"], np.float64)
+        lat_l, lon_l = _arr(st["lat_l"], np.float64), _arr(st["lon_l"], np.float64)
+        bathy, land = _arr(st["bathy"], np.int16), _arr(st["land"], np.int8)
+        assert bathy.shape == (lat_b.size, lon_b.size) and land.shape == (lat_l.size, lon_l.size)
+        _lib.check(self.lib.tcr_upload_static(self._h, lat_b.size, lon_b.size, _ptr(lat_b), _ptr(lon_b), _ptr(bathy),
+                                              lat_l.size, lon_l.size, _ptr(lat_l), _ptr(lon_l), _ptr(land)))
+
+    def upload_masks(self, lon_m, lat_m, planes_u8):
+        lon_m, lat_m = _arr(lon_m, np.float64), _arr(lat_m, np.float64)
+        m = _arr(planes_u8, np.uint8)
+        assert m.shape == (8, lat_m.size, lon_m.size)
+        _lib.check(self.lib.tcr_upload_masks(self._h, lat_m.size, lon_m.size, _ptr(lat_m), _ptr(lon_m), _ptr(m)))
+
+    def alloc_tables(self, n_ym, lon, lat):
+        lon, lat = _arr(lon, np.float64), _arr(lat, np.float64)
+        _lib.check(self.lib.tcr_alloc_tables(self._h, int(n_ym), lat.size, lon.size, _ptr(lat), _ptr(lon)))
+        self.n_ym = int(n_ym)
+        self.grid = (lat.size, lon.size)
+
+    def upload_month(self, ym, planes):
+        """planes: float32 [19][nlat][nlon] (layout.FIELD_NAMES order), host memory."""
+        planes = _arr(planes, np.float32)
+        assert planes.shape == (layout.N_FIELDS,) + self.grid, (planes.shape, self.grid)
+        ptrs = (C.c_void_p * layout.N_FIELDS)(*[planes[i].ctypes.data for i in range(layout.N_FIELDS)])
+        _lib.check(self.lib.tcr_upload_month(self._h, int(ym), ptrs))
+
+    def upload_month_dev(self, ym, d_planes_ptr):
+        _lib.check(self.lib.tcr_upload_month_dev(self._h, int(ym), C.c_void_p(int(d_planes_ptr))))
+
+    def upload_case(self, lon, lat, planes, static, mask_lon=None, mask_lat=None, mask_planes=None):
+        """Everything one basin needs: planes [n_ym][19][nlat][nlon]."""
+        self.upload_static(static)
+        if mask_planes is not None:
+            self.upload_masks(mask_lon, mask_lat, mask_planes)
+        self.alloc_tables(planes.shape[0], lon, lat)
+        for ym in range(planes.shape[0]):
+            self.upload_month(ym, planes[ym])
+        self.synchronize()
+
+    # -- hot path -----------------------------------------------------------------------------
+    def env_interp(self, ym, lon, lat):
+        """RectBivariateSpline(kx=1,ky=1).ev of all 19 monthly fields + bathymetry + land."""
+        ym, lon, lat = _arr(ym, np.int32), _arr(lon, np.float64), _arr(lat, np.float64)
+        out = np.empty((ym.size, N_OUT))
+        _lib.check(self.lib.tcr_env_interp(self._h, ym.size, _ptr(ym), _ptr(lon), _ptr(lat), _ptr(out), 0))
+        return out
+
+    def env_interp_dev(self, n, d_ym, d_lon, d_lat, d_out):
+        """Device pointers (ints); asynchronous on the handle's stream."""
+        vp = C.c_void_p
+        _lib.check(self.lib.tcr_env_interp(self._h, int(n), vp(d_ym), vp(d_lon), vp(d_lat), vp(d_out), 1))
+
+    def integrate(self, ym, lon0, lat0, v0, m0, h_bl, phases):
+        """Coupled_FAST.gen_track + post-processing for explicit seeds."""
+        n = len(lon0)
+        ns = self.n_steps
+        ym = _arr(ym, np.int32)
+        lon0, lat0, v0, m0, h_bl = (_arr(x, np.float64) for x in (lon0, lat0, v0, m0, h_bl))
+        phases = _arr(phases, np.float64).reshape(n, 60)
+        out = dict(track=np.empty((n, ns, 4)), env=np.empty((n, ns, 4)), vmax=np.empty((n, ns)),
+                   n_time=np.zeros(n, np.int32), status=np.zeros(n, np.int32), nfev=np.zeros(n, np.int32),
+                   flags=np.zeros(n, np.uint32))
+        _lib.check(self.lib.tcr_integrate(
+            self._h, n, _ptr(ym), _ptr(lon0), _ptr(lat0), _ptr(v0), _ptr(m0), _ptr(h_bl), _ptr(phases),
+            _ptr(out["track"]), _ptr(out["env"]), _ptr(out["vmax"]), _ptr(out["n_time"]), _ptr(out["status"]),
+            _ptr(out["nfev"]), _ptr(out["flags"]), 0))
+        return out
+
+    def seed_attempts(self, ym_base, year_key, run_seed, k0, n):
+        out = dict(code=np.zeros(n, np.int32), basin=np.zeros(n, np.int32), month=np.zeros(n, np.int32),
+                   lon=np.zeros(n), lat=np.zeros(n), v0=np.zeros(n), m0=np.zeros(n), pi_gen=np.zeros(n))
+        _lib.check(self.lib.tcr_seed_attempts(
+            self._h, int(ym_base), int(year_key), int(run_seed), int(k0), int(n),
+            _ptr(out["code"]), _ptr(out["basin"]), _ptr(out["month"]), _ptr(out["lon"]), _ptr(out["lat"]),
+            _ptr(out["v0"]), _ptr(out["m0"]), _ptr(out["pi_gen"])))
+        return out
+
+    def alloc_results(self, n_years, n_tracks, pinned=True):
+        """The 9-tuple's arrays for n_years years (util/compute.py:126-133), optionally page-locked."""
+        ns = self.n_steps
+        mk = PinnedPool.empty if pinned else (lambda shape, dtype: np.empty(shape, dtype))
+        shp = (n_years, n_tracks, ns)
+        return dict(lon=mk(shp, np.float64), lat=mk(shp, np.float64), v=mk(shp, np.float64), m=mk(shp, np.float64),
+                    vmax=mk(shp, np.float64), env=mk(shp + (4,), np.float64),
+                    tc_month=mk((n_years, n_tracks), np.float64), tc_basin=mk((n_years, n_tracks), np.int32),
+                    n_seeds=mk((n_years, 7, 12), np.float64))
+
+    def run_years(self, ym_base, year_key, run_seed, n_tracks, out=None, pinned=False):
+        """run_tracks(year, n_tracks, b) for several years at once (util/compute.py:64-210)."""
+        ym_base, year_key = _arr(ym_base, np.int32), _arr(year_key, np.int32)
+        ny = ym_base.size
+        if out is None:
+            out = self.alloc_results(ny, n_tracks, pinned=pinned)
+        stats = (TcrYearStats * ny)()
+        _lib.check(self.lib.tcr_run_years(
+            self._h, ny, _ptr(ym_base), _ptr(year_key), int(run_seed), int(n_tracks),
+            _ptr(out["lon"]), _ptr(out["lat"]), _ptr(out["v"]), _ptr(out["m"]), _ptr(out["vmax"]), _ptr(out["env"]),
+            _ptr(out["tc_month"]), _ptr(out["tc_basin"]), _ptr(out["n_seeds"]), stats, 0))
+        out["stats"] = [{f: getattr(s, f) for f, _ in TcrYearStats._fields_} for s in stats]
+        return out
+
+    def run_years_dev(self, ym_base, year_key, run_seed, n_tracks, dptr):
+        """Same with device result pointers (dict of ints); returns the per-year stats."""
+        ym_base, year_key = _arr(ym_base, np.int32), _arr(year_key, np.int32)
+        ny = ym_base.size
+        stats = (TcrYearStats * ny)()
+        vp = C.c_void_p
+        _lib.check(self.lib.tcr_run_years(
+            self._h, ny, _ptr(ym_base), _ptr(year_key), int(run_seed), int(n_tracks),
+            vp(dptr["lon"]), vp(dptr["lat"]), vp(dptr["v"]), vp(dptr["m"]), vp(dptr["vmax"]), vp(dptr["env"]),
+            vp(dptr["tc_month"]), vp(dptr["tc_basin"]), vp(dptr["n_seeds"]), stats, 1))
+        return [{f: getattr(s, f) for f, _ in TcrYearStats._fields_} for s in stats]
