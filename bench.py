@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: storm-steps/s of the per-year track-generation loop
+(reference util/compute.py:64-210) on B200, through libtcrisk.so.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU arm (oracle port, all host threads)
+
+One *step* = one pass of the hot path over one batch: `tcr_run_years` for the workload's years
+(seeding -> adaptive-RK45 integration -> post-processing -> ordered selection -> 9-tuple).
+Workload at every N: BASELINE.json configs[1] per GPU -- NA basin, 10 years, 1000 tracks/year,
+361 output steps, ERA5-shaped synthetic monthly tables (weak scaling: rank r owns its own 10
+years; the only collective is the all-gather of finished tracks at write-out).
+
+A *storm-step* is one emitted output sample of one integrated seed:
+stats.storm_steps counts the samples of every gen_track call the sequential reference loop
+would have made (attempt index <= i*); work beyond i* is NOT counted.
+
+The JSON line carries: value (inputs resident in HBM), e2e (host planes in, host 9-tuple out,
+copies inside the timed region), roofline (dominant kernel of the step, k_integrate),
+roofline_interp (the stand-alone bilinear sampler, the HBM-roofline kernel the north star
+names), cpu_baseline (the oracle port on the host cores, bounded sample), clocks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "storm-steps/sec (ensemble x timesteps)"
+UNIT = "storm-steps/s"
+BASE_YEAR = 2001
+RUN_SEED = 20260101
+
+# algorithmic bytes (DESIGN.md "Roofline accounting")
+B_PER_RHS = 300            # 4 corners x 18 ch x 4 B + 4 x 2 B bathymetry + 4 x 1 B land
+B_PER_QUERY = 396          # stand-alone sampler: 300 B + 16 B query + 80 B result
+B_PER_STEP_TRACK = 32      # lon, lat, v, m float64 written by the integrator per emitted sample
+B_PER_STORM_PICKUP = 1004  # 60 double2 Fourier coefficients + 5 doubles + 1 int per integrated seed
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU, sampled every 200 ms while running."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (kind "port": the reference is Python + SciPy and
+# cannot travel to the GPU box; oracle/tcr_oracle.c restates it and is pinned against it)
+# ---------------------------------------------------------------------------------------------
+def cpu_sample(workload, n_attempts, n_threads, run_seed, year_key=BASE_YEAR):
+    """One bounded sample of the workload on the CPU: seed attempts [0, n_attempts) of year 0 --
+    seeding, gen_track and post-processing of every attempt, exactly the per-attempt work of the
+    reference loop (util/compute.py:136-207).  Every integrated sample counts (no over-shoot)."""
+    from oracle import tcr_oracle as orc
+    env = orc.OracleEnv(workload.lon, workload.lat, workload.planes[:12], workload.static)
+    masks = orc.Masks(workload.mask_lon, workload.mask_lat, workload.mask_planes)
+    t0 = time.perf_counter()
+    o = orc.run_attempts(workload.p, env, 0, masks, run_seed, year_key, 0, int(n_attempts), want_tracks=False,
+                         n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    integ = o["code"] == 2
+    st = {"storm_steps": int(o["n_time"][integ].sum()), "rhs_evals": int(o["nfev"][integ].sum()),
+          "integrated": int(integ.sum()), "kept": int(((o["flags"] & 2) != 0).sum())}
+    return st, dt
+
+
+def cpu_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tropical_cyclone_risk_b200.workload import Workload
+    threads = cpu_threads()
+    wl = Workload(args.basin, [BASE_YEAR], full_res=True)
+    n_att = args.cpu_attempts or 20000 * threads
+    for i in range(args.warmup):
+        cpu_sample(wl, max(1024, n_att // 8), threads, RUN_SEED + 1000 + i)
+    steps = sec = 0.0
+    rhs = 0
+    for i in range(args.steps):
+        st, dt = cpu_sample(wl, n_att, threads, RUN_SEED + i)
+        steps += st["storm_steps"]; rhs += st["rhs_evals"]; sec += dt
+    value = steps / sec
+    sample = "oracle port (oracle/tcr_oracle.c), %s year %d: seed attempts [0, %d) per step (seeding + gen_track + " \
+             "post-processing of every attempt), %d steps, %d threads" % (args.basin, BASE_YEAR, n_att, args.steps, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, wl.p.n_steps),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "rhs_per_s": rhs / sec},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_steps):
+    return {
+        "workload": "BASELINE configs[1] per GPU: %s basin, %d years, tracks_per_year=%d, %d output steps, "
+                    "ERA5-shaped (1 deg) synthetic env fields, 1 m/s roughness" % (args.basin, args.years, args.tracks, n_steps),
+        "basin": args.basin, "years_per_gpu": args.years, "tracks_per_year": args.tracks, "n_steps": int(n_steps),
+        "run_seed": RUN_SEED, "parallelism": "years sharded over ranks; NCCL all-gather of finished tracks at write-out",
+        "l2": "inputs larger than L2: cell-record tables %d months + result block, see l2_bytes" % (12 * args.years),
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from tropical_cyclone_risk_b200.engine import Engine, PinnedPool
+    from tropical_cyclone_risk_b200.workload import Workload
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ny, nt = args.years, args.tracks
+    years = [BASE_YEAR + rank * ny + i for i in range(ny)]
+    wl = Workload(args.basin, years, full_res=True, pinned_alloc=PinnedPool.empty)
+    ns = int(wl.p.n_steps)
+    eng = Engine(wl.p, device=local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    wl.upload(eng)
+    ym_base = np.arange(ny, dtype=np.int32) * 12
+    year_key = np.asarray(years, dtype=np.int32)
+
+    # device-resident result block (the 9-tuple of util/compute.py:210), one flat buffer so the
+    # write-out all-gather is a single collective
+    rows = ny * nt
+    sizes = [("lon", rows * ns), ("lat", rows * ns), ("v", rows * ns), ("m", rows * ns), ("vmax", rows * ns),
+             ("env", rows * ns * 4), ("tc_month", rows), ("n_seeds", ny * 84), ("tc_basin", (rows + 1) // 2)]
+    total = sum(n for _, n in sizes)
+    res = torch.empty(total, dtype=torch.float64, device=dev)
+    dptr, off = {}, 0
+    for name, n in sizes:
+        dptr[name] = res.data_ptr() + off * 8
+        off += n
+    gathered = torch.empty((world, total), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_device(i):
+        st = eng.run_years_dev(ym_base, year_key, RUN_SEED + i, nt, dptr)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, res)
+        return st
+
+    host_out = eng.alloc_results(ny, nt, pinned=True)
+
+    def step_e2e(i):
+        wl.upload_tables(eng)                                   # H2D of this step's inputs (pinned planes)
+        r = eng.run_years(ym_base, year_key, RUN_SEED + i, nt, out=host_out)   # D2H of the 9-tuple
+        return r["stats"]
+
+    def sum_stats(acc, st):
+        for s in st:
+            for k, v in s.items():
+                acc[k] = acc.get(k, 0) + v
+
+    # ---- value: inputs resident in HBM ----------------------------------------------------
+    for i in range(args.warmup):
+        step_device(1000 + i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    eng.set_timing(True)
+    launches0 = eng.launch_count
+    acc = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        sum_stats(acc, step_device(i))
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    ktimes = eng.kernel_times()
+    eng.set_timing(False)
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+
+    # ---- e2e: host planes in, host 9-tuple out ----------------------------------------------
+    for i in range(min(args.warmup, 2)):
+        step_e2e(2000 + i)
+    barrier()
+    acc_e = {}
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for i in range(args.steps):
+        sum_stats(acc_e, step_e2e(i))
+    t1.record(stream)
+    barrier()
+    ms_e = t0.elapsed_time(t1)
+
+    # ---- reduce over ranks: MAX time, SUM work ----------------------------------------------
+    keys = ("storm_steps", "kept_steps", "rhs_evals", "integrated", "attempts", "wasted_steps", "wasted_rhs_evals",
+            "wasted_integrated", "n_waves")
+    vec = torch.tensor([ms, ms_e] + [float(acc[k]) for k in keys] + [float(acc_e["storm_steps"]), float(launches)],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = vec.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vec.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    else:
+        mx = sm = vec
+    mx, sm = mx.cpu().numpy(), sm.cpu().numpy()
+    ms_max, ms_e_max = float(mx[0]), float(mx[1])
+    tot = {k: float(sm[2 + j]) for j, k in enumerate(keys)}
+    steps_e2e, launches_all = float(sm[2 + len(keys)]), int(sm[3 + len(keys)])
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        K = args.steps
+        value = tot["storm_steps"] / (ms_max * 1e-3)
+        e2e_value = steps_e2e / (ms_e_max * 1e-3)
+        h2d = int(wl.planes.nbytes)
+        d2h = int(sum(a.nbytes for a in host_out.values()))
+        # dominant kernel of the step (rank 0's launches)
+        ki_ms, ki_n = ktimes["integrate"]
+        rhs_all = acc["rhs_evals"] + acc["wasted_rhs_evals"]
+        steps_all = acc["storm_steps"] + acc["wasted_steps"]
+        storms_all = acc["integrated"] + acc["wasted_integrated"]
+        ki_bytes = B_PER_RHS * rhs_all + B_PER_STEP_TRACK * steps_all + B_PER_STORM_PICKUP * storms_all
+        ki_ach = ki_bytes / max(ki_n, 1) / (ki_ms / max(ki_n, 1) * 1e-3) / 1e9 if ki_ms > 0 else 0.0
+        roof = {"kernel": "k_integrate", "bound": "hbm", "achieved": ki_ach, "peak": peak, "unit": "GB/s",
+                "frac": ki_ach / peak, "traffic": None, "peak_source": peak_src,
+                "launches": ki_n, "avg_launch_ms": ki_ms / max(ki_n, 1),
+                "share_of_step": ki_ms / ms, "rhs_per_s": rhs_all / (ki_ms * 1e-3) if ki_ms > 0 else 0.0,
+                "note": "latency / fp64-issue bound kernel (SURVEY 8d): HBM fraction reported for honesty, "
+                        "the HBM-roofline kernel is roofline_interp"}
+        kernel_share = {k: v[0] / ms for k, v in ktimes.items() if v[1]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, ns),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e_max / K},
+            "gpu_launches": launches_all,
+            "roofline": roof,
+            "work_per_step": {k: tot[k] / K for k in keys},
+            "kernel_share_of_step": kernel_share,
+            "clocks": clocks,
+        }
+        line["config"]["l2_bytes"] = {"tables": int(wl.n_ym * (wl.lat.size - 1) * (wl.lon.size - 1) * 320),
+                                      "result_block": int(total * 8)}
+        if not args.no_interp:
+            line["roofline_interp"] = bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args)
+        if world == 1 and not args.no_cpu:
+            threads = cpu_threads()
+            n_att = args.cpu_attempts or 60000 * threads
+            cpu_sample(wl, max(1024, n_att // 16), threads, RUN_SEED + 999)      # warm the threads / page in liborc
+            st, dt = cpu_sample(wl, n_att, threads, RUN_SEED)
+            line["cpu_baseline"] = {
+                "value": st["storm_steps"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "oracle port (oracle/tcr_oracle.c), %s year %d, run_seed %d: seed attempts [0, %d) -- seeding + "
+                          "gen_track + post-processing of every attempt (%.1f s, %d threads)" % (
+                              args.basin, BASE_YEAR, RUN_SEED, n_att, dt, threads),
+                "rhs_per_s": st["rhs_evals"] / dt}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args):
+    """The stand-alone bilinear sampler on random queries over every resident table (>> L2)."""
+    n = int(args.interp_queries)
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    b = wl.bounds
+    lon = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * (b[2] - b[0]) + b[0]).contiguous()
+    lat = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * (b[3] - b[1]) + b[1]).contiguous()
+    ym = torch.randint(0, wl.n_ym, (n,), generator=g, device=dev, dtype=torch.int32)
+    out = torch.empty((n, 21), dtype=torch.float64, device=dev)
+    res = {}
+    for variant, name in ((0, "k_env_interp"), (1, "k_env_interp_tma")):
+        eng.set_interp_variant(variant)
+        for _ in range(3):
+            eng.env_interp_dev(n, ym.data_ptr(), lon.data_ptr(), lat.data_ptr(), out.data_ptr())
+        torch.cuda.synchronize()
+        eng.set_timing(True)
+        reps = 10
+        for _ in range(reps):
+            eng.env_interp_dev(n, ym.data_ptr(), lon.data_ptr(), lat.data_ptr(), out.data_ptr())
+        ms, cnt = eng.kernel_times()["env_interp"]
+        eng.set_timing(False)
+        ach = B_PER_QUERY * n / (ms / cnt * 1e-3) / 1e9
+        res[name] = {"achieved": ach, "frac": ach / peak, "avg_launch_ms": ms / cnt, "launches": cnt}
+    eng.set_interp_variant(0)
+    best = max(res, key=lambda k: res[k]["achieved"])
+    return {"kernel": best, "bound": "hbm", "achieved": res[best]["achieved"], "peak": peak, "unit": "GB/s",
+            "frac": res[best]["frac"], "traffic": None, "peak_source": peak_src, "queries_per_launch": n,
+            "algorithmic_bytes_per_query": B_PER_QUERY, "moved_bytes_per_query": 320 + 12 + 20 + 168,
+            "table_bytes": int(wl.n_ym * (wl.lat.size - 1) * (wl.lon.size - 1) * 320), "variants": res,
+            "l2": "random queries over all %d month tables (>> 126 MB L2) + %d MB streamed output" % (wl.n_ym, n * 168 >> 20)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--basin", default="NA")
+    ap.add_argument("--years", type=int, default=10, help="years per GPU")
+    ap.add_argument("--tracks", type=int, default=1000, help="tracks per year")
+    ap.add_argument("--interp-queries", type=float, default=float(1 << 25))
+    ap.add_argument("--cpu-attempts", type=int, default=0, help="seed attempts per CPU sample (default scales with threads)")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-interp", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("bench.py: note: fewer than 3 warm-up steps", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

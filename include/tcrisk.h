@@ -97,6 +97,7 @@ typedef struct tcr_year_stats {
     int64_t rhs_evals;         /* dydt evaluations of those calls                                */
     int64_t wasted_integrated; /* gen_track calls beyond i* (over-shoot of the last wave)        */
     int64_t wasted_steps;      /* their samples                                                  */
+    int64_t wasted_rhs_evals;  /* their dydt evaluations                                         */
     int32_t n_kept;            /* == n_tracks on success                                         */
     int32_t n_waves;
 } tcr_year_stats;
@@ -183,6 +184,21 @@ int tcr_set_tuning(tcr_handle* h, int ctas_per_sm, int threads_per_cta, int64_t 
                    int oversub_permille);
 /* number of kernels launched by this handle so far (bench.py's gpu_launches)               */
 int64_t tcr_launch_count(tcr_handle* h);
+/* device-time accounting: with timing enabled every launch of a kernel class is bracketed by
+ * CUDA events on the handle's stream; tcr_kernel_time synchronises the stream and returns the
+ * accumulated milliseconds and launch count of one class since tcr_set_timing was last called
+ * (the reference prints time.time() deltas instead, util/compute.py:26-35,229,270)            */
+#define TCR_K_ENV_INTERP   0
+#define TCR_K_INTEGRATE    1
+#define TCR_K_POSTPROCESS  2
+#define TCR_K_SEED         3
+#define TCR_K_COEF         4
+#define TCR_K_SELECT       5
+#define TCR_K_GATHER       6
+#define TCR_K_BUILD        7
+#define TCR_N_KERNEL_CLASSES 8
+int tcr_set_timing(tcr_handle* h, int enable);
+int tcr_kernel_time(tcr_handle* h, int kernel_class, double* ms, int64_t* launches);
 /* tcr_env_interp implementation: 0 = per-lane LDG.128 gathers, 1 = TMA bulk copies
  * (cp.async.bulk) of the cell records into shared memory behind an mbarrier pipeline        */
 int tcr_set_interp_variant(tcr_handle* h, int variant);

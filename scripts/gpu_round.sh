@@ -1,0 +1,33 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, bench (both arms), ncu launch list + full captures.
+# Usage (from the repo root, on the B200 box):  bash scripts/gpu_round.sh [tag]
+TAG=${1:-r01}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
+nproc > $OUT/nproc.txt
+echo "== pytest -m gpu"
+timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest_gpu.log
+tail -5 $OUT/pytest_gpu.log
+echo "== smoke"
+timeout 600 python __graft_entry__.py --smoke > $OUT/smoke.log 2>&1; echo "smoke exit $?" | tee -a $OUT/smoke.log
+tail -3 $OUT/smoke.log
+echo "== bench"
+timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "bench exit $?"
+cat $OUT/bench.json; tail -5 $OUT/bench.err
+timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
+cat $OUT/bench_reference.json
+if [ -z "$NO_NCU" ]; then
+echo "== ncu launch list"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu --interp-queries 4194304 > $OUT/ncu_bench.log 2>&1
+echo "== ncu full: k_integrate"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_integrate -s 2 -c 1 -f -o $OUT/prof_integrate \
+    python bench.py --steps 1 --warmup 1 --no-cpu --no-interp > $OUT/ncu_integrate.log 2>&1
+echo "== ncu full: env_interp"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_env_interp -s 3 -c 1 -f -o $OUT/prof_interp \
+    python bench.py --steps 1 --warmup 1 --no-cpu --years 10 --tracks 50 > $OUT/ncu_interp.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_postprocess -s 2 -c 1 -f -o $OUT/prof_post \
+    python bench.py --steps 1 --warmup 1 --no-cpu --no-interp > $OUT/ncu_post.log 2>&1
+fi
+ls -la $OUT

@@ -21,37 +21,21 @@ def golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
 
-class Case:
-    """One basin's prepared inputs: params, monthly planes (float32), static grids, masks,
-    and the same numbers in the CPU oracle's layout."""
+def _workload_cls():
+    from tropical_cyclone_risk_b200.workload import Workload
+    return Workload
+
+
+class Case(_workload_cls()):
+    """One basin's prepared inputs (tropical_cyclone_risk_b200.workload.Workload) plus the same
+    numbers in the CPU oracle's layout."""
 
     def __init__(self, basin, years, months=range(1, 13), full_res=False, roughness=1.0,
                  zero_cov_over_land=False, namelist=None):
-        from tropical_cyclone_risk_b200 import fields, params, synth
-        from tropical_cyclone_risk_b200 import namelist as default_namelist
         from oracle import tcr_oracle as orc
-        nl = namelist or default_namelist
-        self.namelist = nl
-        self.basin = basin
-        self.p = params.params_from_namelist(nl, basin)
-        self.bounds = params.basin_bounds(nl, basin)
-        lon, lat = synth.era5_axes()
-        olon, olat = synth.ocean_axes()
-        planes = []
-        for y in years:
-            for mth in months:
-                raw = synth.synth_month_raw(y, mth, lon, lat, roughness, zero_cov_over_land)
-                mld, strat = synth.synth_ocean(olon, olat, mth)
-                self.lon, self.lat, pl = fields.prepare_month(nl, self.bounds, lon, lat, raw, olon, olat, mld, strat)
-                planes.append(pl)
-        self.planes = np.stack(planes)                      # [n_ym][19][nlat][nlon] float32
-        st = synth.synth_static(full_res=full_res)
-        self.static_global = st
-        self.static = fields.prepare_static(self.bounds, st)
-        mlon, mlat, m = fields.crop_to_basin(st["lon_m"], st["lat_m"], fields.mask_planes(st, basin), self.bounds)
-        self.mask_lon, self.mask_lat, self.mask_planes = mlon, mlat, np.ascontiguousarray(m, dtype=np.uint8)
+        super().__init__(basin, years, months, full_res, roughness, zero_cov_over_land, namelist)
         self.env = orc.OracleEnv(self.lon, self.lat, self.planes, self.static)
-        self.masks = orc.Masks(mlon, mlat, self.mask_planes)
+        self.masks = orc.Masks(self.mask_lon, self.mask_lat, self.mask_planes)
 
 
 @pytest.fixture(scope="session")

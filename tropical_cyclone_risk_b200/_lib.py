@@ -13,6 +13,7 @@ SYMBOLS = (
     "tcr_upload_static", "tcr_upload_masks", "tcr_alloc_tables", "tcr_upload_month", "tcr_upload_month_dev",
     "tcr_env_interp", "tcr_integrate", "tcr_run_years", "tcr_seed_attempts", "tcr_set_tuning",
     "tcr_launch_count", "tcr_set_interp_variant", "tcr_host_alloc", "tcr_host_free",
+    "tcr_set_timing", "tcr_kernel_time",
 )
 
 _lib = None
@@ -55,6 +56,8 @@ def load():
     lib.tcr_launch_count.argtypes = [vp]
     lib.tcr_launch_count.restype = C.c_int64
     lib.tcr_set_interp_variant.argtypes = [vp, C.c_int]
+    lib.tcr_set_timing.argtypes = [vp, C.c_int]
+    lib.tcr_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.tcr_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.tcr_host_free.argtypes = [vp]
     _lib = lib

@@ -835,7 +835,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
 {
     __shared__ int warp_tot[32];
     __shared__ int s_running, s_istar;
-    __shared__ unsigned long long s_acc[6];
+    __shared__ unsigned long long s_acc[7];
     __shared__ unsigned int s_hist[TCR_N_BASINS * 12];
     const int yr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t off = A.wave_off[yr];
@@ -845,7 +845,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
     const int nt0 = A.nt[yr];
     const int want = A.n_tracks - nt0;
     if (tid == 0) { s_running = 0; s_istar = -1; }
-    if (tid < 6) s_acc[tid] = 0ull;
+    if (tid < 7) s_acc[tid] = 0ull;
     for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) s_hist[i] = 0u;
     __syncthreads();
     /* pass 1: rank the kept storms in attempt order, find i* = attempt of the want-th kept */
@@ -886,17 +886,17 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
     const int64_t i_star = s_istar;
     const int64_t last = i_star >= 0 ? i_star : W - 1;      /* attempts consumed: 0..last */
     /* pass 2: counters over the consumed attempts */
-    unsigned long long counted = 0, integ = 0, steps = 0, rhs = 0, w_integ = 0, w_steps = 0;
+    unsigned long long counted = 0, integ = 0, steps = 0, rhs = 0, w_integ = 0, w_steps = 0, w_rhs = 0;
     for (int64_t i = tid; i < W; i += blockDim.x) {
         const int code = A.code[off + i];
         const int slot = A.att_slot[off + i];
         if (i <= last) {
             if (code == 1 || code == 2) { ++counted; atomicAdd(&s_hist[A.basin[off + i] * 12 + A.month[off + i] - 1], 1u); }
             if (slot >= 0) { ++integ; steps += (unsigned long long)A.n_time[slot]; rhs += (unsigned long long)A.nfev[slot]; }
-        } else if (slot >= 0) { ++w_integ; w_steps += (unsigned long long)A.n_time[slot]; }
+        } else if (slot >= 0) { ++w_integ; w_steps += (unsigned long long)A.n_time[slot]; w_rhs += (unsigned long long)A.nfev[slot]; }
     }
     atomicAdd(&s_acc[0], counted); atomicAdd(&s_acc[1], integ); atomicAdd(&s_acc[2], steps);
-    atomicAdd(&s_acc[3], rhs); atomicAdd(&s_acc[5], (w_integ << 40) | w_steps);
+    atomicAdd(&s_acc[3], rhs); atomicAdd(&s_acc[5], (w_integ << 40) | w_steps); atomicAdd(&s_acc[6], w_rhs);
     __syncthreads();
     for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x)
         A.n_seeds[(size_t)yr * TCR_N_BASINS * 12 + i] += (double)s_hist[i];
@@ -911,6 +911,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
         s.kept_steps += (int64_t)s_acc[4];
         s.wasted_integrated += (int64_t)(s_acc[5] >> 40);
         s.wasted_steps += (int64_t)(s_acc[5] & ((1ull << 40) - 1));
+        s.wasted_rhs_evals += (int64_t)s_acc[6];
         s.n_kept = nt0 + got;
         s.n_waves += 1;
         A.nt[yr] = nt0 + got;

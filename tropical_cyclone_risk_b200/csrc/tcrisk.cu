@@ -69,6 +69,8 @@ struct AxisBuf {
     int n = 0;
 };
 
+struct TimedSpan { int which; cudaEvent_t a, b; };
+
 /* scratch of tcr_run_years / tcr_integrate, grown on demand and kept in the handle */
 struct Workspace {
     int64_t cap = 0;        /* slots == attempts per wave */
@@ -115,7 +117,50 @@ struct tcr_handle {
     int64_t max_wave = 0;
     Workspace ws;
     void* pinned = nullptr;      /* small pinned read-back area */
+    /* device-time accounting (tcr_set_timing): event pairs around every launch of a kernel class */
+    bool timing = false;
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> free_events;
+    double class_ms[TCR_N_KERNEL_CLASSES] = {0};
+    int64_t class_launches[TCR_N_KERNEL_CLASSES] = {0};
 };
+
+static cudaEvent_t take_event(tcr_handle* h)
+{
+    cudaEvent_t e = nullptr;
+    if (!h->free_events.empty()) { e = h->free_events.back(); h->free_events.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
+/* brackets one kernel launch with events on the handle's stream when timing is on */
+struct LaunchTimer {
+    tcr_handle* h; int which; cudaEvent_t a = nullptr;
+    LaunchTimer(tcr_handle* h_, int which_) : h(h_), which(which_)
+    {
+        if (h->timing) { a = take_event(h); cudaEventRecord(a, h->stream); }
+    }
+    ~LaunchTimer()
+    {
+        if (a) { cudaEvent_t b = take_event(h); cudaEventRecord(b, h->stream); h->spans.push_back({which, a, b}); }
+    }
+};
+
+static int resolve_spans(tcr_handle* h)
+{
+    if (h->spans.empty()) return 0;
+    CK(cudaStreamSynchronize(h->stream));
+    for (const TimedSpan& sp : h->spans) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        h->class_ms[sp.which] += ms;
+        h->class_launches[sp.which] += 1;
+        h->free_events.push_back(sp.a);
+        h->free_events.push_back(sp.b);
+    }
+    h->spans.clear();
+    return 0;
+}
 
 static int make_axis(tcr_handle* h, const double* host, int n, AxisBuf& ab, TcrAxis& ax)
 {
@@ -190,6 +235,8 @@ int tcr_destroy(tcr_handle* h)
     AxisBuf* axs[] = {&h->ax_lon, &h->ax_lat, &h->ax_lon_b, &h->ax_lat_b, &h->ax_lon_l, &h->ax_lat_l, &h->ax_lon_m, &h->ax_lat_m};
     for (AxisBuf* a : axs) a->buf.release();
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (const TimedSpan& sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (cudaEvent_t e : h->free_events) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -231,6 +278,27 @@ int tcr_set_interp_variant(tcr_handle* h, int variant)
 }
 
 int64_t tcr_launch_count(tcr_handle* h) { return h ? h->launches : 0; }
+
+int tcr_set_timing(tcr_handle* h, int enable)
+{
+    if (!h) return set_err("null handle");
+    CK(cudaSetDevice(h->device));
+    if (resolve_spans(h)) return -1;
+    h->timing = enable != 0;
+    for (int i = 0; i < TCR_N_KERNEL_CLASSES; ++i) { h->class_ms[i] = 0.0; h->class_launches[i] = 0; }
+    return 0;
+}
+
+int tcr_kernel_time(tcr_handle* h, int kernel_class, double* ms, int64_t* launches)
+{
+    if (!h) return set_err("null handle");
+    if (kernel_class < 0 || kernel_class >= TCR_N_KERNEL_CLASSES) return set_err("tcr_kernel_time: unknown kernel class %d", kernel_class);
+    CK(cudaSetDevice(h->device));
+    if (resolve_spans(h)) return -1;
+    if (ms) *ms = h->class_ms[kernel_class];
+    if (launches) *launches = h->class_launches[kernel_class];
+    return 0;
+}
 
 int tcr_host_alloc(size_t bytes, void** out)
 {
@@ -324,8 +392,11 @@ int tcr_upload_month_dev(tcr_handle* h, int ym, const float* d_planes)
     if (!h->rec.p) return set_err("tcr_upload_month: call tcr_alloc_tables first");
     if (ym < 0 || ym >= h->n_ym) return set_err("tcr_upload_month: ym %d out of range [0, %d)", ym, h->n_ym);
     CK(cudaSetDevice(h->device));
-    k_build_month<<<grid_for(h->month_f4, 256, h->num_sms), 256, 0, h->stream>>>(
-        d_planes, h->rec.as<float4>() + h->month_f4 * (size_t)ym, h->nlat, h->nlon);
+    {
+        LaunchTimer lt_(h, TCR_K_BUILD);
+        k_build_month<<<grid_for(h->month_f4, 256, h->num_sms), 256, 0, h->stream>>>(
+            d_planes, h->rec.as<float4>() + h->month_f4 * (size_t)ym, h->nlat, h->nlon);
+    }
     CKK(h);
     return 0;
 }
@@ -354,6 +425,7 @@ int tcr_upload_month(tcr_handle* h, int ym, const float* const* fields)
 /* ---- stand-alone bilinear sampler ------------------------------------------------------------ */
 static int launch_env_interp(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon, const double* lat, double* out)
 {
+    LaunchTimer lt_(h, TCR_K_ENV_INTERP);
     if (h->interp_variant == 1) {
         const size_t smem = (size_t)EIT_STAGES * EIT_TILE * (TCR_REC_F4 * 16 + sizeof(EitLoc)) + EIT_STAGES * sizeof(uint64_t);
         CK(cudaFuncSetAttribute(k_env_interp_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -436,7 +508,10 @@ static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
     int grid = (int)std::max<int64_t>(1, std::min(max_ctas, want_ctas));
     int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
     a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
-    k_integrate<<<grid, bd, smem, h->stream>>>(h->ctx, a);
+    {
+        LaunchTimer lt_(h, TCR_K_INTEGRATE);
+        k_integrate<<<grid, bd, smem, h->stream>>>(h->ctx, a);
+    }
     CKK(h);
     return 0;
 }
@@ -477,6 +552,7 @@ int tcr_integrate(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon
     CK(cudaMemsetAsync(w.vmax.p, 0xff, (size_t)n * ns * 8, s));
     {
         int64_t total = n * TCR_N_PHASES;
+        LaunchTimer lt_(h, TCR_K_COEF);
         k_coef_from_phases<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->ctx, n, ph.as<double>(), w.coef.as<double2>());
         CKK(h);
     }
@@ -496,7 +572,10 @@ int tcr_integrate(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon
     pa.n = n; pa.list = nullptr; pa.list_count = nullptr;
     pa.ym = a.ym; pa.coef = a.coef; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
     pa.env = w.env.as<double>(); pa.vmax = w.vmax.as<double>(); pa.flags = a.flags;
-    k_postprocess<<<(unsigned)std::min<int64_t>(n, (int64_t)h->num_sms * 16), 128, 0, s>>>(h->ctx, pa);
+    {
+        LaunchTimer lt_(h, TCR_K_POSTPROCESS);
+        k_postprocess<<<(unsigned)std::min<int64_t>(n, (int64_t)h->num_sms * 16), 128, 0, s>>>(h->ctx, pa);
+    }
     CKK(h);
     const cudaMemcpyKind out_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (track) CK(cudaMemcpyAsync(track, w.track.p, (size_t)n * ns * 32, out_kind, s));
@@ -665,10 +744,16 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         sa.s_ym = w.s_ym.as<int32_t>(); sa.s_lon = w.s_lon.as<double>(); sa.s_lat = w.s_lat.as<double>();
         sa.s_v0 = w.s_v0.as<double>(); sa.s_m0 = w.s_m0.as<double>(); sa.s_hbl = w.s_hbl.as<double>();
         sa.s_att = w.s_att.as<int64_t>(); sa.s_key = w.s_key.as<int32_t>();
-        k_seed<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->ctx, sa);
+        {
+            LaunchTimer lt_(h, TCR_K_SEED);
+            k_seed<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->ctx, sa);
+        }
         CKK(h);
-        k_coef_from_philox<<<(unsigned)((total * TCR_N_PHASES + 255) / 256), 256, 0, s>>>(
-            h->ctx, d_nslots, sa.s_att, sa.s_key, run_seed, w.coef.as<double2>());
+        {
+            LaunchTimer lt_(h, TCR_K_COEF);
+            k_coef_from_philox<<<(unsigned)((total * TCR_N_PHASES + 255) / 256), 256, 0, s>>>(
+                h->ctx, d_nslots, sa.s_att, sa.s_key, run_seed, w.coef.as<double2>());
+        }
         CKK(h);
 
         IntegArgs a;
@@ -686,7 +771,10 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         pa.n = 0; pa.list = w.cand.as<int32_t>(); pa.list_count = d_ncand;
         pa.ym = a.ym; pa.coef = a.coef; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
         pa.env = w.env.as<double>(); pa.vmax = w.vmax.as<double>(); pa.flags = a.flags;
-        k_postprocess<<<h->num_sms * 8, 128, 0, s>>>(h->ctx, pa);
+        {
+            LaunchTimer lt_(h, TCR_K_POSTPROCESS);
+            k_postprocess<<<h->num_sms * 8, 128, 0, s>>>(h->ctx, pa);
+        }
         CKK(h);
 
         SelectArgs se;
@@ -697,7 +785,10 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         se.nt = d_nt; se.row_slot = w.row_slot.as<int32_t>();
         se.tc_month = d_month; se.tc_basin = d_basin; se.n_seeds = d_seeds;
         se.stats = w.stats.as<tcr_year_stats>();
-        k_select<<<n_years, 1024, 0, s>>>(se);
+        {
+            LaunchTimer lt_(h, TCR_K_SELECT);
+            k_select<<<n_years, 1024, 0, s>>>(se);
+        }
         CKK(h);
 
         GatherArgs ga;
@@ -705,7 +796,10 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         ga.n_years = n_years; ga.n_tracks = n_tracks; ga.row_slot = se.row_slot; ga.n_time = a.n_time;
         ga.track = a.track; ga.env = pa.env; ga.vmax = pa.vmax;
         ga.o_lon = d_lon; ga.o_lat = d_lat; ga.o_v = d_v; ga.o_m = d_m; ga.o_vmax = d_vmax; ga.o_env = d_env;
-        k_gather<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(h->ctx, ga);
+        {
+            LaunchTimer lt_(h, TCR_K_GATHER);
+            k_gather<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(h->ctx, ga);
+        }
         CKK(h);
 
         CK(cudaMemcpyAsync(pin_nt, d_nt, n_years * 4, cudaMemcpyDeviceToHost, s));

@@ -84,6 +84,21 @@ class Engine:
     def launch_count(self):
         return int(self.lib.tcr_launch_count(self._h))
 
+    KERNEL_CLASSES = ("env_interp", "integrate", "postprocess", "seed", "coef", "select", "gather", "build")
+
+    def set_timing(self, enable=True):
+        """CUDA-event accounting of every kernel class on the handle's stream (resets the totals)."""
+        _lib.check(self.lib.tcr_set_timing(self._h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """{class: (milliseconds, launches)} accumulated since set_timing()."""
+        out = {}
+        for i, name in enumerate(self.KERNEL_CLASSES):
+            ms, n = C.c_double(), C.c_int64()
+            _lib.check(self.lib.tcr_kernel_time(self._h, i, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     # -- uploads ------------------------------------------------------------------------------
     def upload_static(self, st):
         """st: dict from fields.prepare_static (basin-cropped bathymetry / land + axes)."""
