@@ -284,7 +284,7 @@ def run_gpu_arm(args):
         value = tot["storm_steps"] / (ms_max * 1e-3)
         e2e_value = steps_e2e / (ms_e_max * 1e-3)
         h2d = int(wl.planes.nbytes)
-        d2h = int(sum(a.nbytes for a in host_out.values()))
+        d2h = int(sum(a.nbytes for a in host_out.values() if isinstance(a, np.ndarray)))
         # dominant kernel of the step (rank 0's launches)
         ki_ms, ki_n = ktimes["integrate"]
         rhs_all = acc["rhs_evals"] + acc["wasted_rhs_evals"]
