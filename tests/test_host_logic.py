@@ -156,7 +156,7 @@ def test_trackfile_schema_roundtrip(tmp_path):
         out2 = compute.run_downscaling("NA", write=True, run_years_fn=_fake_run_years)
     finally:
         compute.configure(namelist=nl)
-    assert out["fn_trk_out"].endswith("tracks_NA_synthetic_201601_202112.nc")
+    assert out["fn_trk_out"].endswith("tracks_NA_synthetic_200101_200212.nc")
     assert out2["fn_trk_out"].endswith("_e0.nc")                    # never overwrites (compute.py:52-58)
     f = trackfile.read_tracks(out["fn_trk_out"])
     want_vars = {"lon_trks", "lat_trks", "u250_trks", "v250_trks", "u850_trks", "v850_trks", "v_trks", "m_trks",
