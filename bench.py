@@ -196,6 +196,8 @@ def run_gpu_arm(args):
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     wl.upload(eng)
+    if args.integ_variant:
+        eng.set_tuning(integ_variant=args.integ_variant)
     ym_base = np.arange(ny, dtype=np.int32) * 12
     year_key = np.asarray(years, dtype=np.int32)
 
@@ -375,6 +377,7 @@ def main():
     ap.add_argument("--tracks", type=int, default=1000, help="tracks per year")
     ap.add_argument("--interp-queries", type=float, default=float(1 << 25))
     ap.add_argument("--cpu-attempts", type=int, default=0, help="seed attempts per CPU sample (default scales with threads)")
+    ap.add_argument("--integ-variant", type=int, default=0, help="integrate-kernel register variant (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-interp", action="store_true")
     args = ap.parse_args()

@@ -178,10 +178,10 @@ int tcr_seed_attempts(tcr_handle* h, int ym_base, int32_t year_key, uint32_t run
                       int32_t* code, int32_t* basin, int32_t* month,
                       double* lon, double* lat, double* v0, double* m0, double* pi_gen);
 
-/* tuning knobs (0 keeps the default): persistent CTAs per SM / threads per CTA of the
- * integrate kernel, candidate rows per wave, wave over-subscription factor (x1000)          */
-int tcr_set_tuning(tcr_handle* h, int ctas_per_sm, int threads_per_cta, int64_t max_wave_cands,
-                   int oversub_permille);
+/* tuning knobs (0 keeps the default): register-budget variant of the integrate kernel
+ * (1 = 256 threads x 1 CTA/SM, 2 = 128 x 3, 3 = 128 x 4), seed attempts per wave, wave
+ * over-subscription factor (x1000)                                                          */
+int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int oversub_permille);
 /* number of kernels launched by this handle so far (bench.py's gpu_launches)               */
 int64_t tcr_launch_count(tcr_handle* h);
 /* device-time accounting: with timing enabled every launch of a kernel class is bracketed by
@@ -196,7 +196,8 @@ int64_t tcr_launch_count(tcr_handle* h);
 #define TCR_K_SELECT       5
 #define TCR_K_GATHER       6
 #define TCR_K_BUILD        7
-#define TCR_N_KERNEL_CLASSES 8
+#define TCR_K_FTABLE       8
+#define TCR_N_KERNEL_CLASSES 9
 int tcr_set_timing(tcr_handle* h, int enable);
 int tcr_kernel_time(tcr_handle* h, int kernel_class, double* ms, int64_t* launches);
 /* tcr_env_interp implementation: 0 = per-lane LDG.128 gathers, 1 = TMA bulk copies

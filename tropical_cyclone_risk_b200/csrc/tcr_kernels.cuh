@@ -67,10 +67,28 @@ __global__ void k_build_masks(const uint8_t* __restrict__ src, uint2* __restrict
     }
 }
 
-__global__ void k_build_axis(const double* __restrict__ ax, double2* __restrict__ out, int n)
+__global__ void k_build_axis(const double* __restrict__ ax, TcrNode* __restrict__ out, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = make_double2(ax[i], i + 1 < n ? 1.0 / (ax[i + 1] - ax[i]) : 0.0);
+    if (i < n) {
+        TcrNode nd;
+        nd.x = ax[i];
+        nd.inv = i + 1 < n ? 1.0 / (ax[i + 1] - ax[i]) : 0.0;
+        nd.x1 = i + 1 < n ? ax[i + 1] : ax[i];
+        nd.pad = 0.0;
+        out[i] = nd;
+    }
+}
+
+/* storm-independent harmonics of the output time grid: sc[j][k] = {sin, cos}(2 pi (k+1) t_j / T_Fs) */
+__global__ void k_build_sincos(const __grid_constant__ TcrCtx cx, double2* __restrict__ sc)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cx.p.n_steps) return;
+    double2 h[TCR_N_HARM];
+    tcr_harmonics(cx, tcr_node_time(cx, j), h);
+#pragma unroll
+    for (int k = 0; k < TCR_N_HARM; ++k) sc[(size_t)j * TCR_N_HARM + k] = h[k];
 }
 
 /* ======================================================================================== */
@@ -283,6 +301,57 @@ __global__ void k_coef_from_philox(const __grid_constant__ TcrCtx cx, const unsi
 }
 
 /* ======================================================================================== */
+/* Fourier tables of a wave's storms: gen_f (bam_track.py:23-31) on the output time grid       */
+/* ftab [n][n_steps][4].  A small dense contraction per storm (n_steps x 30 by 30 x 4) done on */
+/* the fp64 pipe in the exact operation order of the specification (series-by-series fma       */
+/* chains over the harmonics), so it is bit-identical to evaluating the series in the RHS.     */
+/* Thread = one time node (its 15 {sin, cos} pairs stay in registers); the CTA walks a tile of */
+/* storms whose coefficients sit in shared memory (broadcast reads); stores are coalesced:     */
+/* adjacent threads write adjacent 32-byte nodes.                                              */
+/* ======================================================================================== */
+#define FT_THREADS 128
+#define FT_STORMS 16
+__global__ void __launch_bounds__(FT_THREADS) k_fourier_table(const __grid_constant__ TcrCtx cx, int64_t n,
+                                                              const unsigned int* __restrict__ n_dev,
+                                                              const double2* __restrict__ coef, double* __restrict__ ftab)
+{
+    __shared__ double2 cfs[FT_STORMS][TCR_N_PHASES];
+    const int64_t count = n_dev ? (int64_t)*n_dev : n;
+    const int ns = cx.p.n_steps;
+    const int j = blockIdx.x * FT_THREADS + threadIdx.x;
+    double2 sc[TCR_N_HARM];
+    if (j < ns) {
+#pragma unroll
+        for (int k = 0; k < TCR_N_HARM; ++k) sc[k] = __ldg(cx.sc + (size_t)j * TCR_N_HARM + k);
+    }
+    for (int64_t s0 = (int64_t)blockIdx.y * FT_STORMS; s0 < count; s0 += (int64_t)gridDim.y * FT_STORMS) {
+        const int nst = (int)min((int64_t)FT_STORMS, count - s0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nst * TCR_N_PHASES; i += FT_THREADS)
+            (&cfs[0][0])[i] = __ldg(coef + (size_t)s0 * TCR_N_PHASES + i);
+        __syncthreads();
+        if (j < ns) {
+#pragma unroll 2
+            for (int st = 0; st < nst; ++st) {
+                double F[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+                for (int k = 0; k < TCR_N_HARM; ++k) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const double2 ab = cfs[st][i * TCR_N_HARM + k];
+                        F[i] = fma(ab.x, sc[k].x, F[i]);
+                        F[i] = fma(ab.y, sc[k].y, F[i]);
+                    }
+                }
+                double2* dst = reinterpret_cast<double2*>(ftab + ((size_t)(s0 + st) * ns + j) * 4);
+                dst[0] = make_double2(F[0], F[1]);
+                dst[1] = make_double2(F[2], F[3]);
+            }
+        }
+    }
+}
+
+/* ======================================================================================== */
 /* the integrator: Coupled_FAST.gen_track (coupled_fast.py:229-267) incl. scipy's RK45        */
 /* driver loop, t_eval dense output and the terminal event                                    */
 /* ======================================================================================== */
@@ -291,7 +360,7 @@ struct IntegArgs {
     const unsigned int* n_dev;         /* device-side count (run_years)                       */
     const int32_t* ym;                 /* [n] table index                                     */
     const double* lon0; const double* lat0; const double* v0; const double* m0; const double* h_bl;
-    const double2* coef;               /* [n][60]                                             */
+    const double* ftab;                /* [n][n_steps][4] Fourier tables (k_fourier_table)    */
     double* track;                     /* [n][n_steps][4] lon,lat,v,m                         */
     int32_t* n_time; int32_t* status; int32_t* nfev; uint32_t* flags;
     unsigned long long* queue;         /* work counter, zeroed by the host                    */
@@ -307,14 +376,16 @@ enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
  * per-stage bookkeeping is predicated.  A lane whose storm ended pops the next storm from
  * the global queue and spends its macro step on the two initial-step evaluations
  * (select_initial_step); the persistent loop ends when the queue is drained.  Storm state
- * (y, K[7][4], step control) lives in registers for the storm's lifetime; the storm's 120
- * Fourier coefficients live in shared memory; only emitted samples go to HBM.              */
-__global__ void __launch_bounds__(256, 1) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
+ * (y, K[7][4], step control) lives in registers for the storm's lifetime; the storm's Fourier
+ * table is read from HBM/L2 (64 B per evaluation); only emitted samples go to HBM.
+ * THREADS x MINB fixes the register budget (launch bounds): <256,1> 255 registers, <128,3> 168,
+ * <128,4> 128 -- chosen at run time by tcr_set_tuning, default by measurement.   */
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
 {
-    extern __shared__ __align__(16) double2 cf_s[];          /* [60][blockDim.x] */
     const tcr_params& p = cx.p;
-    const int tid = threadIdx.x, lane = tid & 31, stride = blockDim.x;
-    double2* cf = cf_s + tid;
+    const int lane = threadIdx.x & 31;
+    const double* ftab = nullptr;
     const int64_t n = A.n_dev ? (int64_t)*A.n_dev : A.n;
     const int ns = p.n_steps;
     const double t_bound = p.total_time, rtol = p.rtol, atol = p.atol, max_step = p.max_step;
@@ -395,9 +466,7 @@ __global__ void __launch_bounds__(256, 1) k_integrate(const __grid_constant__ Tc
                             ym = A.ym[sid];
                             y[0] = A.lon0[sid]; y[1] = A.lat0[sid]; y[2] = A.v0[sid]; y[3] = A.m0[sid];
                             hbl = A.h_bl[sid];
-                            const double2* src = A.coef + (size_t)sid * TCR_N_PHASES;
-#pragma unroll 4
-                            for (int j = 0; j < TCR_N_PHASES; ++j) cf[j * stride] = __ldg(src + j);
+                            ftab = A.ftab + (size_t)sid * ns * 4;
                             trk = A.track + (size_t)sid * ns * 4;
                             nfev = 0; n_out = 0; n_attempts = 0; any_v = false; t = 0.0; status = 100;
                             mode = M_INIT0;
@@ -462,7 +531,7 @@ __global__ void __launch_bounds__(256, 1) k_integrate(const __grid_constant__ Tc
 
             double dy[4] = {0, 0, 0, 0};
             TcrRhsAux aux = {0, 0, 0};
-            if (ev) { tcr_rhs(cx, ym, cf, stride, hbl, te, ye, dy, aux); ++nfev; }
+            if (ev) { tcr_rhs(cx, ym, ftab, hbl, te, ye, dy, aux); ++nfev; }
 
             /* ---- consume ---- */
             if (mode == M_RK) {
@@ -600,7 +669,7 @@ __global__ void __launch_bounds__(256, 1) k_integrate(const __grid_constant__ Tc
 struct PostArgs {
     int64_t n;                          /* storms if list == NULL */
     const int32_t* list; const unsigned int* list_count;
-    const int32_t* ym; const double2* coef; const double* track;
+    const int32_t* ym; const double* ftab; const double* track;
     const int32_t* n_time; const int32_t* status;
     double* env;                        /* [n][n_steps][4] */
     double* vmax;                       /* [n][n_steps]    */
@@ -609,7 +678,6 @@ struct PostArgs {
 
 __global__ void __launch_bounds__(128) k_postprocess(const __grid_constant__ TcrCtx cx, const PostArgs A)
 {
-    __shared__ double2 cfs[TCR_N_PHASES];
     __shared__ unsigned long long best_bits;
     __shared__ int have;
     const tcr_params& p = cx.p;
@@ -620,11 +688,11 @@ __global__ void __launch_bounds__(128) k_postprocess(const __grid_constant__ Tcr
         const int nt = A.n_time[sid];
         if (nt <= 0 || A.status[sid] == TCR_STATUS_VENT) continue;
         __syncthreads();
-        if (threadIdx.x < TCR_N_PHASES) cfs[threadIdx.x] = A.coef[(size_t)sid * TCR_N_PHASES + threadIdx.x];
         if (threadIdx.x == 0) { best_bits = 0ull; have = 0; }
         __syncthreads();
         const int ym = A.ym[sid];
         const double* trk = A.track + (size_t)sid * ns * 4;
+        const double* ftab = A.ftab + (size_t)sid * ns * 4;
         double* env = A.env + (size_t)sid * ns * 4;
         double* vmx = A.vmax + (size_t)sid * ns;
         for (int k = threadIdx.x; k < nt; k += blockDim.x) {
@@ -634,9 +702,11 @@ __global__ void __launch_bounds__(128) k_postprocess(const __grid_constant__ Tcr
             const double tk = tcr_node_time(cx, k);
             double w[4] = {0.0, 0.0, 0.0, 0.0};
             if (!(tcr_isnan(lon) || tcr_isnan(tk))) {
+                TcrFsNodes fsn;
+                tcr_fs_begin(cx, ftab, tk, fsn);
                 TcrCell c;
                 tcr_cell_at(cx.tab.lon, cx.tab.lat, lon, lat, c);
-                tcr_env_winds_cell(cx, tcr_record(cx.tab, ym, c), c, cfs, 1, tk, w);
+                tcr_env_winds_cell(cx, tcr_record(cx.tab, ym, c), c, fsn, tk, w);
             }
             double2* ed = reinterpret_cast<double2*>(env + (size_t)k * 4);
             ed[0] = make_double2(w[0], w[1]);

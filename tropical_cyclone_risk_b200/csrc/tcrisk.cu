@@ -78,7 +78,7 @@ struct Workspace {
     DevBuf code, basin, month, att_slot;                       /* per attempt */
     DevBuf s_ym, s_lon, s_lat, s_v0, s_m0, s_hbl, s_att, s_key; /* per slot */
     DevBuf n_time, status, nfev, flags, cand;
-    DevBuf coef, track, env, vmax;
+    DevBuf coef, ftab, track, env, vmax;
     DevBuf counters;       /* [0] queue (u64), [1] n_slots (u32 @+8), [2] cand_count (u32 @+12) */
     DevBuf year_i64;       /* wave_off [ny+1], k0 [ny] */
     DevBuf year_i32;       /* ym_base [ny], year_key [ny], nt [ny] */
@@ -87,7 +87,7 @@ struct Workspace {
     void release_all()
     {
         DevBuf* all[] = {&code, &basin, &month, &att_slot, &s_ym, &s_lon, &s_lat, &s_v0, &s_m0, &s_hbl, &s_att, &s_key,
-                         &n_time, &status, &nfev, &flags, &cand, &coef, &track, &env, &vmax, &counters, &year_i64,
+                         &n_time, &status, &nfev, &flags, &cand, &coef, &ftab, &track, &env, &vmax, &counters, &year_i64,
                          &year_i32, &row_slot, &stats, &out};
         for (DevBuf* b : all) b->release();
         cap = 0;
@@ -108,12 +108,13 @@ struct tcr_handle {
     AxisBuf ax_lon, ax_lat;
     int nlat = 0, nlon = 0, n_ym = 0;
     size_t month_f4 = 0;
+    DevBuf sincos;               /* [n_steps][15] double2, storm-independent harmonics */
     /* static */
     DevBuf bathy, land, masks;
     AxisBuf ax_lon_b, ax_lat_b, ax_lon_l, ax_lat_l, ax_lon_m, ax_lat_m;
     bool have_static = false, have_masks = false;
     /* tuning */
-    int ctas_per_sm = 1, threads_per_cta = 224, oversub_permille = 1100, interp_variant = 0;
+    int integ_variant = 0, oversub_permille = 1100, interp_variant = 0;
     int64_t max_wave = 0;
     Workspace ws;
     void* pinned = nullptr;      /* small pinned read-back area */
@@ -169,10 +170,10 @@ static int make_axis(tcr_handle* h, const double* host, int n, AxisBuf& ab, TcrA
         if (!(host[i] > host[i - 1])) return set_err("axis must be strictly ascending (index %d)", i);
     DevBuf tmp;
     if (tmp.ensure(sizeof(double) * n)) return -1;
-    if (ab.buf.ensure(sizeof(double2) * n)) { tmp.release(); return -1; }
+    if (ab.buf.ensure(sizeof(TcrNode) * n)) { tmp.release(); return -1; }
     cudaError_t e = cudaMemcpyAsync(tmp.p, host, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
-        k_build_axis<<<(n + 255) / 256, 256, 0, h->stream>>>(tmp.as<double>(), ab.buf.as<double2>(), n);
+        k_build_axis<<<(n + 255) / 256, 256, 0, h->stream>>>(tmp.as<double>(), ab.buf.as<TcrNode>(), n);
         e = cudaGetLastError();
         h->launches++;
     }
@@ -180,7 +181,7 @@ static int make_axis(tcr_handle* h, const double* host, int n, AxisBuf& ab, TcrA
     tmp.release();
     if (e != cudaSuccess) return set_err("axis upload failed: %s", cudaGetErrorString(e));
     ab.n = n;
-    ax.a = ab.buf.as<double2>();
+    ax.a = ab.buf.as<TcrNode>();
     ax.n = n;
     ax.lo = host[0];
     ax.hi = host[n - 1];
@@ -220,6 +221,17 @@ int tcr_create(int device, const tcr_params* p, tcr_handle** out)
     h->ctx.p = *p;
     h->ctx.t_step = p->total_time / (double)(p->n_steps - 1);
     if (cudaMallocHost(&h->pinned, 1 << 16) != cudaSuccess) { delete h; return set_err("cudaMallocHost failed"); }
+    if (h->sincos.ensure((size_t)p->n_steps * TCR_N_HARM * sizeof(double2))) { cudaFreeHost(h->pinned); delete h; return -1; }
+    h->ctx.sc = h->sincos.as<double2>();
+    k_build_sincos<<<(p->n_steps + 127) / 128, 128, 0, h->stream>>>(h->ctx, h->sincos.as<double2>());
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+        set_err("tcr_create: harmonic table build failed: %s", cudaGetErrorString(e));
+        h->sincos.release(); cudaFreeHost(h->pinned); delete h;
+        return -1;
+    }
+    h->launches++;
     *out = h;
     return 0;
 }
@@ -230,7 +242,7 @@ int tcr_destroy(tcr_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     h->ws.release_all();
-    DevBuf* bufs[] = {&h->rec, &h->stage, &h->bathy, &h->land, &h->masks};
+    DevBuf* bufs[] = {&h->rec, &h->stage, &h->bathy, &h->land, &h->masks, &h->sincos};
     for (DevBuf* b : bufs) b->release();
     AxisBuf* axs[] = {&h->ax_lon, &h->ax_lat, &h->ax_lon_b, &h->ax_lat_b, &h->ax_lon_l, &h->ax_lat_l, &h->ax_lon_m, &h->ax_lat_m};
     for (AxisBuf* a : axs) a->buf.release();
@@ -256,13 +268,12 @@ int tcr_synchronize(tcr_handle* h)
     return 0;
 }
 
-int tcr_set_tuning(tcr_handle* h, int ctas_per_sm, int threads_per_cta, int64_t max_wave_cands, int oversub_permille)
+int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int oversub_permille)
 {
     if (!h) return set_err("null handle");
-    if (ctas_per_sm > 0) h->ctas_per_sm = ctas_per_sm;
-    if (threads_per_cta > 0) {
-        if (threads_per_cta % 32 || threads_per_cta > 256) return set_err("threads_per_cta must be a multiple of 32, <= 256");
-        h->threads_per_cta = threads_per_cta;
+    if (integ_variant > 0) {
+        if (integ_variant > 4) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
+        h->integ_variant = integ_variant - 1;
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
     if (oversub_permille > 0) h->oversub_permille = oversub_permille;
@@ -472,7 +483,7 @@ int tcr_env_interp(tcr_handle* h, int64_t n, const int32_t* ym, const double* lo
 }
 
 /* ---- workspace ----------------------------------------------------------------------------- */
-static size_t slot_bytes(int ns) { return 960 + (size_t)ns * 72 + 96; }
+static size_t slot_bytes(int ns) { return 960 + (size_t)ns * 104 + 96; }
 
 static int ws_ensure(tcr_handle* h, int64_t cap, int n_years)
 {
@@ -486,7 +497,7 @@ static int ws_ensure(tcr_handle* h, int64_t cap, int n_years)
             w.s_m0.ensure(c * 8) || w.s_hbl.ensure(c * 8) || w.s_att.ensure(c * 8) || w.s_key.ensure(c * 4) ||
             w.n_time.ensure(c * 4) || w.status.ensure(c * 4) || w.nfev.ensure(c * 4) || w.flags.ensure(c * 4) ||
             w.cand.ensure(c * 4) || w.coef.ensure(c * TCR_N_PHASES * sizeof(double2)) ||
-            w.track.ensure(c * ns * 32) || w.env.ensure(c * ns * 32) || w.vmax.ensure(c * ns * 8))
+            w.ftab.ensure(c * ns * 32) || w.track.ensure(c * ns * 32) || w.env.ensure(c * ns * 32) || w.vmax.ensure(c * ns * 8))
             return -1;
         w.cap = cap;
     }
@@ -496,25 +507,50 @@ static int ws_ensure(tcr_handle* h, int64_t cap, int n_years)
     return 0;
 }
 
-static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
+/* Fourier tables of slots [0, n) (n on the host) or [0, *n_dev) */
+static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned int* n_dev)
 {
-    const int bd = h->threads_per_cta;
-    const size_t smem = (size_t)TCR_N_PHASES * bd * sizeof(double2);
-    if (smem > h->smem_optin) return set_err("integrate kernel needs %zu B shared memory, device allows %zu", smem, h->smem_optin);
-    CK(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int warps_per_cta = bd / 32;
-    int64_t max_ctas = (int64_t)h->num_sms * h->ctas_per_sm;
-    int64_t want_ctas = (n_upper + warps_per_cta - 1) / warps_per_cta;       /* one storm per warp at least */
-    int grid = (int)std::max<int64_t>(1, std::min(max_ctas, want_ctas));
-    int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
-    a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
+    Workspace& w = h->ws;
+    const int ns = h->ctx.p.n_steps;
+    dim3 grid((unsigned)((ns + FT_THREADS - 1) / FT_THREADS),
+              (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_upper + FT_STORMS - 1) / FT_STORMS, (int64_t)h->num_sms * 8)));
     {
-        LaunchTimer lt_(h, TCR_K_INTEGRATE);
-        k_integrate<<<grid, bd, smem, h->stream>>>(h->ctx, a);
+        LaunchTimer lt_(h, TCR_K_FTABLE);
+        k_fourier_table<<<grid, FT_THREADS, 0, h->stream>>>(h->ctx, n_upper, n_dev, w.coef.as<double2>(), w.ftab.as<double>());
     }
     CKK(h);
     return 0;
 }
+
+}  // extern "C"
+
+template <int THREADS, int MINB>
+static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_upper)
+{
+    const int warps_per_cta = THREADS / 32;
+    int64_t max_ctas = (int64_t)h->num_sms * MINB;
+    int64_t want_ctas = (n_upper + warps_per_cta - 1) / warps_per_cta;       /* one storm per warp at least */
+    int grid = (int)std::max<int64_t>(1, std::min(max_ctas, want_ctas));
+    int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
+    a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
+    LaunchTimer lt_(h, TCR_K_INTEGRATE);
+    k_integrate<THREADS, MINB><<<grid, THREADS, 0, h->stream>>>(h->ctx, a);
+}
+
+static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
+{
+    switch (h->integ_variant) {
+    case 0: launch_integrate_variant<256, 1>(h, a, n_upper); break;
+    case 1: launch_integrate_variant<128, 3>(h, a, n_upper); break;
+    case 2: launch_integrate_variant<128, 4>(h, a, n_upper); break;
+    case 3: launch_integrate_variant<160, 2>(h, a, n_upper); break;
+    default: return set_err("unknown integrate variant %d", h->integ_variant);
+    }
+    CKK(h);
+    return 0;
+}
+
+extern "C" {
 
 /* ---- integrate given seeds ------------------------------------------------------------------ */
 int tcr_integrate(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon0, const double* lat0,
@@ -561,16 +597,16 @@ int tcr_integrate(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon
     a.n = n; a.n_dev = nullptr;
     a.ym = w.s_ym.as<int32_t>(); a.lon0 = w.s_lon.as<double>(); a.lat0 = w.s_lat.as<double>();
     a.v0 = w.s_v0.as<double>(); a.m0 = w.s_m0.as<double>(); a.h_bl = w.s_hbl.as<double>();
-    a.coef = w.coef.as<double2>(); a.track = w.track.as<double>();
+    a.ftab = w.ftab.as<double>(); a.track = w.track.as<double>();
     a.n_time = w.n_time.as<int32_t>(); a.status = w.status.as<int32_t>(); a.nfev = w.nfev.as<int32_t>();
     a.flags = w.flags.as<uint32_t>();
     a.queue = w.counters.as<unsigned long long>();
     a.cand_list = nullptr; a.cand_count = nullptr;
-    if (launch_integrate(h, a, n)) { ph.release(); return -1; }
+    if (launch_fourier_table(h, n, nullptr) || launch_integrate(h, a, n)) { ph.release(); return -1; }
     PostArgs pa;
     memset(&pa, 0, sizeof pa);
     pa.n = n; pa.list = nullptr; pa.list_count = nullptr;
-    pa.ym = a.ym; pa.coef = a.coef; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
+    pa.ym = a.ym; pa.ftab = a.ftab; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
     pa.env = w.env.as<double>(); pa.vmax = w.vmax.as<double>(); pa.flags = a.flags;
     {
         LaunchTimer lt_(h, TCR_K_POSTPROCESS);
@@ -652,7 +688,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     const size_t out_bytes = on_device ? 0 : rows * ns * 72 + rows * 12 + (size_t)n_years * 84 * 8;
-    size_t budget = std::min<size_t>((size_t)32 << 30, (free_b + h->ws.track.bytes + h->ws.env.bytes + h->ws.vmax.bytes + h->ws.coef.bytes) / 2);
+    size_t budget = std::min<size_t>((size_t)32 << 30, (free_b + h->ws.track.bytes + h->ws.ftab.bytes + h->ws.env.bytes + h->ws.vmax.bytes + h->ws.coef.bytes) / 2);
     if (budget > out_bytes) budget -= out_bytes;
     int64_t cap = (int64_t)(budget / slot_bytes(ns));
     if (h->max_wave > 0) cap = std::min(cap, h->max_wave);
@@ -760,16 +796,16 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         memset(&a, 0, sizeof a);
         a.n = 0; a.n_dev = d_nslots;
         a.ym = sa.s_ym; a.lon0 = sa.s_lon; a.lat0 = sa.s_lat; a.v0 = sa.s_v0; a.m0 = sa.s_m0; a.h_bl = sa.s_hbl;
-        a.coef = w.coef.as<double2>(); a.track = w.track.as<double>();
+        a.ftab = w.ftab.as<double>(); a.track = w.track.as<double>();
         a.n_time = w.n_time.as<int32_t>(); a.status = w.status.as<int32_t>(); a.nfev = w.nfev.as<int32_t>();
         a.flags = w.flags.as<uint32_t>();
         a.queue = d_queue; a.cand_list = w.cand.as<int32_t>(); a.cand_count = d_ncand;
-        if (launch_integrate(h, a, total)) return -1;
+        if (launch_fourier_table(h, total, d_nslots) || launch_integrate(h, a, total)) return -1;
 
         PostArgs pa;
         memset(&pa, 0, sizeof pa);
         pa.n = 0; pa.list = w.cand.as<int32_t>(); pa.list_count = d_ncand;
-        pa.ym = a.ym; pa.coef = a.coef; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
+        pa.ym = a.ym; pa.ftab = a.ftab; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
         pa.env = w.env.as<double>(); pa.vmax = w.vmax.as<double>(); pa.flags = a.flags;
         {
             LaunchTimer lt_(h, TCR_K_POSTPROCESS);

@@ -74,8 +74,10 @@ class Engine:
     def synchronize(self):
         _lib.check(self.lib.tcr_synchronize(self._h))
 
-    def set_tuning(self, ctas_per_sm=0, threads_per_cta=0, max_wave=0, oversub_permille=0):
-        _lib.check(self.lib.tcr_set_tuning(self._h, ctas_per_sm, threads_per_cta, max_wave, oversub_permille))
+    def set_tuning(self, integ_variant=0, max_wave=0, oversub_permille=0):
+        """0 keeps a knob: integrate-kernel register variant (1: 256 thr x 1 CTA/SM, 2: 128 x 3,
+        3: 128 x 4), seed attempts per wave, wave over-subscription (x1000)."""
+        _lib.check(self.lib.tcr_set_tuning(self._h, integ_variant, max_wave, oversub_permille))
 
     def set_interp_variant(self, variant):
         _lib.check(self.lib.tcr_set_interp_variant(self._h, int(variant)))
@@ -84,7 +86,7 @@ class Engine:
     def launch_count(self):
         return int(self.lib.tcr_launch_count(self._h))
 
-    KERNEL_CLASSES = ("env_interp", "integrate", "postprocess", "seed", "coef", "select", "gather", "build")
+    KERNEL_CLASSES = ("env_interp", "integrate", "postprocess", "seed", "coef", "select", "gather", "build", "ftable")
 
     def set_timing(self, enable=True):
         """CUDA-event accounting of every kernel class on the handle's stream (resets the totals)."""
