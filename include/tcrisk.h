@@ -179,9 +179,11 @@ int tcr_seed_attempts(tcr_handle* h, int ym_base, int32_t year_key, uint32_t run
                       double* lon, double* lat, double* v0, double* m0, double* pi_gen);
 
 /* tuning knobs (0 keeps the default): register-budget variant of the integrate kernel
- * (1 = 256 threads x 1 CTA/SM, 2 = 128 x 3, 3 = 128 x 4), seed attempts per wave, wave
- * over-subscription factor (x1000)                                                          */
-int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int oversub_permille);
+ * (1 = 256 threads x 1 CTA/SM, 2 = 128 x 3, 3 = 128 x 4, 4 = 160 x 2), upper bounds on the seed
+ * attempts and on the integrated storms of one wave, wave over-subscription factor (x1000).
+ * Results never depend on these (ordered selection); only the amount of discarded work does.  */
+int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int64_t max_wave_slots,
+                   int oversub_permille);
 /* number of kernels launched by this handle so far (bench.py's gpu_launches)               */
 int64_t tcr_launch_count(tcr_handle* h);
 /* device-time accounting: with timing enabled every launch of a kernel class is bracketed by

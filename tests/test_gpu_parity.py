@@ -291,9 +291,18 @@ def test_run_years_independent_of_wave_size(na_year, na_year_eng):
     a = na_year_eng.run_years([0, 0], [2001, 2005], 5, 50)
     na_year_eng.set_tuning(max_wave=4096, oversub_permille=1500)
     b = na_year_eng.run_years([0, 0], [2001, 2005], 5, 50)
-    na_year_eng.set_tuning(max_wave=1 << 40, oversub_permille=1100)
+    # slot capacity far below what a wave's attempts produce: ranges are cut and re-issued
+    na_year_eng.set_tuning(max_wave=16384, max_slots=300, oversub_permille=1100)
+    c2 = na_year_eng.run_years([0, 0], [2001, 2005], 5, 50)
+    na_year_eng.set_tuning(max_wave=1 << 40, max_slots=1 << 40, oversub_permille=1100)
+    d = na_year_eng.run_years([0, 0], [2001, 2005], 5, 50)          # first wave sized by the survival hint
     for key in ("lon", "lat", "v", "m", "vmax", "env", "tc_month", "tc_basin", "n_seeds"):
         assert _same(a[key], b[key]), key
+        assert _same(a[key], c2[key]), key
+        assert _same(a[key], d[key]), key
+    for sa, sc in zip(a["stats"], c2["stats"]):
+        for key in ("attempts", "counted_seeds", "integrated", "storm_steps", "kept_steps", "rhs_evals", "n_kept"):
+            assert sa[key] == sc[key], key
     for sa, sb in zip(a["stats"], b["stats"]):
         for key in ("attempts", "counted_seeds", "integrated", "storm_steps", "kept_steps", "rhs_evals", "n_kept"):
             assert sa[key] == sb[key]

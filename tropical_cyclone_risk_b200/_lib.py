@@ -52,7 +52,7 @@ def load():
     lib.tcr_integrate.argtypes = [vp, C.c_int64] + [vp] * 14 + [C.c_int]
     lib.tcr_run_years.argtypes = [vp, C.c_int, vp, vp, C.c_uint32, C.c_int] + [vp] * 9 + [C.POINTER(TcrYearStats), C.c_int]
     lib.tcr_seed_attempts.argtypes = [vp, C.c_int, C.c_int32, C.c_uint32, C.c_int64, C.c_int64] + [vp] * 8
-    lib.tcr_set_tuning.argtypes = [vp, C.c_int, C.c_int64, C.c_int]
+    lib.tcr_set_tuning.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, C.c_int]
     lib.tcr_launch_count.argtypes = [vp]
     lib.tcr_launch_count.restype = C.c_int64
     lib.tcr_set_interp_variant.argtypes = [vp, C.c_int]

@@ -780,12 +780,8 @@ struct SeedArgs {
     uint32_t run_seed;
     /* per attempt (flat) */
     int32_t* code; int32_t* basin; int32_t* month;
-    double* lon; double* lat; double* v0; double* m0; double* pi_gen;      /* may be NULL */
-    int32_t* att_slot;                  /* slot of an integrated attempt, -1 otherwise (may be NULL) */
-    /* per slot (compaction of code == 2 attempts; may be NULL) */
-    unsigned int* n_slots;
-    int32_t* s_ym; double* s_lon; double* s_lat; double* s_v0; double* s_m0; double* s_hbl;
-    int64_t* s_att; int32_t* s_key;
+    double* lon; double* lat; double* v0; double* m0; double* pi_gen;      /* pi_gen may be NULL */
+    unsigned int* blk_count;            /* [gridDim.x] attempts of the block that go on to gen_track (may be NULL) */
 };
 
 __device__ __forceinline__ double tcr_mask_at(const uint2 r[4], int b, const TcrCell& c)
@@ -863,27 +859,112 @@ __global__ void __launch_bounds__(256) k_seed(const __grid_constant__ TcrCtx cx,
         else if (best > 1e-3 && r_lowlat < prob) code = pi > p.pi_gen_min ? 2 : 1;
         else code = 0;
         A.code[idx] = code; A.basin[idx] = bi; A.month[idx] = mon;
-        if (A.lon) { A.lon[idx] = gen_lon; A.lat[idx] = gen_lat; A.v0[idx] = v0; A.m0[idx] = m0; A.pi_gen[idx] = pi; }
+        A.lon[idx] = gen_lon; A.lat[idx] = gen_lat; A.v0[idx] = v0; A.m0[idx] = m0;
+        if (A.pi_gen) A.pi_gen[idx] = pi;
     }
-    if (A.n_slots) {
-        /* warp-aggregated compaction of the attempts that go on to gen_track */
+    if (A.blk_count) {
+        __shared__ unsigned int s_cnt;
+        if (threadIdx.x == 0) s_cnt = 0u;
+        __syncthreads();
         const unsigned pass = __ballot_sync(TCR_FULL, code == 2);
-        if (pass) {
-            const int lane = threadIdx.x & 31, leader = __ffs(pass) - 1;
-            unsigned int base = 0;
-            if (lane == leader) base = atomicAdd(A.n_slots, (unsigned int)__popc(pass));
-            base = __shfl_sync(TCR_FULL, base, leader);
-            if (code == 2) {
-                const unsigned int s = base + __popc(pass & ((1u << lane) - 1u));
-                A.s_ym[s] = A.ym_base[yr] + mon - 1;
-                A.s_lon[s] = gen_lon; A.s_lat[s] = gen_lat; A.s_v0[s] = v0; A.s_m0[s] = m0;
-                A.s_hbl[s] = p.atm_bl_depth[bi];
-                A.s_att[s] = k; A.s_key[s] = A.year_key[yr];
-                A.att_slot[idx] = (int32_t)s;
-            }
-        }
-        if (idx < total && code != 2) A.att_slot[idx] = -1;
+        if ((threadIdx.x & 31) == 0 && pass) atomicAdd(&s_cnt, (unsigned int)__popc(pass));
+        __syncthreads();
+        if (threadIdx.x == 0) A.blk_count[blockIdx.x] = s_cnt;
     }
+}
+
+/* exclusive scan of the seed blocks' pass counts (one CTA) -> blk_off; n_slots = min(total,
+ * slot_cap); consumed[y] = W_y (k_assign_slots lowers it where the slot capacity runs out)   */
+__global__ void __launch_bounds__(1024) k_scan_counts(const unsigned int* __restrict__ blk_count, unsigned int* __restrict__ blk_off,
+                                                      int n_blocks, unsigned int slot_cap, unsigned int* __restrict__ n_slots,
+                                                      unsigned int* __restrict__ n_pass, const int64_t* __restrict__ wave_off,
+                                                      int n_years, int64_t* __restrict__ consumed)
+{
+    __shared__ unsigned int warp_tot[32];
+    __shared__ unsigned int s_run;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) s_run = 0u;
+    for (int y = tid; y < n_years; y += blockDim.x) consumed[y] = wave_off[y + 1] - wave_off[y];
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += 1024 * 4) {
+        unsigned int v[4], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int i = base + tid * 4 + j;
+            v[j] = i < n_blocks ? blk_count[i] : 0u;
+            sum += v[j];
+        }
+        unsigned int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { unsigned int u = __shfl_up_sync(TCR_FULL, incl, d); if (lane >= d) incl += u; }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned int t = warp_tot[lane], sc = t;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { unsigned int u = __shfl_up_sync(TCR_FULL, sc, d); if (lane >= d) sc += u; }
+            warp_tot[lane] = sc - t;
+        }
+        __syncthreads();
+        unsigned int off = s_run + warp_tot[wid] + incl - sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int i = base + tid * 4 + j;
+            if (i < n_blocks) blk_off[i] = off;
+            off += v[j];
+        }
+        __syncthreads();
+        if (tid == 1023) s_run = off;
+        __syncthreads();
+    }
+    if (tid == 0) { *n_pass = s_run; *n_slots = s_run < slot_cap ? s_run : slot_cap; }
+}
+
+/* slots in ATTEMPT ORDER (year-major): slot = rank of the attempt among the wave's integrated
+ * attempts.  Attempts whose slot would exceed the capacity are not integrated in this wave
+ * (att_slot = -2) and the year's consumed range is cut at the first of them.  Same launch
+ * geometry as k_seed (blk_off is per k_seed block).                                          */
+struct AssignArgs {
+    int n_years;
+    const int64_t* wave_off; const int64_t* k0;
+    const int32_t* ym_base; const int32_t* year_key;
+    const int32_t* code; const int32_t* basin; const int32_t* month;
+    const double* lon; const double* lat; const double* v0; const double* m0;
+    const unsigned int* blk_off; unsigned int slot_cap;
+    int32_t* att_slot; int64_t* consumed;
+    int32_t* s_ym; double* s_lon; double* s_lat; double* s_v0; double* s_m0; double* s_hbl;
+    int64_t* s_att; int32_t* s_key;
+};
+
+__global__ void __launch_bounds__(256) k_assign_slots(const __grid_constant__ TcrCtx cx, const AssignArgs A)
+{
+    __shared__ unsigned int warp_cnt[8];
+    const int64_t total = A.wave_off[A.n_years];
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int code = idx < total ? A.code[idx] : -1;
+    const unsigned pass = __ballot_sync(TCR_FULL, code == 2);
+    if (lane == 0) warp_cnt[wid] = (unsigned int)__popc(pass);
+    __syncthreads();
+    if (idx >= total) return;
+    if (code != 2) { A.att_slot[idx] = -1; return; }
+    unsigned int rank = __popc(pass & ((1u << lane) - 1u));
+    for (int w = 0; w < wid; ++w) rank += warp_cnt[w];
+    const unsigned int s = A.blk_off[blockIdx.x] + rank;
+    int yr = 0;
+    while (yr + 1 < A.n_years && idx >= A.wave_off[yr + 1]) ++yr;
+    if (s >= A.slot_cap) {
+        A.att_slot[idx] = -2;
+        atomicMin(reinterpret_cast<unsigned long long*>(A.consumed + yr), (unsigned long long)(idx - A.wave_off[yr]));
+        return;
+    }
+    const int bi = A.basin[idx], mon = A.month[idx];
+    A.att_slot[idx] = (int32_t)s;
+    A.s_ym[s] = A.ym_base[yr] + mon - 1;
+    A.s_lon[s] = A.lon[idx]; A.s_lat[s] = A.lat[idx]; A.s_v0[s] = A.v0[idx]; A.s_m0[s] = A.m0[idx];
+    A.s_hbl[s] = cx.p.atm_bl_depth[bi];
+    A.s_att[s] = A.k0[yr] + (idx - A.wave_off[yr]);
+    A.s_key[s] = A.year_key[yr];
 }
 
 /* ======================================================================================== */
@@ -893,14 +974,17 @@ __global__ void __launch_bounds__(256) k_seed(const __grid_constant__ TcrCtx cx,
 struct SelectArgs {
     int n_tracks;
     const int64_t* wave_off; const int64_t* k0;
+    const int64_t* consumed;    /* [n_years] attempts of the year's range that were fully processed   */
     const int32_t* code; const int32_t* basin; const int32_t* month; const int32_t* att_slot;
     const int32_t* n_time; const int32_t* nfev; const uint32_t* flags;
     int32_t* nt;                /* [n_years] kept so far (in/out)                              */
+    int64_t* used;              /* [n_years] attempts consumed by this wave: i*+1, or consumed[y] */
     int32_t* row_slot;          /* [n_years][n_tracks] slot of a row assigned in THIS wave, else -1 */
     double* tc_month; int32_t* tc_basin; double* n_seeds;    /* outputs (device)               */
     tcr_year_stats* stats;      /* [n_years] device accumulators                               */
 };
 
+#define SEL_ITEMS 4
 __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
 {
     __shared__ int warp_tot[32];
@@ -909,44 +993,55 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
     __shared__ unsigned int s_hist[TCR_N_BASINS * 12];
     const int yr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t off = A.wave_off[yr];
-    const int64_t W = A.wave_off[yr + 1] - off;
+    const int64_t W = A.consumed[yr];
     for (int r = tid; r < A.n_tracks; r += blockDim.x) A.row_slot[(size_t)yr * A.n_tracks + r] = -1;
-    if (W == 0) return;
+    if (W == 0) { if (tid == 0) A.used[yr] = 0; return; }
     const int nt0 = A.nt[yr];
     const int want = A.n_tracks - nt0;
     if (tid == 0) { s_running = 0; s_istar = -1; }
     if (tid < 7) s_acc[tid] = 0ull;
     for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) s_hist[i] = 0u;
     __syncthreads();
-    /* pass 1: rank the kept storms in attempt order, find i* = attempt of the want-th kept */
-    for (int64_t base = 0; base < W; base += blockDim.x) {
-        const int64_t i = base + tid;
-        int kept = 0, slot = -1;
-        if (i < W) {
-            slot = A.att_slot[off + i];
-            if (slot >= 0 && (A.flags[slot] & TCR_FLAG_KEPT)) kept = 1;
+    /* pass 1: rank the kept storms in attempt order, find i* = attempt of the want-th kept.
+     * Each thread owns SEL_ITEMS consecutive attempts of a 4096-attempt chunk. */
+    for (int64_t base = 0; base < W; base += (int64_t)blockDim.x * SEL_ITEMS) {
+        int kept[SEL_ITEMS], slot[SEL_ITEMS], cnt = 0;
+#pragma unroll
+        for (int j = 0; j < SEL_ITEMS; ++j) {
+            const int64_t i = base + (int64_t)tid * SEL_ITEMS + j;
+            kept[j] = 0; slot[j] = -1;
+            if (i < W) {
+                slot[j] = A.att_slot[off + i];
+                if (slot[j] >= 0 && (A.flags[slot[j]] & TCR_FLAG_KEPT)) kept[j] = 1;
+            }
+            cnt += kept[j];
         }
-        int incl = kept;
+        int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(TCR_FULL, incl, d); if (lane >= d) incl += v; }
         if (lane == 31) warp_tot[wid] = incl;
         __syncthreads();
         if (wid == 0) {
-            int v = warp_tot[lane], s = v;
+            int v = warp_tot[lane], sc = v;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(TCR_FULL, s, d); if (lane >= d) s += u; }
-            warp_tot[lane] = s - v;
+            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(TCR_FULL, sc, d); if (lane >= d) sc += u; }
+            warp_tot[lane] = sc - v;
         }
         __syncthreads();
-        const int run0 = s_running;
-        const int rank = run0 + warp_tot[wid] + incl;             /* 1-based rank of this kept storm */
-        if (kept && rank <= want) {
-            const int row = nt0 + rank - 1;
-            A.row_slot[(size_t)yr * A.n_tracks + row] = slot;
-            A.tc_month[(size_t)yr * A.n_tracks + row] = (double)A.month[off + i];
-            A.tc_basin[(size_t)yr * A.n_tracks + row] = A.basin[off + i];
-            atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot]);
-            if (rank == want) s_istar = (int)i;
+        int rank = s_running + warp_tot[wid] + incl - cnt;          /* kept storms before this thread's items */
+#pragma unroll
+        for (int j = 0; j < SEL_ITEMS; ++j) {
+            if (!kept[j]) continue;
+            ++rank;                                                  /* 1-based rank of this kept storm */
+            if (rank <= want) {
+                const int64_t i = base + (int64_t)tid * SEL_ITEMS + j;
+                const int row = nt0 + rank - 1;
+                A.row_slot[(size_t)yr * A.n_tracks + row] = slot[j];
+                A.tc_month[(size_t)yr * A.n_tracks + row] = (double)A.month[off + i];
+                A.tc_basin[(size_t)yr * A.n_tracks + row] = A.basin[off + i];
+                atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot[j]]);
+                if (rank == want) s_istar = (int)i;
+            }
         }
         __syncthreads();
         if (tid == blockDim.x - 1) s_running = rank;
@@ -965,6 +1060,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
             if (slot >= 0) { ++integ; steps += (unsigned long long)A.n_time[slot]; rhs += (unsigned long long)A.nfev[slot]; }
         } else if (slot >= 0) { ++w_integ; w_steps += (unsigned long long)A.n_time[slot]; w_rhs += (unsigned long long)A.nfev[slot]; }
     }
+    /* slots of this year beyond the consumed range (capacity cut) were never integrated */
     atomicAdd(&s_acc[0], counted); atomicAdd(&s_acc[1], integ); atomicAdd(&s_acc[2], steps);
     atomicAdd(&s_acc[3], rhs); atomicAdd(&s_acc[5], (w_integ << 40) | w_steps); atomicAdd(&s_acc[6], w_rhs);
     __syncthreads();
@@ -985,6 +1081,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
         s.n_kept = nt0 + got;
         s.n_waves += 1;
         A.nt[yr] = nt0 + got;
+        A.used[yr] = last + 1;
     }
 }
 

@@ -71,26 +71,30 @@ struct AxisBuf {
 
 struct TimedSpan { int which; cudaEvent_t a, b; };
 
-/* scratch of tcr_run_years / tcr_integrate, grown on demand and kept in the handle */
+/* scratch of tcr_run_years / tcr_integrate, grown on demand and kept in the handle.  Two
+ * capacities: seed ATTEMPTS per wave (56 B each) and integrated storm SLOTS per wave
+ * (slot_bytes(n_steps) each: Fourier table, track, env winds, vmax).                          */
 struct Workspace {
-    int64_t cap = 0;        /* slots == attempts per wave */
+    int64_t att_cap = 0, slot_cap = 0;
     int ns = 0;
-    DevBuf code, basin, month, att_slot;                       /* per attempt */
-    DevBuf s_ym, s_lon, s_lat, s_v0, s_m0, s_hbl, s_att, s_key; /* per slot */
+    DevBuf code, basin, month, att_slot, a_lon, a_lat, a_v0, a_m0;   /* per attempt */
+    DevBuf blk_count, blk_off;                                       /* per 256-attempt seed block */
+    DevBuf s_ym, s_lon, s_lat, s_v0, s_m0, s_hbl, s_att, s_key;       /* per slot */
     DevBuf n_time, status, nfev, flags, cand;
     DevBuf coef, ftab, track, env, vmax;
-    DevBuf counters;       /* [0] queue (u64), [1] n_slots (u32 @+8), [2] cand_count (u32 @+12) */
-    DevBuf year_i64;       /* wave_off [ny+1], k0 [ny] */
+    DevBuf counters;       /* [0] queue (u64), u32 @+8 n_slots, @+12 cand_count, @+16 n_pass */
+    DevBuf year_i64;       /* wave_off [ny+1], k0 [ny], consumed [ny], used [ny] */
     DevBuf year_i32;       /* ym_base [ny], year_key [ny], nt [ny] */
     DevBuf row_slot, stats;
     DevBuf out;            /* device-side result block when the caller passes host pointers */
     void release_all()
     {
-        DevBuf* all[] = {&code, &basin, &month, &att_slot, &s_ym, &s_lon, &s_lat, &s_v0, &s_m0, &s_hbl, &s_att, &s_key,
+        DevBuf* all[] = {&code, &basin, &month, &att_slot, &a_lon, &a_lat, &a_v0, &a_m0, &blk_count, &blk_off,
+                         &s_ym, &s_lon, &s_lat, &s_v0, &s_m0, &s_hbl, &s_att, &s_key,
                          &n_time, &status, &nfev, &flags, &cand, &coef, &ftab, &track, &env, &vmax, &counters, &year_i64,
                          &year_i32, &row_slot, &stats, &out};
         for (DevBuf* b : all) b->release();
-        cap = 0;
+        att_cap = slot_cap = 0;
     }
 };
 
@@ -115,7 +119,9 @@ struct tcr_handle {
     bool have_static = false, have_masks = false;
     /* tuning */
     int integ_variant = 0, oversub_permille = 1100, interp_variant = 0;
-    int64_t max_wave = 0;
+    /* survival statistics of earlier tcr_run_years calls on this handle: size the first wave */
+    double hint_kept_rate = 0.0, hint_pass_rate = 0.0;
+    int64_t max_wave = 0, max_slots = 0;
     Workspace ws;
     void* pinned = nullptr;      /* small pinned read-back area */
     /* device-time accounting (tcr_set_timing): event pairs around every launch of a kernel class */
@@ -268,7 +274,7 @@ int tcr_synchronize(tcr_handle* h)
     return 0;
 }
 
-int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int oversub_permille)
+int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int64_t max_wave_slots, int oversub_permille)
 {
     if (!h) return set_err("null handle");
     if (integ_variant > 0) {
@@ -276,6 +282,7 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
         h->integ_variant = integ_variant - 1;
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
+    if (max_wave_slots > 0) h->max_slots = max_wave_slots;
     if (oversub_permille > 0) h->oversub_permille = oversub_permille;
     return 0;
 }
@@ -484,26 +491,34 @@ int tcr_env_interp(tcr_handle* h, int64_t n, const int32_t* ym, const double* lo
 
 /* ---- workspace ----------------------------------------------------------------------------- */
 static size_t slot_bytes(int ns) { return 960 + (size_t)ns * 104 + 96; }
+static const size_t kAttemptBytes = 56;
 
-static int ws_ensure(tcr_handle* h, int64_t cap, int n_years)
+static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_years)
 {
     Workspace& w = h->ws;
     const int ns = h->ctx.p.n_steps;
     if (w.ns != ns) { w.release_all(); w.ns = ns; }
-    if (cap > w.cap) {
-        const size_t c = (size_t)cap;
+    if (att_cap > w.att_cap) {
+        const size_t c = (size_t)att_cap, nb = (c + 255) / 256;
         if (w.code.ensure(c * 4) || w.basin.ensure(c * 4) || w.month.ensure(c * 4) || w.att_slot.ensure(c * 4) ||
-            w.s_ym.ensure(c * 4) || w.s_lon.ensure(c * 8) || w.s_lat.ensure(c * 8) || w.s_v0.ensure(c * 8) ||
+            w.a_lon.ensure(c * 8) || w.a_lat.ensure(c * 8) || w.a_v0.ensure(c * 8) || w.a_m0.ensure(c * 8) ||
+            w.blk_count.ensure(nb * 4) || w.blk_off.ensure(nb * 4))
+            return -1;
+        w.att_cap = att_cap;
+    }
+    if (slot_cap > w.slot_cap) {
+        const size_t c = (size_t)slot_cap;
+        if (w.s_ym.ensure(c * 4) || w.s_lon.ensure(c * 8) || w.s_lat.ensure(c * 8) || w.s_v0.ensure(c * 8) ||
             w.s_m0.ensure(c * 8) || w.s_hbl.ensure(c * 8) || w.s_att.ensure(c * 8) || w.s_key.ensure(c * 4) ||
             w.n_time.ensure(c * 4) || w.status.ensure(c * 4) || w.nfev.ensure(c * 4) || w.flags.ensure(c * 4) ||
             w.cand.ensure(c * 4) || w.coef.ensure(c * TCR_N_PHASES * sizeof(double2)) ||
             w.ftab.ensure(c * ns * 32) || w.track.ensure(c * ns * 32) || w.env.ensure(c * ns * 32) || w.vmax.ensure(c * ns * 8))
             return -1;
-        w.cap = cap;
+        w.slot_cap = slot_cap;
     }
     if (w.counters.ensure(64)) return -1;
     const size_t ny = (size_t)std::max(n_years, 1);
-    if (w.year_i64.ensure((2 * ny + 1) * 8) || w.year_i32.ensure(3 * ny * 4) || w.stats.ensure(ny * sizeof(tcr_year_stats))) return -1;
+    if (w.year_i64.ensure((4 * ny + 1) * 8) || w.year_i32.ensure(3 * ny * 4) || w.stats.ensure(ny * sizeof(tcr_year_stats))) return -1;
     return 0;
 }
 
@@ -565,7 +580,7 @@ int tcr_integrate(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon
     if (!h->rec.p || !h->have_static) return set_err("tcr_integrate: tables / static fields not uploaded");
     if (n > 0x7fffffff) return set_err("tcr_integrate: n too large");
     CK(cudaSetDevice(h->device));
-    if (ws_ensure(h, n, 1)) return -1;
+    if (ws_ensure(h, 0, n, 1)) return -1;
     Workspace& w = h->ws;
     const int ns = h->ctx.p.n_steps;
     cudaStream_t s = h->stream;
@@ -652,6 +667,7 @@ int tcr_seed_attempts(tcr_handle* h, int ym_base, int32_t year_key, uint32_t run
     a.run_seed = run_seed;
     a.code = ints.as<int32_t>(); a.basin = a.code + n; a.month = a.basin + n;
     a.lon = dbls.as<double>(); a.lat = a.lon + n; a.v0 = a.lat + n; a.m0 = a.v0 + n; a.pi_gen = a.m0 + n;
+    a.blk_count = nullptr;
     k_seed<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(h->ctx, a);
     CKK(h);
     CK(cudaMemcpyAsync(code, a.code, n * 4, cudaMemcpyDeviceToHost, s));
@@ -684,20 +700,38 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
     const int ns = h->ctx.p.n_steps;
     const size_t rows = (size_t)n_years * n_tracks;
 
-    /* wave capacity: bounded by a memory budget and by what the job can use */
+    /* wave capacity: attempts and slots, bounded by a memory budget and by what the job needs */
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
     const size_t out_bytes = on_device ? 0 : rows * ns * 72 + rows * 12 + (size_t)n_years * 84 * 8;
-    size_t budget = std::min<size_t>((size_t)32 << 30, (free_b + h->ws.track.bytes + h->ws.ftab.bytes + h->ws.env.bytes + h->ws.vmax.bytes + h->ws.coef.bytes) / 2);
-    if (budget > out_bytes) budget -= out_bytes;
-    int64_t cap = (int64_t)(budget / slot_bytes(ns));
-    if (h->max_wave > 0) cap = std::min(cap, h->max_wave);
-    cap = std::min<int64_t>(cap, std::max<int64_t>(65536, (int64_t)rows * 256));
-    cap = std::max<int64_t>(cap, 4096);
-    if (h->ws.ns == ns && h->ws.cap >= 4096 && h->ws.cap >= cap / 2) cap = h->ws.cap;      /* reuse, do not re-allocate */
-    if (ws_ensure(h, cap, n_years)) return -1;
+    {
+        Workspace& w0 = h->ws;
+        size_t held = w0.ftab.bytes + w0.track.bytes + w0.env.bytes + w0.vmax.bytes + w0.coef.bytes + w0.out.bytes;
+        size_t budget = std::min<size_t>((size_t)64 << 30, (size_t)((free_b + held) * 0.6));
+        if (budget > out_bytes) budget -= out_bytes;
+        const bool hinted = h->hint_kept_rate > 0.0;
+        const double pass_est = hinted ? std::min(1.0, h->hint_pass_rate * 1.25 + 0.01) : 0.30;
+        int64_t att_cap = (int64_t)((double)budget / ((double)kAttemptBytes + pass_est * (double)slot_bytes(ns)));
+        /* what the whole job is expected to consume in its first wave */
+        double need = hinted ? (double)rows / h->hint_kept_rate * (h->oversub_permille / 1000.0) + 512.0 * n_years
+                             : (double)rows * 640.0;
+        att_cap = std::min<int64_t>(att_cap, std::max<int64_t>(65536, (int64_t)(need * 1.05)));
+        if (h->max_wave > 0) att_cap = std::min(att_cap, h->max_wave);
+        att_cap = std::max<int64_t>(att_cap, 4096);
+        int64_t slot_cap = std::max<int64_t>(4096, (int64_t)((double)att_cap * pass_est) + 1024);
+        slot_cap = std::min(slot_cap, att_cap);
+        /* reuse a workspace that is big enough for at least half of that; never shrink */
+        if (w0.ns == ns && w0.att_cap >= att_cap / 2 && w0.slot_cap >= slot_cap / 2 && w0.att_cap >= 4096) {
+            att_cap = std::max(w0.att_cap, (int64_t)0); slot_cap = w0.slot_cap;
+            if (h->max_wave > 0) att_cap = std::min(att_cap, h->max_wave);
+        }
+        if (ws_ensure(h, att_cap, slot_cap, n_years)) return -1;
+    }
     Workspace& w = h->ws;
-    cap = w.cap;
+    int64_t cap = w.att_cap;
+    if (h->max_wave > 0) cap = std::min(cap, h->max_wave);
+    int64_t slot_cap = w.slot_cap;
+    if (h->max_slots > 0) slot_cap = std::min(slot_cap, h->max_slots);
     if (w.row_slot.ensure(rows * 4)) return -1;
 
     /* result block on the device */
@@ -712,12 +746,6 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         d_env = d_vmax + rows * ns; d_month = d_env + rows * ns * 4; d_seeds = d_month + rows;
         d_basin = reinterpret_cast<int32_t*>(d_seeds + (size_t)n_years * 84);
     }
-    CK(cudaMemsetAsync(d_lon, 0xff, rows * ns * 8, s));
-    CK(cudaMemsetAsync(d_lat, 0xff, rows * ns * 8, s));
-    CK(cudaMemsetAsync(d_v, 0xff, rows * ns * 8, s));
-    CK(cudaMemsetAsync(d_m, 0xff, rows * ns * 8, s));
-    CK(cudaMemsetAsync(d_vmax, 0xff, rows * ns * 8, s));
-    CK(cudaMemsetAsync(d_env, 0xff, rows * ns * 32, s));
     CK(cudaMemsetAsync(d_month, 0xff, rows * 8, s));
     CK(cudaMemsetAsync(d_basin, 0xff, rows * 4, s));
     CK(cudaMemsetAsync(d_seeds, 0, (size_t)n_years * 84 * 8, s));
@@ -725,6 +753,8 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
 
     int64_t* d_wave_off = w.year_i64.as<int64_t>();
     int64_t* d_k0 = d_wave_off + n_years + 1;
+    int64_t* d_consumed = d_k0 + n_years;
+    int64_t* d_used = d_consumed + n_years;
     int32_t* d_ym_base = w.year_i32.as<int32_t>();
     int32_t* d_key = d_ym_base + n_years;
     int32_t* d_nt = d_key + n_years;
@@ -734,73 +764,98 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
 
     std::vector<int64_t> k0(n_years, 0), W(n_years, 0), att_total(n_years, 0), hoff(2 * n_years + 1, 0);
     std::vector<int32_t> nt(n_years, 0);
+    if ((size_t)n_years * 12 + 32 > (1 << 16)) return set_err("tcr_run_years: too many years in one call (%d)", n_years);
     int32_t* pin_nt = reinterpret_cast<int32_t*>(h->pinned);
-    if ((size_t)n_years * 4 > (1 << 16)) return set_err("tcr_run_years: too many years in one call (%d)", n_years);
+    int64_t* pin_used = reinterpret_cast<int64_t*>(h->pinned) + (n_years + 1) / 2;
 
     unsigned long long* d_queue = w.counters.as<unsigned long long>();
     unsigned int* d_nslots = reinterpret_cast<unsigned int*>(d_queue + 1);
     unsigned int* d_ncand = d_nslots + 1;
+    unsigned int* d_npass = d_nslots + 2;
 
     const int max_waves = 4096;
+    const double oversub = h->oversub_permille / 1000.0;
+    int64_t sum_pass = 0, sum_att_launched = 0;
     int wave = 0;
     for (; wave < max_waves; ++wave) {
         int n_active = 0;
         for (int y = 0; y < n_years; ++y) if (nt[y] < n_tracks) ++n_active;
         if (!n_active) break;
-        const int64_t per_year_cap = std::max<int64_t>(256, cap / n_active);
+        /* attempts wanted per year: remaining tracks / survival rate (this year's own once it has
+         * produced tracks, else the handle's hint, else a probe), over-subscribed */
+        double want_total = 0.0;
+        std::vector<double> want(n_years, 0.0);
+        for (int y = 0; y < n_years; ++y) {
+            if (nt[y] >= n_tracks) continue;
+            const double remaining = (double)(n_tracks - nt[y]);
+            double wy;
+            if (nt[y] > 0) wy = remaining / ((double)nt[y] / (double)att_total[y]) * oversub + 256.0;
+            else if (att_total[y] > 0) wy = (double)att_total[y] * 4.0;
+            else if (h->hint_kept_rate > 0.0) wy = remaining / h->hint_kept_rate * oversub + 256.0;
+            else wy = std::max(2048.0, remaining * 32.0);
+            want[y] = wy;
+            want_total += wy;
+        }
+        const double scale = want_total > (double)cap ? (double)cap / want_total : 1.0;
         int64_t total = 0;
         for (int y = 0; y < n_years; ++y) {
             int64_t wy = 0;
-            if (nt[y] < n_tracks) {
-                const int64_t remaining = n_tracks - nt[y];
-                if (att_total[y] == 0) wy = std::max<int64_t>(2048, remaining * 32);
-                else if (nt[y] == 0) wy = W[y] * 4;
-                else {
-                    double rate = (double)nt[y] / (double)att_total[y];
-                    wy = (int64_t)std::ceil((double)remaining / rate * (h->oversub_permille / 1000.0)) + 256;
-                }
-                wy = std::min(wy, per_year_cap);
-            }
+            if (want[y] > 0.0) wy = std::max<int64_t>(64, (int64_t)(want[y] * scale));
             W[y] = wy;
             hoff[y] = total;
             total += wy;
             hoff[n_years + 1 + y] = k0[y];
         }
         hoff[n_years] = total;
+        if (total > w.att_cap) return set_err("tcr_run_years: internal error: wave of %lld attempts exceeds the workspace", (long long)total);
         CK(cudaMemcpyAsync(d_wave_off, hoff.data(), (2 * n_years + 1) * 8, cudaMemcpyHostToDevice, s));
         CK(cudaMemsetAsync(w.counters.p, 0, 64, s));
+        const unsigned seed_blocks = (unsigned)((total + 255) / 256);
 
         SeedArgs sa;
         memset(&sa, 0, sizeof sa);
         sa.n_years = n_years; sa.wave_off = d_wave_off; sa.k0 = d_k0; sa.ym_base = d_ym_base; sa.year_key = d_key;
         sa.run_seed = run_seed;
         sa.code = w.code.as<int32_t>(); sa.basin = w.basin.as<int32_t>(); sa.month = w.month.as<int32_t>();
-        sa.att_slot = w.att_slot.as<int32_t>();
-        sa.n_slots = d_nslots;
-        sa.s_ym = w.s_ym.as<int32_t>(); sa.s_lon = w.s_lon.as<double>(); sa.s_lat = w.s_lat.as<double>();
-        sa.s_v0 = w.s_v0.as<double>(); sa.s_m0 = w.s_m0.as<double>(); sa.s_hbl = w.s_hbl.as<double>();
-        sa.s_att = w.s_att.as<int64_t>(); sa.s_key = w.s_key.as<int32_t>();
+        sa.lon = w.a_lon.as<double>(); sa.lat = w.a_lat.as<double>(); sa.v0 = w.a_v0.as<double>(); sa.m0 = w.a_m0.as<double>();
+        sa.pi_gen = nullptr;
+        sa.blk_count = w.blk_count.as<unsigned int>();
+        AssignArgs as;
+        memset(&as, 0, sizeof as);
+        as.n_years = n_years; as.wave_off = d_wave_off; as.k0 = d_k0; as.ym_base = d_ym_base; as.year_key = d_key;
+        as.code = sa.code; as.basin = sa.basin; as.month = sa.month;
+        as.lon = sa.lon; as.lat = sa.lat; as.v0 = sa.v0; as.m0 = sa.m0;
+        as.blk_off = w.blk_off.as<unsigned int>(); as.slot_cap = (unsigned int)std::min<int64_t>(slot_cap, 0x7fffffff);
+        as.att_slot = w.att_slot.as<int32_t>(); as.consumed = d_consumed;
+        as.s_ym = w.s_ym.as<int32_t>(); as.s_lon = w.s_lon.as<double>(); as.s_lat = w.s_lat.as<double>();
+        as.s_v0 = w.s_v0.as<double>(); as.s_m0 = w.s_m0.as<double>(); as.s_hbl = w.s_hbl.as<double>();
+        as.s_att = w.s_att.as<int64_t>(); as.s_key = w.s_key.as<int32_t>();
         {
             LaunchTimer lt_(h, TCR_K_SEED);
-            k_seed<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(h->ctx, sa);
+            k_seed<<<seed_blocks, 256, 0, s>>>(h->ctx, sa);
+            k_scan_counts<<<1, 1024, 0, s>>>(sa.blk_count, w.blk_off.as<unsigned int>(), (int)seed_blocks, as.slot_cap,
+                                             d_nslots, d_npass, d_wave_off, n_years, d_consumed);
+            k_assign_slots<<<seed_blocks, 256, 0, s>>>(h->ctx, as);
         }
         CKK(h);
+        h->launches += 2;
+        const int64_t slots_upper = std::min<int64_t>(slot_cap, total);
         {
             LaunchTimer lt_(h, TCR_K_COEF);
-            k_coef_from_philox<<<(unsigned)((total * TCR_N_PHASES + 255) / 256), 256, 0, s>>>(
-                h->ctx, d_nslots, sa.s_att, sa.s_key, run_seed, w.coef.as<double2>());
+            k_coef_from_philox<<<(unsigned)((slots_upper * TCR_N_PHASES + 255) / 256), 256, 0, s>>>(
+                h->ctx, d_nslots, as.s_att, as.s_key, run_seed, w.coef.as<double2>());
         }
         CKK(h);
 
         IntegArgs a;
         memset(&a, 0, sizeof a);
         a.n = 0; a.n_dev = d_nslots;
-        a.ym = sa.s_ym; a.lon0 = sa.s_lon; a.lat0 = sa.s_lat; a.v0 = sa.s_v0; a.m0 = sa.s_m0; a.h_bl = sa.s_hbl;
+        a.ym = as.s_ym; a.lon0 = as.s_lon; a.lat0 = as.s_lat; a.v0 = as.s_v0; a.m0 = as.s_m0; a.h_bl = as.s_hbl;
         a.ftab = w.ftab.as<double>(); a.track = w.track.as<double>();
         a.n_time = w.n_time.as<int32_t>(); a.status = w.status.as<int32_t>(); a.nfev = w.nfev.as<int32_t>();
         a.flags = w.flags.as<uint32_t>();
         a.queue = d_queue; a.cand_list = w.cand.as<int32_t>(); a.cand_count = d_ncand;
-        if (launch_fourier_table(h, total, d_nslots) || launch_integrate(h, a, total)) return -1;
+        if (launch_fourier_table(h, slots_upper, d_nslots) || launch_integrate(h, a, slots_upper)) return -1;
 
         PostArgs pa;
         memset(&pa, 0, sizeof pa);
@@ -815,10 +870,10 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
 
         SelectArgs se;
         memset(&se, 0, sizeof se);
-        se.n_tracks = n_tracks; se.wave_off = d_wave_off; se.k0 = d_k0;
-        se.code = sa.code; se.basin = sa.basin; se.month = sa.month; se.att_slot = sa.att_slot;
+        se.n_tracks = n_tracks; se.wave_off = d_wave_off; se.k0 = d_k0; se.consumed = d_consumed;
+        se.code = sa.code; se.basin = sa.basin; se.month = sa.month; se.att_slot = as.att_slot;
         se.n_time = a.n_time; se.nfev = a.nfev; se.flags = a.flags;
-        se.nt = d_nt; se.row_slot = w.row_slot.as<int32_t>();
+        se.nt = d_nt; se.used = d_used; se.row_slot = w.row_slot.as<int32_t>();
         se.tc_month = d_month; se.tc_basin = d_basin; se.n_seeds = d_seeds;
         se.stats = w.stats.as<tcr_year_stats>();
         {
@@ -839,17 +894,25 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         CKK(h);
 
         CK(cudaMemcpyAsync(pin_nt, d_nt, n_years * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(pin_used, d_consumed, n_years * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(pin_used + n_years, d_npass, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        sum_pass += (int64_t)(*reinterpret_cast<unsigned int*>(pin_used + n_years));
+        sum_att_launched += total;
         for (int y = 0; y < n_years; ++y) {
             if (W[y] > 0) {
                 nt[y] = pin_nt[y];
-                att_total[y] += W[y];
-                k0[y] += W[y];
+                /* a year whose range was cut by the slot capacity only advances by what was processed */
+                const int64_t done = std::min<int64_t>(W[y], pin_used[y]);
+                att_total[y] += done;
+                k0[y] += done;
             }
         }
     }
     bool complete = true;
     for (int y = 0; y < n_years; ++y) if (nt[y] < n_tracks) complete = false;
+    std::vector<tcr_year_stats> hstats(n_years);
+    CK(cudaMemcpyAsync(hstats.data(), w.stats.p, (size_t)n_years * sizeof(tcr_year_stats), cudaMemcpyDeviceToHost, s));
 
     if (!on_device) {
         CK(cudaMemcpyAsync(lon, d_lon, rows * ns * 8, cudaMemcpyDeviceToHost, s));
@@ -862,8 +925,15 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         CK(cudaMemcpyAsync(tc_basin, d_basin, rows * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(n_seeds, d_seeds, (size_t)n_years * 84 * 8, cudaMemcpyDeviceToHost, s));
     }
-    if (stats) CK(cudaMemcpyAsync(stats, w.stats.p, (size_t)n_years * sizeof(tcr_year_stats), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (stats) memcpy(stats, hstats.data(), (size_t)n_years * sizeof(tcr_year_stats));
+    if (complete && sum_att_launched > 0) {
+        /* kept tracks per consumed attempt (i*+1 of every year), integrated storms per launched attempt */
+        int64_t kept = 0, consumed = 0;
+        for (int y = 0; y < n_years; ++y) { kept += hstats[y].n_kept; consumed += hstats[y].attempts; }
+        if (kept > 0 && consumed > 0) h->hint_kept_rate = (double)kept / (double)consumed;
+        h->hint_pass_rate = (double)sum_pass / (double)sum_att_launched;
+    }
     if (!complete) return set_err("tcr_run_years: wave limit reached before every year produced %d tracks", n_tracks);
     return 0;
 }

@@ -74,10 +74,11 @@ class Engine:
     def synchronize(self):
         _lib.check(self.lib.tcr_synchronize(self._h))
 
-    def set_tuning(self, integ_variant=0, max_wave=0, oversub_permille=0):
+    def set_tuning(self, integ_variant=0, max_wave=0, max_slots=0, oversub_permille=0):
         """0 keeps a knob: integrate-kernel register variant (1: 256 thr x 1 CTA/SM, 2: 128 x 3,
-        3: 128 x 4), seed attempts per wave, wave over-subscription (x1000)."""
-        _lib.check(self.lib.tcr_set_tuning(self._h, integ_variant, max_wave, oversub_permille))
+        3: 128 x 4, 4: 160 x 2), seed attempts / integrated storms per wave, wave over-subscription
+        (x1000).  Results never depend on these."""
+        _lib.check(self.lib.tcr_set_tuning(self._h, integ_variant, max_wave, max_slots, oversub_permille))
 
     def set_interp_variant(self, variant):
         _lib.check(self.lib.tcr_set_interp_variant(self._h, int(variant)))
