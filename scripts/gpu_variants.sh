@@ -4,7 +4,7 @@ TAG=${1:-var}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -15 $OUT/pytest_gpu.log
-for v in 1 2 3 4; do
+for v in ${VARIANTS:-1 2 3 4 5 6}; do
   timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-interp --integ-variant $v > $OUT/bench_v$v.json 2> $OUT/bench_v$v.err
   python - <<PY
 import json

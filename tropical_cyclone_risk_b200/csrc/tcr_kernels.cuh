@@ -80,6 +80,12 @@ __global__ void k_build_axis(const double* __restrict__ ax, TcrNode* __restrict_
     }
 }
 
+/* tcr_rcp_seed of the constant divisors of the RHS (out[0] = earth_R, out[1] = pi) */
+__global__ void k_build_consts(double earth_R, double* __restrict__ out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = tcr_rcp_seed(earth_R); out[1] = tcr_rcp_seed(TCR_PI); }
+}
+
 /* storm-independent harmonics of the output time grid: sc[j][k] = {sin, cos}(2 pi (k+1) t_j / T_Fs) */
 __global__ void k_build_sincos(const __grid_constant__ TcrCtx cx, double2* __restrict__ sc)
 {
@@ -380,9 +386,16 @@ enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
  * table is read from HBM/L2 (64 B per evaluation); only emitted samples go to HBM.
  * THREADS x MINB fixes the register budget (launch bounds): <256,1> 255 registers, <128,3> 168,
  * <128,4> 128 -- chosen at run time by tcr_set_tuning, default by measurement.   */
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, bool KSMEM>
 __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
 {
+    /* KSMEM: the stage derivatives K1..K5 (dead during an RHS evaluation) live in shared memory,
+     * [stage][component][thread], which frees 40 registers for a second resident CTA */
+    __shared__ double k_smem[KSMEM ? 20 * THREADS : 1];
+    double Kr[KSMEM ? 1 : 5][4] = {};
+    double* const ks = k_smem + (KSMEM ? threadIdx.x : 0);
+    auto Kg = [&](int j, int i) -> double { if constexpr (KSMEM) return ks[((j - 1) * 4 + i) * THREADS]; else return Kr[j - 1][i]; };
+    auto Ks = [&](int j, int i, double v) { if constexpr (KSMEM) ks[((j - 1) * 4 + i) * THREADS] = v; else Kr[j - 1][i] = v; };
     const tcr_params& p = cx.p;
     const int lane = threadIdx.x & 31;
     const double* ftab = nullptr;
@@ -398,8 +411,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
     double hbl = 0.0, t = 0.0, h = 0.0, h_abs = 0.0, t_new = 0.0, g = 0.0, min_step = 0.0;
     double h0 = 0.0, d1 = 0.0;
     double y[4] = {0, 0, 0, 0}, yn[4] = {0, 0, 0, 0};
-    double K0[4] = {0, 0, 0, 0}, K1[4] = {0, 0, 0, 0}, K2[4] = {0, 0, 0, 0}, K3[4] = {0, 0, 0, 0},
-           K4[4] = {0, 0, 0, 0}, K5[4] = {0, 0, 0, 0}, K6[4] = {0, 0, 0, 0};
+    double K0[4] = {0, 0, 0, 0}, K6[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = 1; j <= 5; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Ks(j, i, 0.0);
     double* trk = nullptr;
 
     /* storm end: n_time / status / nfev / TC criteria (util/compute.py:185-189) */
@@ -465,7 +481,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                             sid = my;
                             ym = A.ym[sid];
                             y[0] = A.lon0[sid]; y[1] = A.lat0[sid]; y[2] = A.v0[sid]; y[3] = A.m0[sid];
-                            hbl = A.h_bl[sid];
+                            hbl = 0.5 * p.Ck / A.h_bl[sid];          /* storm-constant prefactor of dv/dt, dm/dt */
                             ftab = A.ftab + (size_t)sid * ns * 4;
                             trk = A.track + (size_t)sid * ns * 4;
                             nfev = 0; n_out = 0; n_attempts = 0; any_v = false; t = 0.0; status = 100;
@@ -491,30 +507,30 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 case 1:
                     te = t + RK_C2 * h;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(K1[i], RK_A21, K0[i] * RK_A20), h, y[i]);
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(Kg(1, i), RK_A21, K0[i] * RK_A20), h, y[i]);
                     break;
                 case 2:
                     te = t + RK_C3 * h;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(K2[i], RK_A32, fma(K1[i], RK_A31, K0[i] * RK_A30)), h, y[i]);
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(Kg(2, i), RK_A32, fma(Kg(1, i), RK_A31, K0[i] * RK_A30)), h, y[i]);
                     break;
                 case 3:
                     te = t + RK_C4 * h;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        ye[i] = fma(fma(K3[i], RK_A43, fma(K2[i], RK_A42, fma(K1[i], RK_A41, K0[i] * RK_A40))), h, y[i]);
+                        ye[i] = fma(fma(Kg(3, i), RK_A43, fma(Kg(2, i), RK_A42, fma(Kg(1, i), RK_A41, K0[i] * RK_A40))), h, y[i]);
                     break;
                 case 4:
                     te = t + 1.0 * h;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        ye[i] = fma(fma(K4[i], RK_A54, fma(K3[i], RK_A53, fma(K2[i], RK_A52, fma(K1[i], RK_A51, K0[i] * RK_A50)))), h, y[i]);
+                        ye[i] = fma(fma(Kg(4, i), RK_A54, fma(Kg(3, i), RK_A53, fma(Kg(2, i), RK_A52, fma(Kg(1, i), RK_A51, K0[i] * RK_A50)))), h, y[i]);
                     break;
                 default:
                     te = t + h;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        yn[i] = fma(h, fma(K5[i], RK_B5, fma(K4[i], RK_B4, fma(K3[i], RK_B3, fma(K2[i], RK_B2, K0[i] * RK_B0)))), y[i]);
+                        yn[i] = fma(h, fma(Kg(5, i), RK_B5, fma(Kg(4, i), RK_B4, fma(Kg(3, i), RK_B3, fma(Kg(2, i), RK_B2, K0[i] * RK_B0)))), y[i]);
                         ye[i] = yn[i];
                     }
                     break;
@@ -536,11 +552,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
             /* ---- consume ---- */
             if (mode == M_RK) {
                 switch (slot) {
-                case 0: K1[0] = dy[0]; K1[1] = dy[1]; K1[2] = dy[2]; K1[3] = dy[3]; break;
-                case 1: K2[0] = dy[0]; K2[1] = dy[1]; K2[2] = dy[2]; K2[3] = dy[3]; break;
-                case 2: K3[0] = dy[0]; K3[1] = dy[1]; K3[2] = dy[2]; K3[3] = dy[3]; break;
-                case 3: K4[0] = dy[0]; K4[1] = dy[1]; K4[2] = dy[2]; K4[3] = dy[3]; break;
-                case 4: K5[0] = dy[0]; K5[1] = dy[1]; K5[2] = dy[2]; K5[3] = dy[3]; break;
+                case 0: Ks(1, 0, dy[0]); Ks(1, 1, dy[1]); Ks(1, 2, dy[2]); Ks(1, 3, dy[3]); break;
+                case 1: Ks(2, 0, dy[0]); Ks(2, 1, dy[1]); Ks(2, 2, dy[2]); Ks(2, 3, dy[3]); break;
+                case 2: Ks(3, 0, dy[0]); Ks(3, 1, dy[1]); Ks(3, 2, dy[2]); Ks(3, 3, dy[3]); break;
+                case 3: Ks(4, 0, dy[0]); Ks(4, 1, dy[1]); Ks(4, 2, dy[2]); Ks(4, 3, dy[3]); break;
+                case 4: Ks(5, 0, dy[0]); Ks(5, 1, dy[1]); Ks(5, 2, dy[2]); Ks(5, 3, dy[3]); break;
                 default: K6[0] = dy[0]; K6[1] = dy[1]; K6[2] = dy[2]; K6[3] = dy[3]; break;
                 }
             } else if (mode == M_INIT0) {
@@ -598,7 +614,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 double ay = fabs(y[i]), an = fabs(yn[i]);
                 double mx = (tcr_isnan(ay) || tcr_isnan(an)) ? NAN : (ay > an ? ay : an);
                 double scale = atol + mx * rtol;
-                double e = fma(K6[i], RK_E6, fma(K5[i], RK_E5, fma(K4[i], RK_E4, fma(K3[i], RK_E3, fma(K2[i], RK_E2, K0[i] * RK_E0)))));
+                double e = fma(K6[i], RK_E6, fma(Kg(5, i), RK_E5, fma(Kg(4, i), RK_E4, fma(Kg(3, i), RK_E3, fma(Kg(2, i), RK_E2, K0[i] * RK_E0)))));
                 en[i] = (e * h) / scale;
             }
             const double err = tcr_rms4(en);
@@ -622,27 +638,38 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                     double Q1[4], Q2[4], Q3[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        Q1[i] = fma(K6[i], RK_P61, fma(K5[i], RK_P51, fma(K4[i], RK_P41, fma(K3[i], RK_P31, fma(K2[i], RK_P21, K0[i] * RK_P01)))));
-                        Q2[i] = fma(K6[i], RK_P62, fma(K5[i], RK_P52, fma(K4[i], RK_P42, fma(K3[i], RK_P32, fma(K2[i], RK_P22, K0[i] * RK_P02)))));
-                        Q3[i] = fma(K6[i], RK_P63, fma(K5[i], RK_P53, fma(K4[i], RK_P43, fma(K3[i], RK_P33, fma(K2[i], RK_P23, K0[i] * RK_P03)))));
+                        Q1[i] = fma(K6[i], RK_P61, fma(Kg(5, i), RK_P51, fma(Kg(4, i), RK_P41, fma(Kg(3, i), RK_P31, fma(Kg(2, i), RK_P21, K0[i] * RK_P01)))));
+                        Q2[i] = fma(K6[i], RK_P62, fma(Kg(5, i), RK_P52, fma(Kg(4, i), RK_P42, fma(Kg(3, i), RK_P32, fma(Kg(2, i), RK_P22, K0[i] * RK_P02)))));
+                        Q3[i] = fma(K6[i], RK_P63, fma(Kg(5, i), RK_P53, fma(Kg(4, i), RK_P43, fma(Kg(3, i), RK_P33, fma(Kg(2, i), RK_P23, K0[i] * RK_P03)))));
                     }
-                    const double hd = t_new - t_old;
-                    for (int k = n_out; k < i_new; ++k) {
-                        double x = (tcr_node_time(cx, k) - t_old) / hd;
-                        double p2 = x * x, p3 = p2 * x, p4 = p3 * x;
-                        double o[4];
+                    const double hd = t_new - t_old, yhd = tcr_rcp_seed(hd);
+                    /* four samples per trip, computed unconditionally (the last trip repeats its final
+                     * sample) so that the four dependent chains interleave; only the stores are guarded */
+                    for (int k0 = n_out; k0 < i_new; k0 += 4) {
+                        double o[4][4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            double acc = (K0[i] * 1.0) * x;
-                            acc = fma(Q1[i], p2, acc);
-                            acc = fma(Q2[i], p3, acc);
-                            acc = fma(Q3[i], p4, acc);
-                            o[i] = fma(hd, acc, y[i]);
+                        for (int u = 0; u < 4; ++u) {
+                            const int k = min(k0 + u, i_new - 1);
+                            double x = tcr_div_y(tcr_node_time(cx, k) - t_old, hd, yhd);
+                            double p2 = x * x, p3 = p2 * x, p4 = p3 * x;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                double acc = (K0[i] * 1.0) * x;
+                                acc = fma(Q1[i], p2, acc);
+                                acc = fma(Q2[i], p3, acc);
+                                acc = fma(Q3[i], p4, acc);
+                                o[u][i] = fma(hd, acc, y[i]);
+                            }
                         }
-                        double2* dst = reinterpret_cast<double2*>(trk + (size_t)k * 4);
-                        dst[0] = make_double2(o[0], o[1]);
-                        dst[1] = make_double2(o[2], o[3]);
-                        if (o[2] >= p.seed_v_thresh) any_v = true;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (k0 + u < i_new) {
+                                double2* dst = reinterpret_cast<double2*>(trk + (size_t)(k0 + u) * 4);
+                                dst[0] = make_double2(o[u][0], o[u][1]);
+                                dst[1] = make_double2(o[u][2], o[u][3]);
+                                if (o[u][2] >= p.seed_v_thresh) any_v = true;
+                            }
+                        }
                     }
                     n_out = i_new;
                 }

@@ -229,9 +229,14 @@ int tcr_create(int device, const tcr_params* p, tcr_handle** out)
     if (cudaMallocHost(&h->pinned, 1 << 16) != cudaSuccess) { delete h; return set_err("cudaMallocHost failed"); }
     if (h->sincos.ensure((size_t)p->n_steps * TCR_N_HARM * sizeof(double2))) { cudaFreeHost(h->pinned); delete h; return -1; }
     h->ctx.sc = h->sincos.as<double2>();
+    h->ctx.inv_t_step = 1.0 / h->ctx.t_step;
     k_build_sincos<<<(p->n_steps + 127) / 128, 128, 0, h->stream>>>(h->ctx, h->sincos.as<double2>());
+    double* d_consts = reinterpret_cast<double*>(h->pinned);          /* pinned memory is device-accessible (UVA) */
+    k_build_consts<<<1, 32, 0, h->stream>>>(p->earth_R, d_consts);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    h->ctx.y_earth_R = d_consts[0];
+    h->ctx.y_pi = d_consts[1];
     if (e != cudaSuccess) {
         set_err("tcr_create: harmonic table build failed: %s", cudaGetErrorString(e));
         h->sincos.release(); cudaFreeHost(h->pinned); delete h;
@@ -278,7 +283,7 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 {
     if (!h) return set_err("null handle");
     if (integ_variant > 0) {
-        if (integ_variant > 4) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
+        if (integ_variant > 6) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
         h->integ_variant = integ_variant - 1;
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
@@ -539,7 +544,7 @@ static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned i
 
 }  // extern "C"
 
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, bool KSMEM>
 static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_upper)
 {
     const int warps_per_cta = THREADS / 32;
@@ -549,16 +554,18 @@ static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_uppe
     int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
     a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
     LaunchTimer lt_(h, TCR_K_INTEGRATE);
-    k_integrate<THREADS, MINB><<<grid, THREADS, 0, h->stream>>>(h->ctx, a);
+    k_integrate<THREADS, MINB, KSMEM><<<grid, THREADS, 0, h->stream>>>(h->ctx, a);
 }
 
 static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
 {
     switch (h->integ_variant) {
-    case 0: launch_integrate_variant<256, 1>(h, a, n_upper); break;
-    case 1: launch_integrate_variant<128, 3>(h, a, n_upper); break;
-    case 2: launch_integrate_variant<128, 4>(h, a, n_upper); break;
-    case 3: launch_integrate_variant<160, 2>(h, a, n_upper); break;
+    case 0: launch_integrate_variant<256, 1, false>(h, a, n_upper); break;
+    case 1: launch_integrate_variant<128, 3, false>(h, a, n_upper); break;
+    case 2: launch_integrate_variant<128, 4, true>(h, a, n_upper); break;
+    case 3: launch_integrate_variant<160, 2, false>(h, a, n_upper); break;
+    case 4: launch_integrate_variant<128, 3, true>(h, a, n_upper); break;
+    case 5: launch_integrate_variant<192, 2, true>(h, a, n_upper); break;
     default: return set_err("unknown integrate variant %d", h->integ_variant);
     }
     CKK(h);
