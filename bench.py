@@ -344,7 +344,8 @@ def bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args):
     ym = torch.randint(0, wl.n_ym, (n,), generator=g, device=dev, dtype=torch.int32)
     out = torch.empty((n, 21), dtype=torch.float64, device=dev)
     res = {}
-    for variant, name in ((0, "k_env_interp"), (1, "k_env_interp_tma")):
+    for variant, name in ((0, "k_env_interp"), (1, "k_env_interp_tma"), (2, "k_env_interp<4>"), (3, "k_env_interp<5>"),
+                          (4, "k_env_interp_pipe"), (5, "k_env_interp_async<256>"), (6, "k_env_interp_async<128>")):
         eng.set_interp_variant(variant)
         for _ in range(3):
             eng.env_interp_dev(n, ym.data_ptr(), lon.data_ptr(), lat.data_ptr(), out.data_ptr())

@@ -109,7 +109,8 @@ struct EiLoc { const float4* rec; double w00, w01, w10, w11, bathy, land; };
 
 /* variant 0: per-lane LDG.128 of the record quads, flat (query, channel) item space so that
  * both the record reads and the float64 output writes are fully coalesced                    */
-__global__ void __launch_bounds__(EI_TILE) k_env_interp(const __grid_constant__ TcrCtx cx, int64_t n,
+template <int MINB>
+__global__ void __launch_bounds__(EI_TILE, MINB) k_env_interp(const __grid_constant__ TcrCtx cx, int64_t n,
                                                         const int32_t* __restrict__ ym, const double* __restrict__ lon,
                                                         const double* __restrict__ lat, double* __restrict__ out)
 {
@@ -270,6 +271,235 @@ __global__ void __launch_bounds__(EIT_TILE * 2) k_env_interp_tma(const __grid_co
             __stcs(o + i, v);
         }
         __syncthreads();                       /* stage s free for the next refill */
+    }
+}
+
+/* variant 4: warp-specialised cp.async pipeline.  Warps 0-3 (producers) locate 128 queries per
+ * tile, write their weights to the stage and start the asynchronous copies (LDGSTS, L2 -> shared,
+ * no register staging) of the 128 x 320-byte records -- issued cooperatively in flat (query,
+ * channel) order so every warp-level request covers whole sectors -- plus each query's
+ * bathymetry / land cell; completion is signalled on the stage's "full" mbarrier by
+ * cp.async.mbarrier.arrive.  Warps 4-7 (consumers) form the 21 outputs per query from shared
+ * memory and stream them out coalesced, then release the stage ("empty" mbarrier).  With three
+ * stages two tiles of gathers (80 KB per SM) are always in flight, which is what a random-gather
+ * kernel needs to approach the HBM roofline (Little: ~6.4 TB/s x ~0.8 us / 148 SMs = 35 KB).   */
+#define EP_TILE 128
+#define EP_STAGES 3
+#define EP_THREADS 256
+struct __align__(16) EpLoc {
+    double w00, w01, w10, w11;          /* table cell weights (fused-sum form)                   */
+    double bw00, bw01, bw10, bw11;      /* bathymetry cell weights                                */
+    double lx0, lx1, ly0, ly1;          /* land cell weights, FITPACK product order               */
+    short4 bathy; char4 land; int valid;
+};
+#define EP_STAGE_BYTES (EP_TILE * TCR_REC_F4 * 16 + EP_TILE * (int)sizeof(EpLoc) + EP_TILE * 8)
+#define EP_SMEM_BYTES (EP_STAGES * EP_STAGE_BYTES + 2 * EP_STAGES * 8)
+
+__device__ __forceinline__ void tcr_cp_async16(void* dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tcr_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tcr_cp_async8(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tcr_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tcr_cp_async4(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tcr_smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void tcr_cp_async_arrive(uint64_t* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tcr_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcr_mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tcr_smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(EP_THREADS, 1) k_env_interp_pipe(const __grid_constant__ TcrCtx cx, int64_t n,
+                                                                   const int32_t* __restrict__ ym, const double* __restrict__ lon,
+                                                                   const double* __restrict__ lat, double* __restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)EP_STAGES * EP_STAGE_BYTES);
+    uint64_t* empty = full + EP_STAGES;
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (n + EP_TILE - 1) / EP_TILE;
+    if (tid == 0) {
+        for (int s = 0; s < EP_STAGES; ++s) { tcr_mbar_init(full + s, 2 * EP_TILE); tcr_mbar_init(empty + s, EP_TILE); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto stage_rec = [&](int s) { return reinterpret_cast<float4*>(smem_raw + (size_t)s * EP_STAGE_BYTES); };
+    auto stage_loc = [&](int s) { return reinterpret_cast<EpLoc*>(smem_raw + (size_t)s * EP_STAGE_BYTES + EP_TILE * TCR_REC_F4 * 16); };
+    auto stage_ptr = [&](int s) {
+        return reinterpret_cast<const float4**>(smem_raw + (size_t)s * EP_STAGE_BYTES + EP_TILE * TCR_REC_F4 * 16 + EP_TILE * sizeof(EpLoc));
+    };
+
+    if (tid < EP_TILE) {
+        /* ---------------- producers ---------------- */
+        int64_t tile = blockIdx.x;
+        double x = 0.0, y = 0.0; int m = 0;
+        if (tile < n_tiles && tile * EP_TILE + tid < n) { const int64_t q = tile * EP_TILE + tid; x = lon[q]; y = lat[q]; m = ym[q]; }
+        for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % EP_STAGES;
+            if (it >= EP_STAGES) tcr_mbar_wait(empty + s, (uint32_t)((it / EP_STAGES) - 1) & 1u);
+            const int64_t q0 = tile * EP_TILE;
+            const int nq = (int)min((int64_t)EP_TILE, n - q0);
+            EpLoc* loc = stage_loc(s);
+            const float4** rp = stage_ptr(s);
+            if (tid < nq) {
+                TcrCellLoc lt, ll, lb;
+                tcr_cell_begin(cx.tab.lon, cx.tab.lat, x, y, lt);
+                tcr_cell_begin(cx.st.lon_l, cx.st.lat_l, x, y, ll);
+                tcr_cell_begin(cx.st.lon_b, cx.st.lat_b, x, y, lb);
+                TcrCell c, cl, cb;
+                tcr_cell_end(cx.tab.lon, cx.tab.lat, lt, c);
+                tcr_cell_end(cx.st.lon_l, cx.st.lat_l, ll, cl);
+                tcr_cell_end(cx.st.lon_b, cx.st.lat_b, lb, cb);
+                EpLoc& l = loc[tid];
+                l.w00 = c.w00; l.w01 = c.w01; l.w10 = c.w10; l.w11 = c.w11;
+                l.bw00 = cb.w00; l.bw01 = cb.w01; l.bw10 = cb.w10; l.bw11 = cb.w11;
+                l.lx0 = cl.wx0; l.lx1 = cl.wx1; l.ly0 = cl.wy0; l.ly1 = cl.wy1;
+                l.valid = 1;
+                tcr_cp_async8(&l.bathy, cx.st.bathy + (size_t)cb.iy * cx.st.ncx_b + cb.ix);
+                tcr_cp_async4(&l.land, cx.st.land + (size_t)cl.iy * cx.st.ncx_l + cl.ix);
+                rp[tid] = tcr_record(cx.tab, m, c);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(EP_TILE) : "memory");          /* record pointers visible to the producers */
+            float4* rec = stage_rec(s);
+            const int n_items = nq * TCR_REC_F4;
+#pragma unroll 4
+            for (int j = 0; j < TCR_REC_F4; ++j) {
+                const int i = tid + j * EP_TILE;
+                if (i < n_items) {
+                    const int qi = i / TCR_REC_F4, ch = i - qi * TCR_REC_F4;
+                    tcr_cp_async16(rec + i, rp[qi] + ch);
+                }
+            }
+            tcr_cp_async_arrive(full + s);       /* fires when this thread's copies have landed */
+            tcr_mbar_arrive(full + s);           /* releases this thread's plain shared-memory writes */
+            /* next tile's coordinates: in flight while the copies are issued */
+            const int64_t nt = tile + gridDim.x;
+            if (nt < n_tiles && nt * EP_TILE + tid < n) { const int64_t q = nt * EP_TILE + tid; x = lon[q]; y = lat[q]; m = ym[q]; }
+        }
+    } else {
+        /* ---------------- consumers ---------------- */
+        const int ct = tid - EP_TILE;
+        int64_t tile = blockIdx.x;
+        for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int s = it % EP_STAGES;
+            tcr_mbar_wait(full + s, (uint32_t)(it / EP_STAGES) & 1u);
+            const int64_t q0 = tile * EP_TILE;
+            const int nq = (int)min((int64_t)EP_TILE, n - q0);
+            const int n_items = nq * TCR_N_INTERP_OUT;
+            const float4* rec = stage_rec(s);
+            const EpLoc* loc = stage_loc(s);
+            double* o = out + q0 * TCR_N_INTERP_OUT;
+#pragma unroll 3
+            for (int j = 0; j < TCR_N_INTERP_OUT; ++j) {
+                const int i = ct + j * EP_TILE;
+                if (i < n_items) {
+                    const int qi = i / TCR_N_INTERP_OUT, ch = i - qi * TCR_N_INTERP_OUT;
+                    const EpLoc& l = loc[qi];
+                    double v;
+                    if (ch < TCR_N_FIELDS) {
+                        const float4 r = rec[qi * TCR_REC_F4 + ch];
+                        v = fma((double)r.w, l.w11, fma((double)r.z, l.w10, fma((double)r.y, l.w01, (double)r.x * l.w00)));
+                    } else if (ch == TCR_N_FIELDS) {
+                        const short4 r = l.bathy;
+                        v = fma((double)r.w, l.bw11, fma((double)r.z, l.bw10, fma((double)r.y, l.bw01, (double)r.x * l.bw00)));
+                    } else {
+                        const char4 r = l.land;
+                        double sp = 0.0;
+                        sp = sp + (double)r.x * l.lx0 * l.ly0;
+                        sp = sp + (double)r.y * l.lx0 * l.ly1;
+                        sp = sp + (double)r.z * l.lx1 * l.ly0;
+                        sp = sp + (double)r.w * l.lx1 * l.ly1;
+                        v = sp;
+                    }
+                    __stcs(o + i, v);
+                }
+            }
+            tcr_mbar_arrive(empty + s);
+        }
+    }
+}
+
+/* variant 5: one tile of EA_TILE queries per CTA, all of the tile's record quads fetched by
+ * cp.async (LDGSTS, no register staging) in one burst -- EA_TILE x 320 B in flight per CTA, the
+ * other resident CTAs of the SM computing meanwhile -- then the outputs are formed from shared
+ * memory with a fixed channel per thread (252 = 12 queries x 21 channels of the 256 threads are
+ * active per pass, item = pass * 252 + t, so loads, stores and the smem reads are all contiguous
+ * and no per-item index arithmetic is left).                                                  */
+template <int EA_TILE>
+__global__ void __launch_bounds__(256) k_env_interp_async(const __grid_constant__ TcrCtx cx, int64_t n,
+                                                          const int32_t* __restrict__ ym, const double* __restrict__ lon,
+                                                          const double* __restrict__ lat, double* __restrict__ out)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* rec = reinterpret_cast<float4*>(smem_raw);                                        /* [EA_TILE][20] */
+    EiLoc* loc = reinterpret_cast<EiLoc*>(smem_raw + (size_t)EA_TILE * TCR_REC_F4 * 16);       /* [EA_TILE]     */
+    const int tid = threadIdx.x;
+    const int64_t q0 = (int64_t)blockIdx.x * EA_TILE;
+    const int nq = (int)min((int64_t)EA_TILE, n - q0);
+    const int lane = tid & 31;
+    for (int base = 0; base < nq; base += 256) {
+        const int qq = base + tid;
+        const bool valid = qq < nq;
+        const float4* my_rec = nullptr;
+        TcrCellLoc ll, lb;
+        TcrCell c;
+        double x = 0.0, y = 0.0;
+        if (valid) {
+            const int64_t q = q0 + qq;
+            x = lon[q]; y = lat[q];
+            TcrCellLoc lt;
+            tcr_cell_begin(cx.tab.lon, cx.tab.lat, x, y, lt);
+            tcr_cell_begin(cx.st.lon_l, cx.st.lat_l, x, y, ll);
+            tcr_cell_begin(cx.st.lon_b, cx.st.lat_b, x, y, lb);
+            tcr_cell_end(cx.tab.lon, cx.tab.lat, lt, c);
+            my_rec = tcr_record(cx.tab, ym[q], c);
+        }
+        /* the warp's 32 records, one coalesced 320-byte asynchronous copy each (lanes 0..19),
+         * issued before the static grids are touched */
+        const unsigned long long rp = (unsigned long long)my_rec;
+        const int wq0 = base + (tid & ~31);
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const unsigned long long src = __shfl_sync(TCR_FULL, rp, k);
+            if (src != 0ull && lane < TCR_REC_F4)
+                tcr_cp_async16(rec + (wq0 + k) * TCR_REC_F4 + lane, reinterpret_cast<const float4*>(src) + lane);
+        }
+        if (valid) {
+            TcrCell cl, cb;
+            tcr_cell_end(cx.st.lon_l, cx.st.lat_l, ll, cl);
+            tcr_cell_end(cx.st.lon_b, cx.st.lat_b, lb, cb);
+            EiLoc l;
+            l.rec = my_rec;
+            l.w00 = c.w00; l.w01 = c.w01; l.w10 = c.w10; l.w11 = c.w11;
+            l.bathy = tcr_bathy_cell(cx.st, cb);
+            l.land = tcr_land_cell(cx.st, cl);
+            loc[qq] = l;
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    if (tid < 252) {
+        const int ch = tid % TCR_N_INTERP_OUT, qs = tid / TCR_N_INTERP_OUT;        /* fixed channel, query sub-index 0..11 */
+        double* o = out + q0 * TCR_N_INTERP_OUT + tid;
+#pragma unroll 4
+        for (int qq = qs; qq < nq; qq += 12, o += 252) {
+            const EiLoc& l = loc[qq];
+            double v;
+            if (ch < TCR_N_FIELDS) {
+                const float4 r = rec[qq * TCR_REC_F4 + ch];
+                v = fma((double)r.w, l.w11, fma((double)r.z, l.w10, fma((double)r.y, l.w01, (double)r.x * l.w00)));
+            } else {
+                v = (ch == TCR_N_FIELDS) ? l.bathy : l.land;
+            }
+            __stcs(o, v);
+        }
     }
 }
 

@@ -295,7 +295,8 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 int tcr_set_interp_variant(tcr_handle* h, int variant)
 {
     if (!h) return set_err("null handle");
-    if (variant < 0 || variant > 1) return set_err("interp variant must be 0 (LDG) or 1 (TMA bulk)");
+    if (variant < 0 || variant > 6)
+        return set_err("interp variant must be 0 (LDG), 1 (TMA bulk), 2 / 3 (LDG, 4 / 5 CTAs per SM) or 4 (cp.async pipeline)");
     h->interp_variant = variant;
     return 0;
 }
@@ -455,9 +456,27 @@ static int launch_env_interp(tcr_handle* h, int64_t n, const int32_t* ym, const 
         int64_t tiles = (n + EIT_TILE - 1) / EIT_TILE;
         int grid = (int)std::min<int64_t>(tiles, h->num_sms);
         k_env_interp_tma<<<grid, EIT_TILE * 2, smem, h->stream>>>(h->ctx, n, ym, lon, lat, out);
+    } else if (h->interp_variant == 4) {
+        CK(cudaFuncSetAttribute(k_env_interp_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EP_SMEM_BYTES));
+        int64_t tiles = (n + EP_TILE - 1) / EP_TILE;
+        int grid = (int)std::min<int64_t>(tiles, h->num_sms);
+        k_env_interp_pipe<<<grid, EP_THREADS, EP_SMEM_BYTES, h->stream>>>(h->ctx, n, ym, lon, lat, out);
+    } else if (h->interp_variant == 5 || h->interp_variant == 6) {
+        const int tile = h->interp_variant == 5 ? 256 : 128;
+        const int smem = tile * (TCR_REC_F4 * 16 + (int)sizeof(EiLoc));
+        int64_t tiles = (n + tile - 1) / tile;
+        if (tile == 256) {
+            CK(cudaFuncSetAttribute(k_env_interp_async<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k_env_interp_async<256><<<(unsigned)tiles, 256, smem, h->stream>>>(h->ctx, n, ym, lon, lat, out);
+        } else {
+            CK(cudaFuncSetAttribute(k_env_interp_async<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k_env_interp_async<128><<<(unsigned)tiles, 256, smem, h->stream>>>(h->ctx, n, ym, lon, lat, out);
+        }
     } else {
         int64_t tiles = (n + EI_TILE - 1) / EI_TILE;
-        k_env_interp<<<(unsigned)tiles, EI_TILE, 0, h->stream>>>(h->ctx, n, ym, lon, lat, out);
+        if (h->interp_variant == 2) k_env_interp<4><<<(unsigned)tiles, EI_TILE, 0, h->stream>>>(h->ctx, n, ym, lon, lat, out);
+        else if (h->interp_variant == 3) k_env_interp<5><<<(unsigned)tiles, EI_TILE, 0, h->stream>>>(h->ctx, n, ym, lon, lat, out);
+        else k_env_interp<3><<<(unsigned)tiles, EI_TILE, 0, h->stream>>>(h->ctx, n, ym, lon, lat, out);
     }
     CKK(h);
     return 0;
