@@ -193,7 +193,10 @@ def run_gpu_arm(args):
     wl = Workload(args.basin, years, full_res=True, pinned_alloc=PinnedPool.empty)
     ns = int(wl.p.n_steps)
     eng = Engine(wl.p, device=local)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-blocking stream for the library, torch and NCCL alike: the legacy default
+    # stream's implicit synchronisation serialises against the collective's stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     wl.upload(eng)
     if args.integ_variant:
@@ -214,10 +217,20 @@ def run_gpu_arm(args):
         off += n
     gathered = torch.empty((world, total), dtype=torch.float64, device=dev) if world > 1 else None
 
+    diag = os.environ.get("TCR_BENCH_DIAG") == "1"
+
     def step_device(i):
+        t0 = time.perf_counter()
         st = eng.run_years_dev(ym_base, year_key, RUN_SEED + i, nt, dptr)
+        t1 = time.perf_counter()
         if world > 1:
             dist.all_gather_into_tensor(gathered, res)
+        if diag:
+            t2 = time.perf_counter()
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            print("rank %d step %d: run_years %.2f ms, all_gather enqueue %.2f ms, drain %.2f ms" % (
+                rank, i, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)), file=sys.stderr, flush=True)
         return st
 
     host_out = eng.alloc_results(ny, nt, pinned=True)

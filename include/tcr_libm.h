@@ -189,6 +189,7 @@ TCR_HD double tcr_asin(double x)
                  qS3 = -6.88283971605453293030e-01, qS4 = 7.70381505559019352791e-02;
     double ax = fabs(x);
     if (!(ax <= 1.0)) return NAN;
+    if (ax == 1.0) return x * pio2_hi + x * pio2_lo;      /* asin(+-1) = +-pi/2 (fdlibm special case) */
     if (ax < 0.5) {
         double t = x * x;
         double p = t * (pS0 + t * (pS1 + t * (pS2 + t * (pS3 + t * (pS4 + t * pS5)))));

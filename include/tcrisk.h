@@ -178,10 +178,13 @@ int tcr_seed_attempts(tcr_handle* h, int ym_base, int32_t year_key, uint32_t run
                       int32_t* code, int32_t* basin, int32_t* month,
                       double* lon, double* lat, double* v0, double* m0, double* pi_gen);
 
-/* tuning knobs (0 keeps the default): register-budget variant of the integrate kernel
- * (1 = 256 threads x 1 CTA/SM, 2 = 128 x 3, 3 = 128 x 4, 4 = 160 x 2), upper bounds on the seed
- * attempts and on the integrated storms of one wave, wave over-subscription factor (x1000).
- * Results never depend on these (ordered selection); only the amount of discarded work does.  */
+/* tuning knobs (0 keeps the default): variant of the integrate kernel = threads x CTAs/SM
+ * [K: stage derivatives in shared memory] [L: CTA-lockstep RHS evaluations]:
+ * 1 = 256x1, 2 = 128x3, 3 = 128x4 K, 4 = 160x2, 5 = 128x3 K, 6 = 192x2 K, 7 = 192x2 K L (default),
+ * 8 = 256x1 L, 9 = 288x1 K L, 10 = 384x1 K L, 11 = 512x1 K L, 12 = 128x3 K L, 13 = 224x1 L;
+ * upper bounds on the seed attempts and on the integrated storms of one wave; wave
+ * over-subscription factor (x1000).  Results never depend on these (ordered selection, bit-exact
+ * kernels); only speed and the amount of discarded work do.                                  */
 int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int64_t max_wave_slots,
                    int oversub_permille);
 /* number of kernels launched by this handle so far (bench.py's gpu_launches)               */

@@ -31,14 +31,22 @@ def main():
             if h == k:
                 print("  %-70s %-14s %s" % (h, units[i], vals[i]))
     rows = list(csv.reader(io.StringIO(ncu(rep, "--page", "source", "--csv", "--print-source", "sass"))))
-    hdr = rows[1]
+    h_at = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    hdr = rows[h_at]
+    rows = rows[h_at - 1:]
     ix = {h: i for i, h in enumerate(hdr)}
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot = collections.Counter()
     ns = ninst = nthr = 0
     opc = collections.defaultdict(lambda: [0, 0])
-    for r in rows[2:]:
-        if len(r) < len(hdr):
+    n_kernels = 0
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            n_kernels += 1
+            continue
+        if n_kernels > 1:
+            break                       # first selected launch only
+        if len(r) < len(hdr) or r[0] == "Address":
             continue
         s = int(r[ix["# Samples"]] or 0)
         ie = int(r[ix["Instructions Executed"]] or 0)
@@ -56,12 +64,14 @@ def main():
     print("== opcode mix (inst%, samples%): " + ", ".join("%s %.1f/%.1f" % (op, 100.0 * a / max(ninst, 1), 100.0 * b / max(ns, 1))
                                                          for op, (a, b) in sorted(opc.items(), key=lambda kv: -kv[1][0])[:14]))
     rows = list(csv.reader(io.StringIO(ncu(rep, "--page", "source", "--csv", "--print-source", "cuda,sass"))))
-    cur, hdr, out = None, None, []
+    cur, hdr, out, seen = None, None, [], set()
     for r in rows:
         if not r:
             continue
         if r[0] == "File Path":
-            cur = r[1].split("/")[-1]; continue
+            if cur is not None and r[1].split("/")[-1] in seen:
+                break                   # second launch starts: its files repeat
+            cur = r[1].split("/")[-1]; seen.add(cur); continue
         if r[0] == "Function Name":
             continue
         if r[0] == "Line No":
