@@ -18,16 +18,17 @@ cat $OUT/bench.json; tail -5 $OUT/bench.err
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > $OUT/bench_reference.json 2> $OUT/bench_reference.err
 cat $OUT/bench_reference.json
 if [ -z "$NO_NCU" ]; then
-echo "== ncu launch list"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu --interp-queries 4194304 > $OUT/ncu_bench.log 2>&1
-echo "== ncu full: k_integrate"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_integrate -s 2 -c 1 -f -o $OUT/prof_integrate \
-    python bench.py --steps 1 --warmup 1 --no-cpu --no-interp > $OUT/ncu_integrate.log 2>&1
+echo "== ncu launch list (same command as the bench, fewer steps)"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu --interp-queries 4194304 > $OUT/ncu_bench.log 2>&1
+echo "== ncu full: k_integrate (one-wave steps after the warm-up: launch 4)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_integrate -s 4 -c 1 -f -o $OUT/prof_integrate \
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-interp > $OUT/ncu_integrate.log 2>&1
 echo "== ncu full: env_interp"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_env_interp -s 3 -c 1 -f -o $OUT/prof_interp \
-    python bench.py --steps 1 --warmup 1 --no-cpu --years 10 --tracks 50 > $OUT/ncu_interp.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_postprocess -s 2 -c 1 -f -o $OUT/prof_post \
-    python bench.py --steps 1 --warmup 1 --no-cpu --no-interp > $OUT/ncu_post.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_env_interp -s 4 -c 1 -f -o $OUT/prof_interp \
+    python bench.py --steps 1 --warmup 1 --no-cpu --years 10 --tracks 20 > $OUT/ncu_interp.log 2>&1
+echo "== ncu full: k_fourier_table, k_select, k_postprocess"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fourier_table|k_select|k_postprocess|k_seed|k_gather" -s 20 -c 5 -f -o $OUT/prof_others \
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-interp > $OUT/ncu_others.log 2>&1
 fi
 ls -la $OUT
