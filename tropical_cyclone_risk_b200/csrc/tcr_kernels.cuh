@@ -616,7 +616,7 @@ enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
  * table is read from HBM/L2 (64 B per evaluation); only emitted samples go to HBM.
  * THREADS x MINB fixes the register budget (launch bounds): <256,1> 255 registers, <128,3> 168,
  * <128,4> 128 -- chosen at run time by tcr_set_tuning, default by measurement.   */
-template <int THREADS, int MINB, bool KSMEM, bool CTA_LOCKSTEP>
+template <int THREADS, int MINB, bool KSMEM, int CTA_LOCKSTEP>
 __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
 {
     /* KSMEM: the stage derivatives K1..K5 (dead during an RHS evaluation) live in shared memory,
@@ -721,12 +721,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                     if ((int64_t)base + cnt >= n) drained = true;
                 }
             }
-            if constexpr (CTA_LOCKSTEP) {
+            if constexpr (CTA_LOCKSTEP != 0) {
                 /* all warps of the CTA enter every RHS evaluation together: the ~45 KB of RHS code
                  * (larger than the 32 KB L1.5 instruction cache) is then fetched once per CTA instead
                  * of once per warp; the CTA retires when its last warp runs dry */
+                /* CTA_LOCKSTEP = bit mask of the slots that re-align the warps (bit 0 always set) */
                 if (slot == 0) { if (__syncthreads_or(mode != M_IDLE) == 0) return; }
-                else __syncthreads();
+                else if ((CTA_LOCKSTEP >> slot) & 1) __syncthreads();
             } else {
                 if (slot == 0 && __ballot_sync(TCR_FULL, mode != M_IDLE) == 0u) return;   /* warp-uniform */
             }

@@ -192,6 +192,23 @@ static int make_axis(tcr_handle* h, const double* host, int n, AxisBuf& ab, TcrA
     ax.lo = host[0];
     ax.hi = host[n - 1];
     ax.inv_d = (double)(n - 1) / (host[n - 1] - host[0]);
+    /* arithmetic nodes only if they reproduce the tabulated ones bit for bit */
+    const volatile double dx = host[1] - host[0];
+    const volatile double inv_dx = 1.0 / dx;
+    bool uniform = true;
+    for (int i = 0; i < n && uniform; ++i) {
+        const volatile double prod = (double)i * dx;          /* two roundings, as on the device (-fmad=false) */
+        const volatile double xi = host[0] + prod;
+        if (xi != host[i]) uniform = false;
+        if (i + 1 < n) {
+            const volatile double d = host[i + 1] - host[i];
+            const volatile double inv = 1.0 / d;
+            if (inv != inv_dx) uniform = false;
+        }
+    }
+    ax.uniform = uniform ? 1 : 0;
+    ax.dx = dx;
+    ax.inv_dx = inv_dx;
     return 0;
 }
 
@@ -283,7 +300,7 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 {
     if (!h) return set_err("null handle");
     if (integ_variant > 0) {
-        if (integ_variant > 13) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
+        if (integ_variant > 16) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
         h->integ_variant = integ_variant - 1;
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
@@ -563,7 +580,7 @@ static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned i
 
 }  // extern "C"
 
-template <int THREADS, int MINB, bool KSMEM, bool LOCKSTEP = false>
+template <int THREADS, int MINB, bool KSMEM, int LOCKSTEP = 0>
 static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_upper)
 {
     const int warps_per_cta = THREADS / 32;
@@ -587,13 +604,16 @@ static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
     case 3: launch_integrate_variant<160, 2, false>(h, a, n_upper); break;
     case 4: launch_integrate_variant<128, 3, true>(h, a, n_upper); break;
     case 5: launch_integrate_variant<192, 2, true>(h, a, n_upper); break;
-    case 6: launch_integrate_variant<192, 2, true, true>(h, a, n_upper); break;
-    case 7: launch_integrate_variant<256, 1, false, true>(h, a, n_upper); break;
-    case 8: launch_integrate_variant<288, 1, true, true>(h, a, n_upper); break;
-    case 9: launch_integrate_variant<384, 1, true, true>(h, a, n_upper); break;
-    case 10: launch_integrate_variant<512, 1, true, true>(h, a, n_upper); break;
-    case 11: launch_integrate_variant<128, 3, true, true>(h, a, n_upper); break;
-    case 12: launch_integrate_variant<224, 1, false, true>(h, a, n_upper); break;
+    case 6: launch_integrate_variant<192, 2, true, 63>(h, a, n_upper); break;
+    case 7: launch_integrate_variant<256, 1, false, 63>(h, a, n_upper); break;
+    case 8: launch_integrate_variant<288, 1, true, 63>(h, a, n_upper); break;
+    case 9: launch_integrate_variant<384, 1, true, 63>(h, a, n_upper); break;
+    case 10: launch_integrate_variant<512, 1, true, 63>(h, a, n_upper); break;
+    case 11: launch_integrate_variant<128, 3, true, 63>(h, a, n_upper); break;
+    case 12: launch_integrate_variant<224, 1, false, 63>(h, a, n_upper); break;
+    case 13: launch_integrate_variant<192, 2, true, 21>(h, a, n_upper); break;      /* re-align at slots 0, 2, 4 */
+    case 14: launch_integrate_variant<192, 2, true, 9>(h, a, n_upper); break;       /* slots 0, 3 */
+    case 15: launch_integrate_variant<192, 2, true, 1>(h, a, n_upper); break;       /* slot 0 only */
     default: return set_err("unknown integrate variant %d", h->integ_variant);
     }
     CKK(h);
