@@ -54,44 +54,84 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons of one GPU, sampled every 50 ms while running."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region by a background
+    thread through NVML (nvidia_ml_py): two cheap queries every 10 ms.  (A polling `nvidia-smi -lms`
+    process was measured to stall the CUDA driver for milliseconds at a time and distort a region
+    that is only ~100 ms long; it remains the fallback when NVML cannot be loaded.)"""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, index):
-        self.proc = None
+        import threading
+        self.samples, self.reasons, self.stop_flag, self.proc, self.nvml = [], set(), False, None, None
+        self.max_mhz = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            pass
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+            except Exception:
+                pass
+            self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid) if uuid else pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nvml = None
+            try:
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                    "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
+                                              "--format=csv,noheader,nounits", "-lms", "500"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except OSError:
+                pass
+
+    def _loop(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.010)
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(1.0)
+            return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(self.samples), "reasons": sorted(self.reasons), "source": "nvml, 10 ms period"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, smax, reasons, power = [], [], set(), []
+        sm, smax, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 6:
                 continue
             try:
-                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+                sm.append(float(f[0])); smax.append(float(f[1]))
             except ValueError:
                 continue
-            for name, val in zip(names, f[3:7]):
+            for name, val in zip(names, f[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 500"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -244,12 +284,13 @@ def run_gpu_arm(args):
         for s in st:
             for k, v in s.items():
                 acc[k] = acc.get(k, 0) + v
+        acc.setdefault("waves", []).append(max(s["n_waves"] for s in st))
 
     # ---- value: inputs resident in HBM ----------------------------------------------------
     for i in range(args.warmup):
         step_device(1000 + i)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and os.environ.get("TCR_BENCH_NO_CLOCKS") != "1" else None
     eng.set_timing(True)
     launches0 = eng.launch_count
     acc = {}
@@ -323,6 +364,7 @@ def run_gpu_arm(args):
             "gpu_launches": launches_all,
             "roofline": roof,
             "work_per_step": {k: tot[k] / K for k in keys},
+            "waves_per_step": acc["waves"],
             "kernel_share_of_step": kernel_share,
             "clocks": clocks,
         }

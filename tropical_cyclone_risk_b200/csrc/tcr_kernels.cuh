@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(FT_THREADS) k_fourier_table(const __grid_const
                                                               const unsigned int* __restrict__ n_dev,
                                                               const double2* __restrict__ coef, double* __restrict__ ftab)
 {
-    __shared__ double2 cfs[FT_STORMS][TCR_N_PHASES];
+    __shared__ __align__(16) double2 cfs[2][FT_STORMS][TCR_N_PHASES];      /* double-buffered coefficient tiles */
     const int64_t count = n_dev ? (int64_t)*n_dev : n;
     const int ns = cx.p.n_steps;
     const int j = blockIdx.x * FT_THREADS + threadIdx.x;
@@ -560,12 +560,25 @@ __global__ void __launch_bounds__(FT_THREADS) k_fourier_table(const __grid_const
 #pragma unroll
         for (int k = 0; k < TCR_N_HARM; ++k) sc[k] = __ldg(cx.sc + (size_t)j * TCR_N_HARM + k);
     }
-    for (int64_t s0 = (int64_t)blockIdx.y * FT_STORMS; s0 < count; s0 += (int64_t)gridDim.y * FT_STORMS) {
+    const int64_t stride = (int64_t)gridDim.y * FT_STORMS;
+    /* asynchronous copy (LDGSTS) of one tile's coefficients: the next tile lands while this one is used */
+    auto prefetch = [&](int64_t s0, int buf) {
+        if (s0 < count) {
+            const int nst = (int)min((int64_t)FT_STORMS, count - s0);
+            for (int i = threadIdx.x; i < nst * TCR_N_PHASES; i += FT_THREADS)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&cfs[buf][0][0] + i)),
+                             "l"(coef + (size_t)s0 * TCR_N_PHASES + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int64_t s0 = (int64_t)blockIdx.y * FT_STORMS;
+    int buf = 0;
+    prefetch(s0, 0);
+    for (; s0 < count; s0 += stride, buf ^= 1) {
+        prefetch(s0 + stride, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
         const int nst = (int)min((int64_t)FT_STORMS, count - s0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < nst * TCR_N_PHASES; i += FT_THREADS)
-            (&cfs[0][0])[i] = __ldg(coef + (size_t)s0 * TCR_N_PHASES + i);
-        __syncthreads();
         if (j < ns) {
 #pragma unroll 2
             for (int st = 0; st < nst; ++st) {
@@ -574,16 +587,17 @@ __global__ void __launch_bounds__(FT_THREADS) k_fourier_table(const __grid_const
                 for (int k = 0; k < TCR_N_HARM; ++k) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const double2 ab = cfs[st][i * TCR_N_HARM + k];
+                        const double2 ab = cfs[buf][st][i * TCR_N_HARM + k];
                         F[i] = fma(ab.x, sc[k].x, F[i]);
                         F[i] = fma(ab.y, sc[k].y, F[i]);
                     }
                 }
                 double2* dst = reinterpret_cast<double2*>(ftab + ((size_t)(s0 + st) * ns + j) * 4);
-                dst[0] = make_double2(F[0], F[1]);
-                dst[1] = make_double2(F[2], F[3]);
+                __stcs(dst, make_double2(F[0], F[1]));
+                __stcs(dst + 1, make_double2(F[2], F[3]));
             }
         }
+        __syncthreads();                       /* tile `buf` is free for the prefetch of the iteration after next */
     }
 }
 
@@ -1237,12 +1251,73 @@ __global__ void __launch_bounds__(256) k_assign_slots(const __grid_constant__ Tc
 /* ordered selection: the sequential `while nt < n_tracks` semantics of compute.py:134-209    */
 /* over the indexed attempt stream.  One CTA per year.                  */
 /* ======================================================================================== */
+/* totals of one wave, fully parallel (thread per attempt): per year the counters of ALL consumed
+ * attempts (k_select subtracts the over-shoot beyond i*), and one byte per attempt saying whether
+ * it produced a kept storm (so that the ordered scan of k_select reads a dense byte stream).   */
+struct WaveStatsArgs {
+    int n_years;
+    const int64_t* wave_off; const int64_t* consumed;
+    const int32_t* code; const int32_t* basin; const int32_t* month; const int32_t* att_slot;
+    const int32_t* n_time; const int32_t* nfev; const uint32_t* flags;
+    uint8_t* att_kept;                   /* [total attempts]                                     */
+    unsigned long long* wave_tot;        /* [n_years][4] counted, integrated, storm-steps, RHS    */
+    unsigned int* wave_hist;             /* [n_years][7*12] counted attempts per (basin, month)   */
+};
+
+__global__ void __launch_bounds__(256) k_wave_stats(const WaveStatsArgs A)
+{
+    __shared__ unsigned int s_hist[TCR_N_BASINS * 12];
+    __shared__ unsigned long long s_tot[4];
+    const int64_t total = A.wave_off[A.n_years];
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int tid = threadIdx.x;
+    /* year of the block's first attempt: the shared accumulators belong to it */
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+    int yr0 = 0;
+    while (yr0 + 1 < A.n_years && first >= A.wave_off[yr0 + 1]) ++yr0;
+    for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) s_hist[i] = 0u;
+    if (tid < 4) s_tot[tid] = 0ull;
+    __syncthreads();
+    if (idx < total) {
+        int yr = yr0;
+        while (yr + 1 < A.n_years && idx >= A.wave_off[yr + 1]) ++yr;
+        const int64_t li = idx - A.wave_off[yr];
+        uint8_t kept = 0;
+        if (li < A.consumed[yr]) {
+            const int code = A.code[idx], slot = A.att_slot[idx];
+            const bool counted = (code == 1 || code == 2);
+            unsigned long long steps = 0, rhs = 0;
+            if (slot >= 0) {
+                steps = (unsigned long long)A.n_time[slot]; rhs = (unsigned long long)A.nfev[slot];
+                if (A.flags[slot] & TCR_FLAG_KEPT) kept = 1;
+            }
+            const int bin = counted ? A.basin[idx] * 12 + A.month[idx] - 1 : 0;
+            if (yr == yr0) {
+                if (counted) { atomicAdd(&s_hist[bin], 1u); atomicAdd(&s_tot[0], 1ull); }
+                if (slot >= 0) { atomicAdd(&s_tot[1], 1ull); atomicAdd(&s_tot[2], steps); atomicAdd(&s_tot[3], rhs); }
+            } else {                                        /* block straddles a year boundary: rare */
+                if (counted) { atomicAdd(&A.wave_hist[yr * TCR_N_BASINS * 12 + bin], 1u); atomicAdd(&A.wave_tot[yr * 4 + 0], 1ull); }
+                if (slot >= 0) {
+                    atomicAdd(&A.wave_tot[yr * 4 + 1], 1ull); atomicAdd(&A.wave_tot[yr * 4 + 2], steps);
+                    atomicAdd(&A.wave_tot[yr * 4 + 3], rhs);
+                }
+            }
+        }
+        A.att_kept[idx] = kept;
+    }
+    __syncthreads();
+    for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&A.wave_hist[yr0 * TCR_N_BASINS * 12 + i], s_hist[i]);
+    if (tid < 4 && s_tot[tid]) atomicAdd(&A.wave_tot[yr0 * 4 + tid], s_tot[tid]);
+}
+
 struct SelectArgs {
     int n_tracks;
     const int64_t* wave_off; const int64_t* k0;
     const int64_t* consumed;    /* [n_years] attempts of the year's range that were fully processed   */
     const int32_t* code; const int32_t* basin; const int32_t* month; const int32_t* att_slot;
-    const int32_t* n_time; const int32_t* nfev; const uint32_t* flags;
+    const int32_t* n_time; const int32_t* nfev;
+    const uint8_t* att_kept; const unsigned long long* wave_tot; const unsigned int* wave_hist;   /* k_wave_stats */
     int32_t* nt;                /* [n_years] kept so far (in/out)                              */
     int64_t* used;              /* [n_years] attempts consumed by this wave: i*+1, or consumed[y] */
     int32_t* row_slot;          /* [n_years][n_tracks] slot of a row assigned in THIS wave, else -1 */
@@ -1250,12 +1325,12 @@ struct SelectArgs {
     tcr_year_stats* stats;      /* [n_years] device accumulators                               */
 };
 
-#define SEL_ITEMS 4
+#define SEL_ITEMS 8
 __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
 {
     __shared__ int warp_tot[32];
     __shared__ int s_running, s_istar;
-    __shared__ unsigned long long s_acc[7];
+    __shared__ unsigned long long s_acc[5];
     __shared__ unsigned int s_hist[TCR_N_BASINS * 12];
     const int yr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int64_t off = A.wave_off[yr];
@@ -1265,23 +1340,19 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
     const int nt0 = A.nt[yr];
     const int want = A.n_tracks - nt0;
     if (tid == 0) { s_running = 0; s_istar = -1; }
-    if (tid < 7) s_acc[tid] = 0ull;
+    if (tid < 5) s_acc[tid] = 0ull;
     for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) s_hist[i] = 0u;
     __syncthreads();
     /* pass 1: rank the kept storms in attempt order, find i* = attempt of the want-th kept.
-     * Each thread owns SEL_ITEMS consecutive attempts of a 4096-attempt chunk. */
+     * Each thread owns SEL_ITEMS consecutive attempts (one 8-byte load of kept flags when aligned). */
+    const uint8_t* kb = A.att_kept + off;
     for (int64_t base = 0; base < W; base += (int64_t)blockDim.x * SEL_ITEMS) {
-        int kept[SEL_ITEMS], slot[SEL_ITEMS], cnt = 0;
-#pragma unroll
-        for (int j = 0; j < SEL_ITEMS; ++j) {
-            const int64_t i = base + (int64_t)tid * SEL_ITEMS + j;
-            kept[j] = 0; slot[j] = -1;
-            if (i < W) {
-                slot[j] = A.att_slot[off + i];
-                if (slot[j] >= 0 && (A.flags[slot[j]] & TCR_FLAG_KEPT)) kept[j] = 1;
-            }
-            cnt += kept[j];
-        }
+        const int64_t i0 = base + (int64_t)tid * SEL_ITEMS;
+        unsigned long long bits = 0ull;
+        if (i0 + SEL_ITEMS <= W && (((uintptr_t)(kb + i0)) & 7) == 0) bits = *reinterpret_cast<const unsigned long long*>(kb + i0);
+        else
+            for (int j = 0; j < SEL_ITEMS; ++j) if (i0 + j < W) bits |= (unsigned long long)kb[i0 + j] << (8 * j);
+        const int cnt = __popcll(bits);
         int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(TCR_FULL, incl, d); if (lane >= d) incl += v; }
@@ -1295,18 +1366,20 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
         }
         __syncthreads();
         int rank = s_running + warp_tot[wid] + incl - cnt;          /* kept storms before this thread's items */
-#pragma unroll
-        for (int j = 0; j < SEL_ITEMS; ++j) {
-            if (!kept[j]) continue;
-            ++rank;                                                  /* 1-based rank of this kept storm */
-            if (rank <= want) {
-                const int64_t i = base + (int64_t)tid * SEL_ITEMS + j;
-                const int row = nt0 + rank - 1;
-                A.row_slot[(size_t)yr * A.n_tracks + row] = slot[j];
-                A.tc_month[(size_t)yr * A.n_tracks + row] = (double)A.month[off + i];
-                A.tc_basin[(size_t)yr * A.n_tracks + row] = A.basin[off + i];
-                atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot[j]]);
-                if (rank == want) s_istar = (int)i;
+        if (cnt) {
+            for (int j = 0; j < SEL_ITEMS; ++j) {
+                if (!((bits >> (8 * j)) & 1ull)) continue;
+                ++rank;                                              /* 1-based rank of this kept storm */
+                if (rank <= want) {
+                    const int64_t i = i0 + j;
+                    const int row = nt0 + rank - 1;
+                    const int slot = A.att_slot[off + i];
+                    A.row_slot[(size_t)yr * A.n_tracks + row] = slot;
+                    A.tc_month[(size_t)yr * A.n_tracks + row] = (double)A.month[off + i];
+                    A.tc_basin[(size_t)yr * A.n_tracks + row] = A.basin[off + i];
+                    atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot]);
+                    if (rank == want) s_istar = (int)i;
+                }
             }
         }
         __syncthreads();
@@ -1316,34 +1389,32 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
     }
     const int64_t i_star = s_istar;
     const int64_t last = i_star >= 0 ? i_star : W - 1;      /* attempts consumed: 0..last */
-    /* pass 2: counters over the consumed attempts */
-    unsigned long long counted = 0, integ = 0, steps = 0, rhs = 0, w_integ = 0, w_steps = 0, w_rhs = 0;
-    for (int64_t i = tid; i < W; i += blockDim.x) {
+    /* pass 2: the over-shoot (last, W) only; the totals over [0, W) come from k_wave_stats */
+    unsigned long long w_counted = 0, w_integ = 0, w_steps = 0, w_rhs = 0;
+    for (int64_t i = last + 1 + tid; i < W; i += blockDim.x) {
         const int code = A.code[off + i];
         const int slot = A.att_slot[off + i];
-        if (i <= last) {
-            if (code == 1 || code == 2) { ++counted; atomicAdd(&s_hist[A.basin[off + i] * 12 + A.month[off + i] - 1], 1u); }
-            if (slot >= 0) { ++integ; steps += (unsigned long long)A.n_time[slot]; rhs += (unsigned long long)A.nfev[slot]; }
-        } else if (slot >= 0) { ++w_integ; w_steps += (unsigned long long)A.n_time[slot]; w_rhs += (unsigned long long)A.nfev[slot]; }
+        if (code == 1 || code == 2) { ++w_counted; atomicAdd(&s_hist[A.basin[off + i] * 12 + A.month[off + i] - 1], 1u); }
+        if (slot >= 0) { ++w_integ; w_steps += (unsigned long long)A.n_time[slot]; w_rhs += (unsigned long long)A.nfev[slot]; }
     }
-    /* slots of this year beyond the consumed range (capacity cut) were never integrated */
-    atomicAdd(&s_acc[0], counted); atomicAdd(&s_acc[1], integ); atomicAdd(&s_acc[2], steps);
-    atomicAdd(&s_acc[3], rhs); atomicAdd(&s_acc[5], (w_integ << 40) | w_steps); atomicAdd(&s_acc[6], w_rhs);
+    if (w_counted) atomicAdd(&s_acc[0], w_counted);
+    if (w_integ) { atomicAdd(&s_acc[1], w_integ); atomicAdd(&s_acc[2], w_steps); atomicAdd(&s_acc[3], w_rhs); }
     __syncthreads();
     for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x)
-        A.n_seeds[(size_t)yr * TCR_N_BASINS * 12 + i] += (double)s_hist[i];
+        A.n_seeds[(size_t)yr * TCR_N_BASINS * 12 + i] += (double)(A.wave_hist[yr * TCR_N_BASINS * 12 + i] - s_hist[i]);
     if (tid == 0) {
         tcr_year_stats& s = A.stats[yr];
+        const unsigned long long* tot = A.wave_tot + yr * 4;
         const int got = min(want, s_running);
         s.attempts = A.k0[yr] + last + 1;
-        s.counted_seeds += (int64_t)s_acc[0];
-        s.integrated += (int64_t)s_acc[1];
-        s.storm_steps += (int64_t)s_acc[2];
-        s.rhs_evals += (int64_t)s_acc[3];
+        s.counted_seeds += (int64_t)(tot[0] - s_acc[0]);
+        s.integrated += (int64_t)(tot[1] - s_acc[1]);
+        s.storm_steps += (int64_t)(tot[2] - s_acc[2]);
+        s.rhs_evals += (int64_t)(tot[3] - s_acc[3]);
         s.kept_steps += (int64_t)s_acc[4];
-        s.wasted_integrated += (int64_t)(s_acc[5] >> 40);
-        s.wasted_steps += (int64_t)(s_acc[5] & ((1ull << 40) - 1));
-        s.wasted_rhs_evals += (int64_t)s_acc[6];
+        s.wasted_integrated += (int64_t)s_acc[1];
+        s.wasted_steps += (int64_t)s_acc[2];
+        s.wasted_rhs_evals += (int64_t)s_acc[3];
         s.n_kept = nt0 + got;
         s.n_waves += 1;
         A.nt[yr] = nt0 + got;

@@ -79,6 +79,7 @@ struct Workspace {
     int ns = 0;
     DevBuf code, basin, month, att_slot, a_lon, a_lat, a_v0, a_m0;   /* per attempt */
     DevBuf blk_count, blk_off;                                       /* per 256-attempt seed block */
+    DevBuf att_kept, wave_tot;                                       /* k_wave_stats: byte per attempt; per-year totals + histogram */
     DevBuf s_ym, s_lon, s_lat, s_v0, s_m0, s_hbl, s_att, s_key;       /* per slot */
     DevBuf n_time, status, nfev, flags, cand;
     DevBuf coef, ftab, track, env, vmax;
@@ -89,7 +90,7 @@ struct Workspace {
     DevBuf out;            /* device-side result block when the caller passes host pointers */
     void release_all()
     {
-        DevBuf* all[] = {&code, &basin, &month, &att_slot, &a_lon, &a_lat, &a_v0, &a_m0, &blk_count, &blk_off,
+        DevBuf* all[] = {&code, &basin, &month, &att_slot, &a_lon, &a_lat, &a_v0, &a_m0, &blk_count, &blk_off, &att_kept, &wave_tot,
                          &s_ym, &s_lon, &s_lat, &s_v0, &s_m0, &s_hbl, &s_att, &s_key,
                          &n_time, &status, &nfev, &flags, &cand, &coef, &ftab, &track, &env, &vmax, &counters, &year_i64,
                          &year_i32, &row_slot, &stats, &out};
@@ -118,9 +119,10 @@ struct tcr_handle {
     AxisBuf ax_lon_b, ax_lat_b, ax_lon_l, ax_lat_l, ax_lon_m, ax_lat_m;
     bool have_static = false, have_masks = false;
     /* tuning */
-    int integ_variant = 6, oversub_permille = 1100, interp_variant = 0;
+    int integ_variant = 6, oversub_permille = 1020, interp_variant = 0;
     /* survival statistics of earlier tcr_run_years calls on this handle: size the first wave */
     double hint_kept_rate = 0.0, hint_pass_rate = 0.0;
+    std::vector<double> hint_year_rate;     /* per year slot of the previous call (same n_years): survival differs by year */
     int64_t max_wave = 0, max_slots = 0;
     Workspace ws;
     void* pinned = nullptr;      /* small pinned read-back area */
@@ -543,7 +545,7 @@ static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_yea
         const size_t c = (size_t)att_cap, nb = (c + 255) / 256;
         if (w.code.ensure(c * 4) || w.basin.ensure(c * 4) || w.month.ensure(c * 4) || w.att_slot.ensure(c * 4) ||
             w.a_lon.ensure(c * 8) || w.a_lat.ensure(c * 8) || w.a_v0.ensure(c * 8) || w.a_m0.ensure(c * 8) ||
-            w.blk_count.ensure(nb * 4) || w.blk_off.ensure(nb * 4))
+            w.blk_count.ensure(nb * 4) || w.blk_off.ensure(nb * 4) || w.att_kept.ensure(c + 16))
             return -1;
         w.att_cap = att_cap;
     }
@@ -559,6 +561,7 @@ static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_yea
     }
     if (w.counters.ensure(64)) return -1;
     const size_t ny = (size_t)std::max(n_years, 1);
+    if (w.wave_tot.ensure(ny * (4 * 8 + TCR_N_BASINS * 12 * 4))) return -1;
     if (w.year_i64.ensure((4 * ny + 1) * 8) || w.year_i32.ensure(3 * ny * 4) || w.stats.ensure(ny * sizeof(tcr_year_stats))) return -1;
     return 0;
 }
@@ -755,32 +758,43 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
     const int ns = h->ctx.p.n_steps;
     const size_t rows = (size_t)n_years * n_tracks;
 
-    /* wave capacity: attempts and slots, bounded by a memory budget and by what the job needs */
-    size_t free_b = 0, total_b = 0;
-    CK(cudaMemGetInfo(&free_b, &total_b));
+    /* wave capacity: attempts and slots -- what the job is expected to consume in its first wave,
+     * bounded by a memory budget.  A workspace that already fits is reused without touching the
+     * allocator (cudaMemGetInfo / cudaMalloc are millisecond-class host calls). */
     const size_t out_bytes = on_device ? 0 : rows * ns * 72 + rows * 12 + (size_t)n_years * 84 * 8;
     {
         Workspace& w0 = h->ws;
-        size_t held = w0.ftab.bytes + w0.track.bytes + w0.env.bytes + w0.vmax.bytes + w0.coef.bytes + w0.out.bytes;
-        size_t budget = std::min<size_t>((size_t)64 << 30, (size_t)((free_b + held) * 0.6));
-        if (budget > out_bytes) budget -= out_bytes;
         const bool hinted = h->hint_kept_rate > 0.0;
         const double pass_est = hinted ? std::min(1.0, h->hint_pass_rate * 1.25 + 0.01) : 0.30;
-        int64_t att_cap = (int64_t)((double)budget / ((double)kAttemptBytes + pass_est * (double)slot_bytes(ns)));
-        /* what the whole job is expected to consume in its first wave */
-        double need = hinted ? (double)rows / h->hint_kept_rate * (h->oversub_permille / 1000.0) + 512.0 * n_years
-                             : (double)rows * 640.0;
-        att_cap = std::min<int64_t>(att_cap, std::max<int64_t>(65536, (int64_t)(need * 1.05)));
-        if (h->max_wave > 0) att_cap = std::min(att_cap, h->max_wave);
-        att_cap = std::max<int64_t>(att_cap, 4096);
-        int64_t slot_cap = std::max<int64_t>(4096, (int64_t)((double)att_cap * pass_est) + 1024);
-        slot_cap = std::min(slot_cap, att_cap);
-        /* reuse a workspace that is big enough for at least half of that; never shrink */
-        if (w0.ns == ns && w0.att_cap >= att_cap / 2 && w0.slot_cap >= slot_cap / 2 && w0.att_cap >= 4096) {
-            att_cap = std::max(w0.att_cap, (int64_t)0); slot_cap = w0.slot_cap;
-            if (h->max_wave > 0) att_cap = std::min(att_cap, h->max_wave);
+        double need = (double)rows * 640.0;
+        if (hinted) {
+            need = 0.0;
+            for (int y = 0; y < n_years; ++y) {
+                const double rate = ((int)h->hint_year_rate.size() == n_years && h->hint_year_rate[y] > 0.0) ? h->hint_year_rate[y]
+                                                                                                             : h->hint_kept_rate;
+                need += ((double)n_tracks + 4.0 * std::sqrt((double)n_tracks) + 8.0) / rate * (h->oversub_permille / 1000.0);
+            }
         }
-        if (ws_ensure(h, att_cap, slot_cap, n_years)) return -1;
+        int64_t want_att = std::max<int64_t>(65536, (int64_t)(need * 1.05));
+        if (h->max_wave > 0) want_att = std::min(want_att, h->max_wave);
+        want_att = std::max<int64_t>(want_att, 4096);
+        int64_t want_slot = std::min(want_att, std::max<int64_t>(4096, (int64_t)((double)want_att * pass_est) + 1024));
+        const bool fits = w0.ns == ns && w0.att_cap >= want_att && w0.slot_cap >= want_slot &&
+                          (on_device || w0.out.bytes >= out_bytes + 256);
+        if (!fits) {
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            size_t held = w0.ftab.bytes + w0.track.bytes + w0.env.bytes + w0.vmax.bytes + w0.coef.bytes + w0.out.bytes;
+            size_t budget = std::min<size_t>((size_t)64 << 30, (size_t)((free_b + held) * 0.6));
+            if (budget > out_bytes) budget -= out_bytes;
+            const int64_t cap_mem = (int64_t)((double)budget / ((double)kAttemptBytes + pass_est * (double)slot_bytes(ns)));
+            /* 25 % headroom so that the next call's slightly different estimate still fits */
+            int64_t att_cap = std::max<int64_t>(4096, std::min(cap_mem, want_att + want_att / 4));
+            int64_t slot_cap = std::min(att_cap, std::max<int64_t>(4096, (int64_t)((double)att_cap * pass_est) + 1024));
+            if (ws_ensure(h, std::max(att_cap, w0.att_cap), std::max(slot_cap, w0.slot_cap), n_years)) return -1;
+        } else if (ws_ensure(h, w0.att_cap, w0.slot_cap, n_years)) {
+            return -1;
+        }
     }
     Workspace& w = h->ws;
     int64_t cap = w.att_cap;
@@ -828,6 +842,24 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
     unsigned int* d_ncand = d_nslots + 1;
     unsigned int* d_npass = d_nslots + 2;
 
+    std::vector<tcr_year_stats> hstats(n_years);
+    bool final_done = false;
+    auto final_copies = [&]() -> int {
+        CK(cudaMemcpyAsync(hstats.data(), w.stats.p, (size_t)n_years * sizeof(tcr_year_stats), cudaMemcpyDeviceToHost, s));
+        if (!on_device) {
+            CK(cudaMemcpyAsync(lon, d_lon, rows * ns * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(lat, d_lat, rows * ns * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(v, d_v, rows * ns * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(m, d_m, rows * ns * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(vmax, d_vmax, rows * ns * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(env, d_env, rows * ns * 32, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(tc_month, d_month, rows * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(tc_basin, d_basin, rows * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(n_seeds, d_seeds, (size_t)n_years * 84 * 8, cudaMemcpyDeviceToHost, s));
+        }
+        return 0;
+    };
+
     const int max_waves = 4096;
     const double oversub = h->oversub_permille / 1000.0;
     int64_t sum_pass = 0, sum_att_launched = 0;
@@ -836,17 +868,21 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         int n_active = 0;
         for (int y = 0; y < n_years; ++y) if (nt[y] < n_tracks) ++n_active;
         if (!n_active) break;
-        /* attempts wanted per year: remaining tracks / survival rate (this year's own once it has
-         * produced tracks, else the handle's hint, else a probe), over-subscribed */
+        /* attempts wanted per year: (remaining tracks + a Poisson margin of ~3.5 sigma) / survival rate --
+         * this year's own rate once it has produced tracks, else the hint of the previous call for the
+         * same year slot, else the handle's average, else a probe -- times the over-subscription.
+         * A mop-up wave costs a full kernel tail (~2 ms), so falling short must be rare. */
         double want_total = 0.0;
         std::vector<double> want(n_years, 0.0);
         for (int y = 0; y < n_years; ++y) {
             if (nt[y] >= n_tracks) continue;
             const double remaining = (double)(n_tracks - nt[y]);
+            const double target = remaining + 3.5 * std::sqrt(remaining) + 4.0;
             double wy;
-            if (nt[y] > 0) wy = remaining / ((double)nt[y] / (double)att_total[y]) * oversub + 256.0;
+            if (nt[y] > 0) wy = target / ((double)nt[y] / (double)att_total[y]) * oversub;
             else if (att_total[y] > 0) wy = (double)att_total[y] * 4.0;
-            else if (h->hint_kept_rate > 0.0) wy = remaining / h->hint_kept_rate * oversub + 256.0;
+            else if ((int)h->hint_year_rate.size() == n_years && h->hint_year_rate[y] > 0.0) wy = target / h->hint_year_rate[y] * oversub;
+            else if (h->hint_kept_rate > 0.0) wy = target / h->hint_kept_rate * oversub;
             else wy = std::max(2048.0, remaining * 32.0);
             want[y] = wy;
             want_total += wy;
@@ -923,19 +959,32 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         }
         CKK(h);
 
+        WaveStatsArgs wa;
+        memset(&wa, 0, sizeof wa);
+        wa.n_years = n_years; wa.wave_off = d_wave_off; wa.consumed = d_consumed;
+        wa.code = sa.code; wa.basin = sa.basin; wa.month = sa.month; wa.att_slot = as.att_slot;
+        wa.n_time = a.n_time; wa.nfev = a.nfev; wa.flags = a.flags;
+        wa.att_kept = w.att_kept.as<uint8_t>();
+        wa.wave_tot = w.wave_tot.as<unsigned long long>();
+        wa.wave_hist = reinterpret_cast<unsigned int*>(wa.wave_tot + 4 * (size_t)n_years);
+        CK(cudaMemsetAsync(w.wave_tot.p, 0, (size_t)n_years * (4 * 8 + TCR_N_BASINS * 12 * 4), s));
+
         SelectArgs se;
         memset(&se, 0, sizeof se);
         se.n_tracks = n_tracks; se.wave_off = d_wave_off; se.k0 = d_k0; se.consumed = d_consumed;
         se.code = sa.code; se.basin = sa.basin; se.month = sa.month; se.att_slot = as.att_slot;
-        se.n_time = a.n_time; se.nfev = a.nfev; se.flags = a.flags;
+        se.n_time = a.n_time; se.nfev = a.nfev;
+        se.att_kept = wa.att_kept; se.wave_tot = wa.wave_tot; se.wave_hist = wa.wave_hist;
         se.nt = d_nt; se.used = d_used; se.row_slot = w.row_slot.as<int32_t>();
         se.tc_month = d_month; se.tc_basin = d_basin; se.n_seeds = d_seeds;
         se.stats = w.stats.as<tcr_year_stats>();
         {
             LaunchTimer lt_(h, TCR_K_SELECT);
+            k_wave_stats<<<seed_blocks, 256, 0, s>>>(wa);
             k_select<<<n_years, 1024, 0, s>>>(se);
         }
         CKK(h);
+        h->launches += 1;
 
         GatherArgs ga;
         memset(&ga, 0, sizeof ga);
@@ -951,7 +1000,12 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         CK(cudaMemcpyAsync(pin_nt, d_nt, n_years * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(pin_used, d_consumed, n_years * 8, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(pin_used + n_years, d_npass, 4, cudaMemcpyDeviceToHost, s));
+        /* a wave sized from survival hints almost always completes every year: queue the final
+         * read-back behind it so that the call costs ONE host synchronisation, not two */
+        const bool speculative = h->hint_kept_rate > 0.0 && scale == 1.0;
+        if (speculative) { if (final_copies()) return -1; }
         CK(cudaStreamSynchronize(s));
+        final_done = speculative;
         sum_pass += (int64_t)(*reinterpret_cast<unsigned int*>(pin_used + n_years));
         sum_att_launched += total;
         for (int y = 0; y < n_years; ++y) {
@@ -966,20 +1020,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
     }
     bool complete = true;
     for (int y = 0; y < n_years; ++y) if (nt[y] < n_tracks) complete = false;
-    std::vector<tcr_year_stats> hstats(n_years);
-    CK(cudaMemcpyAsync(hstats.data(), w.stats.p, (size_t)n_years * sizeof(tcr_year_stats), cudaMemcpyDeviceToHost, s));
-
-    if (!on_device) {
-        CK(cudaMemcpyAsync(lon, d_lon, rows * ns * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(lat, d_lat, rows * ns * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(v, d_v, rows * ns * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(m, d_m, rows * ns * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(vmax, d_vmax, rows * ns * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(env, d_env, rows * ns * 32, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(tc_month, d_month, rows * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(tc_basin, d_basin, rows * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(n_seeds, d_seeds, (size_t)n_years * 84 * 8, cudaMemcpyDeviceToHost, s));
-    }
+    if (!final_done || !complete) { if (final_copies()) return -1; }
     CK(cudaStreamSynchronize(s));
     if (stats) memcpy(stats, hstats.data(), (size_t)n_years * sizeof(tcr_year_stats));
     if (complete && sum_att_launched > 0) {
@@ -987,6 +1028,9 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         int64_t kept = 0, consumed = 0;
         for (int y = 0; y < n_years; ++y) { kept += hstats[y].n_kept; consumed += hstats[y].attempts; }
         if (kept > 0 && consumed > 0) h->hint_kept_rate = (double)kept / (double)consumed;
+        h->hint_year_rate.assign(n_years, 0.0);
+        for (int y = 0; y < n_years; ++y)
+            if (hstats[y].attempts > 0) h->hint_year_rate[y] = (double)hstats[y].n_kept / (double)hstats[y].attempts;
         h->hint_pass_rate = (double)sum_pass / (double)sum_att_launched;
     }
     if (!complete) return set_err("tcr_run_years: wave limit reached before every year produced %d tracks", n_tracks);
