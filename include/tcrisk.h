@@ -133,6 +133,9 @@ int tcr_upload_masks(tcr_handle* h, int nlat_m, int nlon_m, const double* lat_m,
  * [nlat][nlon] into the [nlat][nlon][20] record layout on the device.                      */
 int tcr_alloc_tables(tcr_handle* h, int n_ym, int nlat, int nlon, const double* lat, const double* lon);
 int tcr_upload_month(tcr_handle* h, int ym, const float* const* fields /*[TCR_N_FIELDS]*/);
+/* n_months consecutive months from one contiguous host block [n_months][19][nlat][nlon]: one
+ * host->device copy and one table-building launch (a year, or all years of a batch, at once) */
+int tcr_upload_months(tcr_handle* h, int ym0, int n_months, const float* planes);
 /* same, source planes already in HBM as one contiguous [19][nlat][nlon] float32 block       */
 int tcr_upload_month_dev(tcr_handle* h, int ym, const float* d_planes);
 

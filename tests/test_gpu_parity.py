@@ -422,3 +422,27 @@ def test_cfg5_wp_900s_properties():
         assert (r["tc_basin"][0] == 6).mean() > 0.99                        # WP (sorted index 6), border points aside
     finally:
         eng.close()
+
+
+def test_year_pipeline_matches_blocking_call(na_year, na_year_eng):
+    """Double-buffered batches (download of batch i overlapping batch i+1) return exactly what the
+    blocking call returns, for every batch in flight."""
+    import torch
+    from tropical_cyclone_risk_b200.pipeline import YearPipeline
+    torch.cuda.set_device(0)
+    pipe = YearPipeline(na_year_eng, 1, 40, depth=2)
+    try:
+        tickets = []
+        for seed in (3, 4, 5):
+            t, stats = pipe.submit([0], [2001], seed, )
+            tickets.append((t, seed, stats))
+            if len(tickets) >= 2:                                # at most `depth` results are alive
+                tk, sd, st = tickets.pop(0)
+                got = {k: np.array(v) for k, v in pipe.result(tk).items()}
+                want = na_year_eng.run_years([0], [2001], sd, 40)
+                for key in ("lon", "lat", "v", "m", "vmax", "env", "tc_month", "tc_basin", "n_seeds"):
+                    assert _same(got[key], want[key]), (sd, key)
+                assert st[0]["storm_steps"] == want["stats"][0]["storm_steps"]
+        pipe.drain()
+    finally:
+        na_year_eng.set_stream(0)

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libtcrisk.so")
 
 SYMBOLS = (
     "tcr_create", "tcr_destroy", "tcr_last_error", "tcr_set_stream", "tcr_synchronize", "tcr_version",
-    "tcr_upload_static", "tcr_upload_masks", "tcr_alloc_tables", "tcr_upload_month", "tcr_upload_month_dev",
+    "tcr_upload_static", "tcr_upload_masks", "tcr_alloc_tables", "tcr_upload_month", "tcr_upload_months", "tcr_upload_month_dev",
     "tcr_env_interp", "tcr_integrate", "tcr_run_years", "tcr_seed_attempts", "tcr_set_tuning",
     "tcr_launch_count", "tcr_set_interp_variant", "tcr_host_alloc", "tcr_host_free",
     "tcr_set_timing", "tcr_kernel_time",
@@ -48,6 +48,7 @@ def load():
     lib.tcr_alloc_tables.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     lib.tcr_upload_month.argtypes = [vp, C.c_int, C.POINTER(vp)]
     lib.tcr_upload_month_dev.argtypes = [vp, C.c_int, vp]
+    lib.tcr_upload_months.argtypes = [vp, C.c_int, C.c_int, vp]
     lib.tcr_env_interp.argtypes = [vp, C.c_int64, vp, vp, vp, vp, C.c_int]
     lib.tcr_integrate.argtypes = [vp, C.c_int64] + [vp] * 14 + [C.c_int]
     lib.tcr_run_years.argtypes = [vp, C.c_int, vp, vp, C.c_uint32, C.c_int] + [vp] * 9 + [C.POINTER(TcrYearStats), C.c_int]

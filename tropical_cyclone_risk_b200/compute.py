@@ -147,8 +147,7 @@ def run_years(years, n_tracks, b, device=None, engine=None, bounds=None):
         planes.append(pl)
     engine.alloc_tables(12 * len(years), lon, lat)
     for i, pl in enumerate(planes):
-        for k in range(12):
-            engine.upload_month(12 * i + k, pl[k])
+        engine.upload_months(12 * i, pl)
     ym_base = np.arange(len(years), dtype=np.int32) * 12
     return engine.run_years(ym_base, np.asarray(years, dtype=np.int32), _session.run_seed, n_tracks)
 

@@ -11,10 +11,13 @@
 /* table builders: planes -> cell records                                                    */
 /* ======================================================================================== */
 /* one month: planes [19][nlat][nlon] float32 -> rec [ncy][ncx][20] float4 (corner quads)      */
+/* blockIdx.y = month of a batch: planes [n][19][nlat][nlon] -> rec [n][ncy][ncx][20] */
 __global__ void k_build_month(const float* __restrict__ planes, float4* __restrict__ rec, int nlat, int nlon)
 {
     const int ncx = nlon - 1, ncy = nlat - 1;
     const size_t total = (size_t)ncx * ncy * TCR_REC_F4;
+    planes += (size_t)blockIdx.y * TCR_N_FIELDS * nlat * nlon;
+    rec += (size_t)blockIdx.y * total;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int ch = (int)(idx % TCR_REC_F4);
         size_t cell = idx / TCR_REC_F4;

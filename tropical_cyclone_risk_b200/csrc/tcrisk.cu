@@ -444,6 +444,25 @@ int tcr_upload_month_dev(tcr_handle* h, int ym, const float* d_planes)
     return 0;
 }
 
+int tcr_upload_months(tcr_handle* h, int ym0, int n_months, const float* planes)
+{
+    if (!h || !planes) return set_err("tcr_upload_months: null argument");
+    if (!h->rec.p) return set_err("tcr_upload_months: call tcr_alloc_tables first");
+    if (n_months <= 0) return 0;
+    if (ym0 < 0 || ym0 + n_months > h->n_ym) return set_err("tcr_upload_months: months [%d, %d) out of range [0, %d)", ym0, ym0 + n_months, h->n_ym);
+    CK(cudaSetDevice(h->device));
+    const size_t plane = (size_t)h->nlat * h->nlon, bytes = plane * TCR_N_FIELDS * sizeof(float) * (size_t)n_months;
+    if (h->stage.ensure(bytes)) return -1;
+    CK(cudaMemcpyAsync(h->stage.p, planes, bytes, cudaMemcpyHostToDevice, h->stream));
+    {
+        LaunchTimer lt_(h, TCR_K_BUILD);
+        dim3 grid((unsigned)grid_for(h->month_f4, 256, h->num_sms), (unsigned)n_months);
+        k_build_month<<<grid, 256, 0, h->stream>>>(h->stage.as<float>(), h->rec.as<float4>() + h->month_f4 * (size_t)ym0, h->nlat, h->nlon);
+    }
+    CKK(h);
+    return 0;
+}
+
 int tcr_upload_month(tcr_handle* h, int ym, const float* const* fields)
 {
     if (!h || !fields) return set_err("tcr_upload_month: null argument");

@@ -131,6 +131,14 @@ class Engine:
         ptrs = (C.c_void_p * layout.N_FIELDS)(*[planes[i].ctypes.data for i in range(layout.N_FIELDS)])
         _lib.check(self.lib.tcr_upload_month(self._h, int(ym), ptrs))
 
+    def upload_months(self, ym0, planes):
+        """planes: float32 [n][19][nlat][nlon], C-contiguous host memory (pinned for full PCIe speed):
+        one copy + one launch for all n months."""
+        if not (isinstance(planes, np.ndarray) and planes.dtype == np.float32 and planes.flags.c_contiguous):
+            planes = _arr(planes, np.float32)
+        assert planes.shape[1:] == (layout.N_FIELDS,) + self.grid, (planes.shape, self.grid)
+        _lib.check(self.lib.tcr_upload_months(self._h, int(ym0), int(planes.shape[0]), _ptr(planes)))
+
     def upload_month_dev(self, ym, d_planes_ptr):
         _lib.check(self.lib.tcr_upload_month_dev(self._h, int(ym), C.c_void_p(int(d_planes_ptr))))
 
@@ -140,8 +148,7 @@ class Engine:
         if mask_planes is not None:
             self.upload_masks(mask_lon, mask_lat, mask_planes)
         self.alloc_tables(planes.shape[0], lon, lat)
-        for ym in range(planes.shape[0]):
-            self.upload_month(ym, planes[ym])
+        self.upload_months(0, planes)
         self.synchronize()
 
     # -- hot path -----------------------------------------------------------------------------

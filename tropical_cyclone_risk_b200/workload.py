@@ -60,5 +60,4 @@ class Workload:
         eng.synchronize()
 
     def upload_tables(self, eng):
-        for ym in range(self.n_ym):
-            eng.upload_month(ym, self.planes[ym])
+        eng.upload_months(0, self.planes)
