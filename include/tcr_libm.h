@@ -221,4 +221,17 @@ TCR_HD double tcr_tanh(double x)
     return x < 0.0 ? -t : t;
 }
 
+/* ---- great-circle distance, km (haversine; reference util/sphere.py:15-30 and the notebook's
+ * own copy, notebooks/sample_analysis.ipynb cell 13), radius of the sphere in km ---------------- */
+TCR_HD double tcr_haversine_r(double r_km, double lon1, double lat1, double lon2, double lat2)
+{
+    lon1 = lon1 * TCR_DEG2RAD; lat1 = lat1 * TCR_DEG2RAD;
+    lon2 = lon2 * TCR_DEG2RAD; lat2 = lat2 * TCR_DEG2RAD;
+    double dlon = lon2 - lon1, dlat = lat2 - lat1;
+    double sa = tcr_sin(dlat / 2), sb = tcr_sin(dlon / 2);
+    double a = sa * sa + tcr_cos(lat1) * tcr_cos(lat2) * (sb * sb);
+    double c = 2.0 * tcr_asin(sqrt(a));
+    return r_km * c;
+}
+
 #endif /* TCR_LIBM_H */

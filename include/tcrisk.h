@@ -205,12 +205,24 @@ int64_t tcr_launch_count(tcr_handle* h);
 #define TCR_K_GATHER       6
 #define TCR_K_BUILD        7
 #define TCR_K_FTABLE       8
-#define TCR_N_KERNEL_CLASSES 9
+#define TCR_K_POI          9
+#define TCR_N_KERNEL_CLASSES 10
 int tcr_set_timing(tcr_handle* h, int enable);
 int tcr_kernel_time(tcr_handle* h, int kernel_class, double* ms, int64_t* launches);
 /* tcr_env_interp implementation: 0 = per-lane LDG.128 gathers, 1 = TMA bulk copies
  * (cp.async.bulk) of the cell records into shared memory behind an mbarrier pipeline        */
 int tcr_set_interp_variant(tcr_handle* h, int variant);
+/* ---- return-period reduction over finished tracks (SURVEY 8f "next" row N4) ------------- */
+/* replaces: notebooks/sample_analysis.ipynb cell 15 -- dists = haversine(clon, clat, lon_trks,
+ * lat_trks); vmax_at_poi = vmax_trks.where(dists <= radius_km).max(dim='time').  lon/lat/vmax
+ * [n_rows][n_steps] (NaN padded), out [n_rows] (NaN where the track never comes within the
+ * radius).  r_earth_m = 6378000 in the notebook.  Host or device pointers per on_device.      */
+int tcr_poi_vmax(tcr_handle* h, int64_t n_rows, int n_steps, const double* lon, const double* lat, const double* vmax,
+                 double poi_lon, double poi_lat, double radius_km, double r_earth_m, double* out, int on_device);
+/* replaces: cell 17 -- exceedance_count[b] = sum(vmax_at_poi >= vmax_bins[b]); n_bins <= 64;
+ * v host or device per on_device, bins and counts host                                        */
+int tcr_exceedance(tcr_handle* h, int64_t n, const double* v, int n_bins, const double* bins, int64_t* counts, int on_device);
+
 /* page-locked host memory for the caller's input planes / result arrays (the reference's
  * NumPy arrays of util/compute.py:126-133 become views of this block): makes the host<->device
  * copies of tcr_upload_month / tcr_run_years run at PCIe speed                               */

@@ -873,6 +873,39 @@ void orc_run_attempts(const tcr_params* p, const orc_env* envs /*[12]*/, const o
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* return-period reduction: notebooks/sample_analysis.ipynb cells 13-17      */
+/* ------------------------------------------------------------------------------------ */
+/* cell 15: dists = haversine(clon, clat, lon_trks, lat_trks);
+ *          vmax_at_poi = vmax_trks.where(dists <= radius).max(dim='time')   (NaN if never within) */
+void orc_poi_vmax(int64_t n_rows, int n_steps, const double* lon, const double* lat, const double* vmax,
+                  double poi_lon, double poi_lat, double radius_km, double r_earth_m, double* out)
+{
+    const double r_km = r_earth_m / 1000.0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        double best = NAN;
+        for (int k = 0; k < n_steps; ++k) {
+            const size_t i = (size_t)r * n_steps + k;
+            double d = tcr_haversine_r(r_km, poi_lon, poi_lat, lon[i], lat[i]);
+            if (d <= radius_km) {
+                double v = vmax[i];
+                if (!tcr_isnan(v) && (tcr_isnan(best) || v > best)) best = v;
+            }
+        }
+        out[r] = best;
+    }
+}
+
+/* cell 17: exceedance_count[i] = sum(vmax_at_poi >= vmax_bins[i]) */
+void orc_exceedance(int64_t n, const double* v, int n_bins, const double* bins, int64_t* counts)
+{
+    for (int b = 0; b < n_bins; ++b) {
+        int64_t c = 0;
+        for (int64_t i = 0; i < n; ++i) if (v[i] >= bins[b]) ++c;
+        counts[b] = c;
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* unit-test hooks                                                                       */
 /* ------------------------------------------------------------------------------------ */
 void orc_dydt_at(const tcr_params* p, const orc_env* e, const double* coef,

@@ -233,6 +233,25 @@ def run_attempts(p, env, ym_base, masks, run_seed, year_key, k0, n, want_tracks=
     return out
 
 
+def poi_vmax(lon, lat, vmax, poi_lon, poi_lat, radius_km=100.0, r_earth_m=6378000.0):
+    """notebooks/sample_analysis.ipynb cell 15: per-track maximum of vmax within radius_km of a point."""
+    lon, lat, vmax = (np.ascontiguousarray(x, dtype=np.float64) for x in (lon, lat, vmax))
+    n_steps = lon.shape[-1]
+    out = np.empty(lon.size // n_steps)
+    lib().orc_poi_vmax(C.c_int64(out.size), C.c_int(n_steps), _dp(lon), _dp(lat), _dp(vmax), C.c_double(poi_lon),
+                       C.c_double(poi_lat), C.c_double(radius_km), C.c_double(r_earth_m), _dp(out))
+    return out.reshape(lon.shape[:-1])
+
+
+def exceedance(v, bins):
+    """cell 17: number of tracks whose vmax_at_poi reaches each bin."""
+    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+    bins = np.ascontiguousarray(bins, dtype=np.float64)
+    counts = np.zeros(bins.size, np.int64)
+    lib().orc_exceedance(C.c_int64(v.size), _dp(v), C.c_int(bins.size), _dp(bins), counts.ctypes.data_as(C.POINTER(C.c_int64)))
+    return counts
+
+
 def phases_for(run_seed, year_key, k):
     ph = np.empty(N_PHASES)
     lib().orc_phases(C.c_uint32(run_seed), C.c_int32(year_key), C.c_int64(k), _dp(ph))

@@ -1463,3 +1463,60 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ TcrCtx c
         eo[0] = e0; eo[1] = e1;
     }
 }
+
+/* ======================================================================================== */
+/* return-period reduction over the finished-track tensor:                     */
+/* notebooks/sample_analysis.ipynb cells 13-17.  One warp per track; a streaming, HBM-bound    */
+/* pass (24 B per sample: lon, lat, vmax): the fp64 haversine is only evaluated for samples    */
+/* whose latitude is within the radius of the point (a great-circle distance is never shorter  */
+/* than R |dlat|, so the 1 % slack below cannot change any result).                            */
+/* ======================================================================================== */
+__global__ void __launch_bounds__(256) k_poi_vmax(int64_t n_rows, int n_steps, const double* __restrict__ lon,
+                                                  const double* __restrict__ lat, const double* __restrict__ vmax,
+                                                  double poi_lon, double poi_lat, double radius_km, double r_km,
+                                                  double* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double band_deg = radius_km / r_km * (180.0 / TCR_PI) * 1.01 + 1e-9;
+    for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
+        const size_t base = (size_t)row * n_steps;
+        double best = -INFINITY;
+        bool have = false;
+        for (int k = lane; k < n_steps; k += 32) {
+            const double la = __ldcs(lat + base + k);
+            if (fabs(la - poi_lat) > band_deg) continue;            /* also false for NaN: falls through */
+            const double lo = __ldcs(lon + base + k);
+            const double d = tcr_haversine_r(r_km, poi_lon, poi_lat, lo, la);
+            if (d <= radius_km) {
+                const double v = __ldcs(vmax + base + k);
+                if (!tcr_isnan(v)) { have = true; if (v > best) best = v; }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double o = __shfl_xor_sync(TCR_FULL, best, d);
+            const int h2 = __shfl_xor_sync(TCR_FULL, (int)have, d);
+            if (o > best) best = o;
+            have = have || (h2 != 0);
+        }
+        if (lane == 0) out[row] = have ? best : NAN;
+    }
+}
+
+/* exceedance_count[b] = #{ i : v[i] >= bins[b] }  (cell 17); counts accumulate (zeroed by the host) */
+__global__ void __launch_bounds__(256) k_exceedance(int64_t n, const double* __restrict__ v, int n_bins,
+                                                    const double* __restrict__ bins, unsigned long long* __restrict__ counts)
+{
+    __shared__ unsigned int s_cnt[64];
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) s_cnt[b] = 0u;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double x = v[i];
+        for (int b = 0; b < n_bins; ++b)
+            if (x >= bins[b]) atomicAdd(&s_cnt[b], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x)
+        if (s_cnt[b]) atomicAdd(&counts[b], (unsigned long long)s_cnt[b]);
+}

@@ -1056,4 +1056,71 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
     return 0;
 }
 
+/* ---- return-period reduction ----------------------------------------------------- */
+int tcr_poi_vmax(tcr_handle* h, int64_t n_rows, int n_steps, const double* lon, const double* lat, const double* vmax,
+                 double poi_lon, double poi_lat, double radius_km, double r_earth_m, double* out, int on_device)
+{
+    if (!h) return set_err("null handle");
+    if (n_rows < 0 || n_steps <= 0) return set_err("tcr_poi_vmax: bad shape");
+    if (n_rows == 0) return 0;
+    if (!lon || !lat || !vmax || !out) return set_err("tcr_poi_vmax: null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t n = (size_t)n_rows * n_steps;
+    const double *d_lon = lon, *d_lat = lat, *d_v = vmax;
+    double* d_out = out;
+    DevBuf in, o;
+    if (!on_device) {
+        if (in.ensure(n * 24) || o.ensure((size_t)n_rows * 8)) { in.release(); o.release(); return -1; }
+        double* b = in.as<double>();
+        CK(cudaMemcpyAsync(b, lon, n * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b + n, lat, n * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b + 2 * n, vmax, n * 8, cudaMemcpyHostToDevice, s));
+        d_lon = b; d_lat = b + n; d_v = b + 2 * n; d_out = o.as<double>();
+    }
+    {
+        LaunchTimer lt_(h, TCR_K_POI);
+        const int grid = (int)std::min<int64_t>((n_rows + 7) / 8, (int64_t)h->num_sms * 16);
+        k_poi_vmax<<<grid, 256, 0, s>>>(n_rows, n_steps, d_lon, d_lat, d_v, poi_lon, poi_lat, radius_km, r_earth_m / 1000.0, d_out);
+    }
+    CKK(h);
+    if (!on_device) {
+        CK(cudaMemcpyAsync(out, d_out, (size_t)n_rows * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        in.release(); o.release();
+    }
+    return 0;
+}
+
+int tcr_exceedance(tcr_handle* h, int64_t n, const double* v, int n_bins, const double* bins, int64_t* counts, int on_device)
+{
+    if (!h) return set_err("null handle");
+    if (n < 0 || n_bins < 0 || n_bins > 64) return set_err("tcr_exceedance: bad shape (at most 64 bins)");
+    if (!counts || (n_bins && !bins) || (n && !v)) return set_err("tcr_exceedance: null argument");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    DevBuf buf;
+    if (buf.ensure((size_t)n_bins * 16 + 64 + (on_device ? 0 : (size_t)n * 8))) return -1;
+    double* d_bins = buf.as<double>();
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(d_bins + n_bins);
+    const double* d_v = v;
+    CK(cudaMemcpyAsync(d_bins, bins, (size_t)n_bins * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(d_cnt, 0, (size_t)n_bins * 8, s));
+    if (!on_device && n) {
+        double* dv = reinterpret_cast<double*>(d_cnt + n_bins);
+        CK(cudaMemcpyAsync(dv, v, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+        d_v = dv;
+    }
+    if (n && n_bins) {
+        LaunchTimer lt_(h, TCR_K_POI);
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)h->num_sms * 8));
+        k_exceedance<<<grid, 256, 0, s>>>(n, d_v, n_bins, d_bins, d_cnt);
+    }
+    CKK(h);
+    CK(cudaMemcpyAsync(counts, d_cnt, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    buf.release();
+    return 0;
+}
+
 }  // extern "C"

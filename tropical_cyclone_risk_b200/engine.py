@@ -87,7 +87,8 @@ class Engine:
     def launch_count(self):
         return int(self.lib.tcr_launch_count(self._h))
 
-    KERNEL_CLASSES = ("env_interp", "integrate", "postprocess", "seed", "coef", "select", "gather", "build", "ftable")
+    KERNEL_CLASSES = ("env_interp", "integrate", "postprocess", "seed", "coef", "select", "gather", "build", "ftable",
+                      "poi")
 
     def set_timing(self, enable=True):
         """CUDA-event accounting of every kernel class on the handle's stream (resets the totals)."""
@@ -224,3 +225,31 @@ class Engine:
             vp(dptr["lon"]), vp(dptr["lat"]), vp(dptr["v"]), vp(dptr["m"]), vp(dptr["vmax"]), vp(dptr["env"]),
             vp(dptr["tc_month"]), vp(dptr["tc_basin"]), vp(dptr["n_seeds"]), stats, 1))
         return [{f: getattr(s, f) for f, _ in TcrYearStats._fields_} for s in stats]
+
+    # -- return-period reduction (notebooks/sample_analysis.ipynb cells 13-17) -----------------------
+    def poi_vmax(self, lon, lat, vmax, poi_lon, poi_lat, radius_km=100.0, r_earth_m=6378000.0):
+        """Per-track maximum of vmax while within radius_km of (poi_lon, poi_lat); NaN if never."""
+        lon, lat, vmax = (_arr(x, np.float64) for x in (lon, lat, vmax))
+        ns = lon.shape[-1]
+        out = np.empty(lon.size // ns)
+        _lib.check(self.lib.tcr_poi_vmax(self._h, out.size, ns, _ptr(lon), _ptr(lat), _ptr(vmax), float(poi_lon),
+                                         float(poi_lat), float(radius_km), float(r_earth_m), _ptr(out), 0))
+        return out.reshape(lon.shape[:-1])
+
+    def poi_vmax_dev(self, n_rows, n_steps, d_lon, d_lat, d_vmax, poi_lon, poi_lat, d_out, radius_km=100.0,
+                     r_earth_m=6378000.0):
+        vp = C.c_void_p
+        _lib.check(self.lib.tcr_poi_vmax(self._h, int(n_rows), int(n_steps), vp(d_lon), vp(d_lat), vp(d_vmax), float(poi_lon),
+                                         float(poi_lat), float(radius_km), float(r_earth_m), vp(d_out), 1))
+
+    def exceedance(self, v, bins, on_device_ptr=None, n=None):
+        """counts[b] = #(v >= bins[b]); v a host array, or a device pointer with its length n."""
+        bins = _arr(bins, np.float64)
+        counts = np.zeros(bins.size, np.int64)
+        if on_device_ptr is None:
+            v = _arr(v, np.float64).reshape(-1)
+            _lib.check(self.lib.tcr_exceedance(self._h, v.size, _ptr(v), bins.size, _ptr(bins), _ptr(counts), 0))
+        else:
+            _lib.check(self.lib.tcr_exceedance(self._h, int(n), C.c_void_p(int(on_device_ptr)), bins.size, _ptr(bins),
+                                               _ptr(counts), 1))
+        return counts
