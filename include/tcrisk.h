@@ -139,6 +139,25 @@ int tcr_upload_months(tcr_handle* h, int ym0, int n_months, const float* planes)
 /* same, source planes already in HBM as one contiguous [19][nlat][nlon] float32 block       */
 int tcr_upload_month_dev(tcr_handle* h, int ym, const float* d_planes);
 
+/* ---- per-month field preparation on the device (SURVEY 8f "next" row N1) ---------------- */
+/* replaces: the per-month body of run_tracks' setup loop (util/compute.py:107-121: NaN policy,
+ * PI scaling :76, chi transform :113-115, ocean regrid :117-118 via util/mat.py:159-164) and
+ * BetaAdvectionTrack._interp_basin_field (track/bam_track.py:72-74: basin crop of
+ * util/basins.py:57-75 + nan_to_num).  raw [17][nlat_g][nlon_g] float32 = the 14 wind statistics
+ * (channel order of the tables), vmax, chi, rh_mid on the GLOBAL grid (any row order: src_row maps
+ * output rows to storage rows, lat_g is in storage order); ocean [2][nlat_o][nlon_o] = mld, strat on
+ * their own ascending grid; src_col / src_row = the basin crop (with longitude re-wrapping) as
+ * index maps.  Writes month `ym` of the tables (ym < 0: do not upload) and, if planes_out is
+ * non-NULL, returns the 19 prepared float32 planes [19][nlat_b][nlon_b] to the host.          */
+typedef struct tcr_prep_spec {
+    int32_t nlat_g, nlon_g, nlat_o, nlon_o, nlat_b, nlon_b;
+    double pi_reduc, sqrt_ck_cd;  /* vpot = vmax * PI_reduc * sqrt(Ck/Cd), left to right (compute.py:76) */
+    double log_chi_fac, chi_fac;  /* namelist.py                          (compute.py:115) */
+} tcr_prep_spec;
+int tcr_prepare_month(tcr_handle* h, int ym, const tcr_prep_spec* spec, const float* raw, const float* ocean,
+                      const double* lon_g, const double* lat_g, const double* lon_o, const double* lat_o,
+                      const int32_t* src_col, const int32_t* src_row, float* planes_out);
+
 /* ---- stand-alone bilinear sampler (roofline kernel) ----------------------------------- */
 /* replaces: RectBivariateSpline(kx=1,ky=1).ev on every field (util/mat.py:142-153,
  * bam_track.py:93-108, coupled_fast.py:35-58,125-126).  out[n][21] float64.                */

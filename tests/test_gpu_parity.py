@@ -446,3 +446,51 @@ def test_year_pipeline_matches_blocking_call(na_year, na_year_eng):
         pipe.drain()
     finally:
         na_year_eng.set_stream(0)
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" row N1: per-month field preparation on the device
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("basin,descending", [("NA", False), ("GL", False), ("SP", True)])
+def test_prepare_month_on_device(basin, descending):
+    """tcr_prepare_month against fields.prepare_month (the NumPy restatement of util/compute.py:107-121,
+    track/bam_track.py:72-74, util/basins.py:57-75).  Everything is bit-identical except chi, whose
+    exp(log(.)) goes through tcr_libm on the device and glibc in NumPy: <= 1 float32 ulp."""
+    from tropical_cyclone_risk_b200 import fields, params, synth
+    from tropical_cyclone_risk_b200 import namelist as nl
+    from tropical_cyclone_risk_b200.engine import Engine
+    lon, lat = synth.era5_axes()
+    olon, olat = synth.ocean_axes()
+    raw = synth.synth_month_raw(2007, 8, lon, lat)
+    rng = np.random.default_rng(3)
+    for k in ("vmax", "chi", "ua250_Mean", "va850_Var"):                 # NaN policies
+        raw[k] = raw[k].copy()
+        raw[k][rng.random(raw[k].shape) < 0.02] = np.nan
+    mld, strat = synth.synth_ocean(olon, olat, 8)
+    mld = mld.copy(); mld[rng.random(mld.shape) < 0.05] = np.nan         # the real climatologies carry NaNs over land
+    bounds = params.basin_bounds(nl, basin)
+    want_lon, want_lat, want = fields.prepare_month(nl, bounds, lon, lat, raw, olon, olat, mld, strat)
+    lat_s, raw_s = (lat[::-1], {k: v[::-1] for k, v in raw.items()}) if descending else (lat, raw)
+    eng = Engine(params.params_from_namelist(nl, basin), device=0)
+    try:
+        got_lon, got_lat, got = eng.prepare_month(-1, nl, bounds, lon, lat_s, raw_s, olon, olat, mld, strat, return_planes=True)
+        assert np.array_equal(got_lon, want_lon) and np.array_equal(got_lat, want_lat)
+        for c in range(19):
+            if c == 14:
+                assert np.all(np.abs(got[c] - want[c]) <= np.spacing(np.abs(want[c]))), "chi"
+                assert (got[c] == want[c]).mean() > 0.999
+            else:
+                assert np.array_equal(got[c], want[c], equal_nan=True), c
+        # and the upload path: tables built from the device-prepared month sample like the host-prepared ones
+        st = synth.synth_static(full_res=False)
+        eng.upload_static(fields.prepare_static(bounds, st))
+        eng.alloc_tables(1, want_lon, want_lat)
+        eng.prepare_month(0, nl, bounds, lon, lat_s, raw_s, olon, olat, mld, strat)
+        q = np.random.default_rng(4)
+        qlon = q.uniform(bounds[0], bounds[2], 4000); qlat = q.uniform(bounds[1], bounds[3], 4000)
+        a = eng.env_interp(np.zeros(4000, np.int32), qlon, qlat)
+        eng.upload_month(0, got)
+        b = eng.env_interp(np.zeros(4000, np.int32), qlon, qlat)
+        assert _same(a, b)
+    finally:
+        eng.close()

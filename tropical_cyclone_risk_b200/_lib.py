@@ -13,7 +13,7 @@ SYMBOLS = (
     "tcr_upload_static", "tcr_upload_masks", "tcr_alloc_tables", "tcr_upload_month", "tcr_upload_months", "tcr_upload_month_dev",
     "tcr_env_interp", "tcr_integrate", "tcr_run_years", "tcr_seed_attempts", "tcr_set_tuning",
     "tcr_launch_count", "tcr_set_interp_variant", "tcr_host_alloc", "tcr_host_free",
-    "tcr_set_timing", "tcr_kernel_time", "tcr_poi_vmax", "tcr_exceedance",
+    "tcr_set_timing", "tcr_kernel_time", "tcr_poi_vmax", "tcr_exceedance", "tcr_prepare_month",
 )
 
 _lib = None
@@ -61,6 +61,7 @@ def load():
     lib.tcr_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.tcr_poi_vmax.argtypes = [vp, C.c_int64, C.c_int, vp, vp, vp, C.c_double, C.c_double, C.c_double, C.c_double, vp, C.c_int]
     lib.tcr_exceedance.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp, C.c_int]
+    lib.tcr_prepare_month.argtypes = [vp, C.c_int, vp] + [vp] * 9
     lib.tcr_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.tcr_host_free.argtypes = [vp]
     _lib = lib

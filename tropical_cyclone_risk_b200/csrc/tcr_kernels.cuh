@@ -1520,3 +1520,82 @@ __global__ void __launch_bounds__(256) k_exceedance(int64_t n, const double* __r
     for (int b = threadIdx.x; b < n_bins; b += blockDim.x)
         if (s_cnt[b]) atomicAdd(&counts[b], (unsigned long long)s_cnt[b]);
 }
+
+/* ======================================================================================== */
+/* per-month field preparation on the device: what the top of run_tracks does   */
+/* with xarray / NumPy per month (util/compute.py:107-121) and BetaAdvectionTrack does per    */
+/* field (track/bam_track.py:72-74): NaN policies, PI scaling, chi transform, bilinear regrid  */
+/* of the ocean climatologies to the thermo grid (util/mat.py:159-164), basin crop with        */
+/* longitude re-wrapping (util/basins.py:57-75, as index maps).  raw [17][nlat_g][nlon_g]:     */
+/* 14 wind statistics, vmax, chi, rh_mid; ocean [2][nlat_o][nlon_o]: mld, strat.               */
+/* out planes [19][nlat_b][nlon_b] float32 (the input of k_build_month).                       */
+/* ======================================================================================== */
+struct PrepArgs {
+    int nlat_g, nlon_g, nlat_o, nlon_o, nlat_b, nlon_b;
+    double pi_reduc, sqrt_ck_cd, log_chi_fac, chi_fac;
+    const float* raw; const float* ocean;
+    const double* lon_g; const double* lat_g; const double* lon_o; const double* lat_o;
+    const int32_t* src_col; const int32_t* src_row;
+    float* out;
+};
+
+__device__ __forceinline__ void tcr_locate_plain(const double* ax, int n, double x, int& i0, double& w0, double& w1)
+{
+    double a = x;
+    if (a < ax[0]) a = ax[0];
+    if (a > ax[n - 1]) a = ax[n - 1];
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (ax[mid] <= a) lo = mid; else hi = mid; }
+    if (lo > n - 2) lo = n - 2;
+    const double f = 1.0 / (ax[lo + 1] - ax[lo]);
+    i0 = lo; w0 = f * (ax[lo + 1] - a); w1 = f * (a - ax[lo]);
+}
+
+__device__ __forceinline__ double tcr_nan_to_num(double x)
+{
+    if (tcr_isnan(x)) return 0.0;
+    if (x == INFINITY) return 1.7976931348623157e308;
+    if (x == -INFINITY) return -1.7976931348623157e308;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) k_prepare_month(const PrepArgs A)
+{
+    const size_t plane_b = (size_t)A.nlat_b * A.nlon_b, plane_g = (size_t)A.nlat_g * A.nlon_g;
+    const size_t total = plane_b * TCR_N_FIELDS;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx / plane_b);
+        const size_t rem = idx - (size_t)c * plane_b;
+        const int i = (int)(rem / A.nlon_b), j = (int)(rem - (size_t)i * A.nlon_b);
+        const int r = A.src_row[i], q = A.src_col[j];
+        double v;
+        if (c < CH_CHI) {                                   /* 14 wind statistics: nan_to_num (bam_track.py:74) */
+            v = tcr_nan_to_num((double)A.raw[(size_t)c * plane_g + (size_t)r * A.nlon_g + q]);
+        } else if (c == CH_VPOT) {                          /* vmax * PI_reduc * sqrt(Ck/Cd), NaN -> 0 (compute.py:76,110) */
+            v = tcr_nan_to_num((double)A.raw[(size_t)14 * plane_g + (size_t)r * A.nlon_g + q] * A.pi_reduc * A.sqrt_ck_cd);
+        } else if (c == CH_CHI) {                           /* compute.py:113,115 */
+            double x = (double)A.raw[(size_t)15 * plane_g + (size_t)r * A.nlon_g + q];
+            if (tcr_isnan(x)) x = 5.0;
+            double t = tcr_exp(tcr_log(x + 1e-3) + A.log_chi_fac) + A.chi_fac;
+            t = tcr_isnan(t) ? t : (t < 5.0 ? t : 5.0);                     /* np.minimum / np.maximum propagate NaN */
+            v = tcr_isnan(t) ? t : (t > 1e-5 ? t : 1e-5);
+        } else if (c == CH_RH) {                            /* rh_mid is sampled raw (compute.py:114) */
+            v = (double)A.raw[(size_t)16 * plane_g + (size_t)r * A.nlon_g + q];
+        } else {                                            /* mld / strat: nan_to_num, then bilinear regrid (compute.py:117-118) */
+            const float* f = A.ocean + (size_t)(c - CH_MLD) * A.nlat_o * A.nlon_o;
+            int ix, iy; double wx0, wx1, wy0, wy1;
+            tcr_locate_plain(A.lon_o, A.nlon_o, A.lon_g[q], ix, wx0, wx1);
+            tcr_locate_plain(A.lat_o, A.nlat_o, A.lat_g[r], iy, wy0, wy1);
+            const double f00 = tcr_nan_to_num((double)f[(size_t)iy * A.nlon_o + ix]);
+            const double f01 = tcr_nan_to_num((double)f[(size_t)(iy + 1) * A.nlon_o + ix]);
+            const double f10 = tcr_nan_to_num((double)f[(size_t)iy * A.nlon_o + ix + 1]);
+            const double f11 = tcr_nan_to_num((double)f[(size_t)(iy + 1) * A.nlon_o + ix + 1]);
+            double sp = f00 * wx0 * wy0;                     /* fields.bilinear / FITPACK product order */
+            sp = sp + f01 * wx0 * wy1;
+            sp = sp + f10 * wx1 * wy0;
+            sp = sp + f11 * wx1 * wy1;
+            v = sp;
+        }
+        A.out[idx] = (float)v;
+    }
+}

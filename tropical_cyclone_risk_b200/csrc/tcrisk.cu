@@ -109,7 +109,7 @@ struct tcr_handle {
     size_t smem_optin = 0;
     int64_t launches = 0;
     /* tables */
-    DevBuf rec, stage;
+    DevBuf rec, stage, prep;
     AxisBuf ax_lon, ax_lat;
     int nlat = 0, nlon = 0, n_ym = 0;
     size_t month_f4 = 0;
@@ -272,7 +272,7 @@ int tcr_destroy(tcr_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     h->ws.release_all();
-    DevBuf* bufs[] = {&h->rec, &h->stage, &h->bathy, &h->land, &h->masks, &h->sincos};
+    DevBuf* bufs[] = {&h->rec, &h->stage, &h->prep, &h->bathy, &h->land, &h->masks, &h->sincos};
     for (DevBuf* b : bufs) b->release();
     AxisBuf* axs[] = {&h->ax_lon, &h->ax_lat, &h->ax_lon_b, &h->ax_lat_b, &h->ax_lon_l, &h->ax_lat_l, &h->ax_lon_m, &h->ax_lat_m};
     for (AxisBuf* a : axs) a->buf.release();
@@ -1120,6 +1120,65 @@ int tcr_exceedance(tcr_handle* h, int64_t n, const double* v, int n_bins, const 
     CK(cudaMemcpyAsync(counts, d_cnt, (size_t)n_bins * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     buf.release();
+    return 0;
+}
+
+/* ---- per-month field preparation on the device ---------------------------------- */
+int tcr_prepare_month(tcr_handle* h, int ym, const tcr_prep_spec* sp, const float* raw, const float* ocean,
+                      const double* lon_g, const double* lat_g, const double* lon_o, const double* lat_o,
+                      const int32_t* src_col, const int32_t* src_row, float* planes_out)
+{
+    if (!h || !sp || !raw || !ocean || !lon_g || !lat_g || !lon_o || !lat_o || !src_col || !src_row)
+        return set_err("tcr_prepare_month: null argument");
+    if (sp->nlat_g < 2 || sp->nlon_g < 2 || sp->nlat_o < 2 || sp->nlon_o < 2 || sp->nlat_b < 2 || sp->nlon_b < 2)
+        return set_err("tcr_prepare_month: bad shape");
+    if (ym >= 0) {
+        if (!h->rec.p) return set_err("tcr_prepare_month: call tcr_alloc_tables first");
+        if (ym >= h->n_ym) return set_err("tcr_prepare_month: ym %d out of range [0, %d)", ym, h->n_ym);
+        if (sp->nlat_b != h->nlat || sp->nlon_b != h->nlon)
+            return set_err("tcr_prepare_month: cropped grid %dx%d differs from the table grid %dx%d", sp->nlat_b, sp->nlon_b, h->nlat, h->nlon);
+    }
+    for (int j = 0; j < sp->nlon_b; ++j) if (src_col[j] < 0 || src_col[j] >= sp->nlon_g) return set_err("tcr_prepare_month: src_col[%d] out of range", j);
+    for (int i = 0; i < sp->nlat_b; ++i) if (src_row[i] < 0 || src_row[i] >= sp->nlat_g) return set_err("tcr_prepare_month: src_row[%d] out of range", i);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t plane_g = (size_t)sp->nlat_g * sp->nlon_g, plane_o = (size_t)sp->nlat_o * sp->nlon_o;
+    const size_t plane_b = (size_t)sp->nlat_b * sp->nlon_b;
+    /* one scratch block: raw | ocean | axes | index maps ; the prepared planes go to the table stage buffer */
+    const size_t b_raw = plane_g * 17 * 4, b_oc = plane_o * 2 * 4;
+    const size_t b_ax = ((size_t)sp->nlon_g + sp->nlat_g + sp->nlon_o + sp->nlat_o) * 8;
+    const size_t b_ix = ((size_t)sp->nlon_b + sp->nlat_b) * 4;
+    if (h->prep.ensure(b_raw + b_oc + b_ax + b_ix + 64)) return -1;
+    if (h->stage.ensure(plane_b * TCR_N_FIELDS * sizeof(float))) return -1;
+    char* base = h->prep.as<char>();
+    float* d_raw = reinterpret_cast<float*>(base);
+    float* d_oc = reinterpret_cast<float*>(base + b_raw);
+    double* d_ax = reinterpret_cast<double*>(base + b_raw + b_oc + ((8 - (b_raw + b_oc) % 8) % 8));
+    int32_t* d_ix = reinterpret_cast<int32_t*>(d_ax + sp->nlon_g + sp->nlat_g + sp->nlon_o + sp->nlat_o);
+    CK(cudaMemcpyAsync(d_raw, raw, b_raw, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_oc, ocean, b_oc, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_ax, lon_g, (size_t)sp->nlon_g * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_ax + sp->nlon_g, lat_g, (size_t)sp->nlat_g * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_ax + sp->nlon_g + sp->nlat_g, lon_o, (size_t)sp->nlon_o * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_ax + sp->nlon_g + sp->nlat_g + sp->nlon_o, lat_o, (size_t)sp->nlat_o * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_ix, src_col, (size_t)sp->nlon_b * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_ix + sp->nlon_b, src_row, (size_t)sp->nlat_b * 4, cudaMemcpyHostToDevice, s));
+    PrepArgs a;
+    memset(&a, 0, sizeof a);
+    a.nlat_g = sp->nlat_g; a.nlon_g = sp->nlon_g; a.nlat_o = sp->nlat_o; a.nlon_o = sp->nlon_o; a.nlat_b = sp->nlat_b; a.nlon_b = sp->nlon_b;
+    a.pi_reduc = sp->pi_reduc; a.sqrt_ck_cd = sp->sqrt_ck_cd; a.log_chi_fac = sp->log_chi_fac; a.chi_fac = sp->chi_fac;
+    a.raw = d_raw; a.ocean = d_oc;
+    a.lon_g = d_ax; a.lat_g = d_ax + sp->nlon_g; a.lon_o = a.lat_g + sp->nlat_g; a.lat_o = a.lon_o + sp->nlon_o;
+    a.src_col = d_ix; a.src_row = d_ix + sp->nlon_b;
+    a.out = h->stage.as<float>();
+    {
+        LaunchTimer lt_(h, TCR_K_BUILD);
+        k_prepare_month<<<grid_for(plane_b * TCR_N_FIELDS, 256, h->num_sms), 256, 0, s>>>(a);
+    }
+    CKK(h);
+    if (planes_out) CK(cudaMemcpyAsync(planes_out, h->stage.p, plane_b * TCR_N_FIELDS * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (ym >= 0) { if (tcr_upload_month_dev(h, ym, h->stage.as<float>())) return -1; }
+    if (planes_out) CK(cudaStreamSynchronize(s));
     return 0;
 }
 

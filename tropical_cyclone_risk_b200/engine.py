@@ -140,6 +140,32 @@ class Engine:
         assert planes.shape[1:] == (layout.N_FIELDS,) + self.grid, (planes.shape, self.grid)
         _lib.check(self.lib.tcr_upload_months(self._h, int(ym0), int(planes.shape[0]), _ptr(planes)))
 
+    def prepare_month(self, ym, namelist, bounds, lon, lat, raw, ocean_lon, ocean_lat, mld, strat, return_planes=False):
+        """Device-side fields.prepare_month (util/compute.py:107-121 + bam_track.py:72-74) for month slot `ym`
+        (ym < 0: prepare only).  raw: dict of the 14 wind statistics + 'vmax', 'chi', 'rh_mid' on the global
+        grid (lon, lat in storage order); mld / strat on the ascending ocean grid.  Returns the prepared planes
+        [19][nlat_b][nlon_b] float32 when return_planes."""
+        from . import fields
+        from .params import TcrPrepSpec
+        lon, lat = _arr(lon, np.float64), _arr(lat, np.float64)
+        olon, olat = _arr(ocean_lon, np.float64), _arr(ocean_lat, np.float64)
+        lon_b, lat_b, src_col, src_row = fields.crop_index_maps(lon, lat, bounds)
+        names = list(layout.FIELD_NAMES[:14]) + ["vmax", "chi", "rh_mid"]
+        stack = np.ascontiguousarray(np.stack([np.asarray(raw[n], dtype=np.float32) for n in names]))
+        ocean = np.ascontiguousarray(np.stack([np.asarray(mld, dtype=np.float32), np.asarray(strat, dtype=np.float32)]))
+        sp = TcrPrepSpec()
+        sp.nlat_g, sp.nlon_g = lat.size, lon.size
+        sp.nlat_o, sp.nlon_o = olat.size, olon.size
+        sp.nlat_b, sp.nlon_b = lat_b.size, lon_b.size
+        sp.pi_reduc = float(namelist.PI_reduc)
+        sp.sqrt_ck_cd = float(np.sqrt(namelist.Ck / namelist.Cd))
+        sp.log_chi_fac, sp.chi_fac = float(namelist.log_chi_fac), float(namelist.chi_fac)
+        out = np.empty((layout.N_FIELDS, lat_b.size, lon_b.size), np.float32) if return_planes else None
+        _lib.check(self.lib.tcr_prepare_month(
+            self._h, int(ym), C.byref(sp), _ptr(stack), _ptr(ocean), _ptr(lon), _ptr(lat), _ptr(olon), _ptr(olat),
+            _ptr(src_col), _ptr(src_row), _ptr(out) if return_planes else C.c_void_p()))
+        return (lon_b, lat_b, out) if return_planes else (lon_b, lat_b)
+
     def upload_month_dev(self, ym, d_planes_ptr):
         _lib.check(self.lib.tcr_upload_month_dev(self._h, int(ym), C.c_void_p(int(d_planes_ptr))))
 

@@ -35,6 +35,20 @@ def crop_to_basin(lon, lat, field, bounds):
     return lon[lon_mask], lat[lat_mask], field[..., lat_mask, :][..., lon_mask]
 
 
+def crop_index_maps(lon, lat, bounds):
+    """crop_to_basin as index maps: (lon_b, lat_b, src_col, src_row) with field_b == field[src_row][:, src_col]
+    (what tcr_prepare_month consumes).  Axes in storage order; latitude may be descending."""
+    lon = np.asarray(lon, dtype=np.float64)
+    lat = np.asarray(lat, dtype=np.float64)
+    rows = np.arange(lat.size)
+    if lat[0] > lat[1]:                                              # util/compute.py:80-84
+        lat, rows = lat[::-1], rows[::-1]
+    cols = np.arange(lon.size, dtype=np.float64)
+    lon_b, lat_b, cols_b = crop_to_basin(lon, lat, np.broadcast_to(cols, (lat.size, lon.size)), bounds)
+    _, _, rows_b = crop_to_basin(lon, lat, np.broadcast_to(rows[:, None].astype(np.float64), (lat.size, lon.size)), bounds)
+    return lon_b, lat_b, cols_b[0].astype(np.int32), rows_b[:, 0].astype(np.int32)
+
+
 def _locate(axis, x):
     """Clamped interval index and the two linear B-spline weights (FITPACK fpbspl, k=1)."""
     x = np.clip(x, axis[0], axis[-1])

@@ -50,6 +50,12 @@ class TcrYearStats(C.Structure):
     ]
 
 
+class TcrPrepSpec(C.Structure):
+    _fields_ = [("nlat_g", C.c_int32), ("nlon_g", C.c_int32), ("nlat_o", C.c_int32), ("nlon_o", C.c_int32),
+                ("nlat_b", C.c_int32), ("nlon_b", C.c_int32),
+                ("pi_reduc", C.c_double), ("sqrt_ck_cd", C.c_double), ("log_chi_fac", C.c_double), ("chi_fac", C.c_double)]
+
+
 def parse_bound(text):
     """'45S' -> -45.0, '0S' -> -0.0 (sign preserved, as TC_Basin._adj_bnd, util/basins.py:23-27)."""
     x = float(text[:-1])
