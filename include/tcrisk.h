@@ -202,8 +202,11 @@ int tcr_seed_attempts(tcr_handle* h, int ym_base, int32_t year_key, uint32_t run
 
 /* tuning knobs (0 keeps the default): variant of the integrate kernel = threads x CTAs/SM
  * [K: stage derivatives in shared memory] [L: CTA-lockstep RHS evaluations]:
- * 1 = 256x1, 2 = 128x3, 3 = 128x4 K, 4 = 160x2, 5 = 128x3 K, 6 = 192x2 K, 7 = 192x2 K L (default),
- * 8 = 256x1 L, 9 = 288x1 K L, 10 = 384x1 K L, 11 = 512x1 K L, 12 = 128x3 K L, 13 = 224x1 L;
+ * 1 = 256x1, 2 = 128x3, 3 = 128x4 K, 4 = 160x2, 5 = 128x3 K, 6 = 192x2 K, 7 = 192x2 K L,
+ * 8 = 256x1 L, 9 = 288x1 K L, 10 = 384x1 K L, 11 = 512x1 K L, 12 = 128x3 K L, 13 = 224x1 L,
+ * 14-16 = 192x2 K with lockstep re-alignment at slots {0,2,4} / {0,3} / {0}, 17 = 256x2 KK L,
+ * 18 = 192x2 KK L (default: every stage vector in shared memory, 168 registers, no spills),
+ * 19 = 192x3 KK L, 20 = 224x2 KK L, 21 = 384x1 KK L  (KK: K0..K6 and y_new in shared memory);
  * upper bounds on the seed attempts and on the integrated storms of one wave; wave
  * over-subscription factor (x1000).  Results never depend on these (ordered selection, bit-exact
  * kernels); only speed and the amount of discarded work do.                                  */

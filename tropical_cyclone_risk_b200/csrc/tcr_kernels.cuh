@@ -633,16 +633,19 @@ enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
  * table is read from HBM/L2 (64 B per evaluation); only emitted samples go to HBM.
  * THREADS x MINB fixes the register budget (launch bounds): <256,1> 255 registers, <128,3> 168,
  * <128,4> 128 -- chosen at run time by tcr_set_tuning, default by measurement.   */
-template <int THREADS, int MINB, bool KSMEM, int CTA_LOCKSTEP>
+template <int THREADS, int MINB, int KSMEM, int CTA_LOCKSTEP>
 __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
 {
-    /* KSMEM: the stage derivatives K1..K5 (dead during an RHS evaluation) live in shared memory,
-     * [stage][component][thread], which frees 40 registers for a second resident CTA */
-    extern __shared__ __align__(16) double k_smem[];          /* KSMEM: 20 * THREADS doubles (dynamic) */
-    double Kr[KSMEM ? 1 : 5][4] = {};
+    /* Stage storage, "stage" j = 0..7: K0 (FSAL derivative), K1..K5, K6, and the step's end state y_new.
+     * KSMEM = 1: K1..K5 (dead during an RHS evaluation) live in shared memory, [stage][component][thread],
+     * which frees 40 registers; KSMEM = 2: all eight (64 registers); KSMEM = 0: registers only. */
+    extern __shared__ __align__(16) double k_smem[];
+    double Kr[8][4] = {};
     double* const ks = k_smem + (KSMEM ? threadIdx.x : 0);
-    auto Kg = [&](int j, int i) -> double { if constexpr (KSMEM) return ks[((j - 1) * 4 + i) * THREADS]; else return Kr[j - 1][i]; };
-    auto Ks = [&](int j, int i, double v) { if constexpr (KSMEM) ks[((j - 1) * 4 + i) * THREADS] = v; else Kr[j - 1][i] = v; };
+    auto in_smem = [](int j) { return KSMEM == 2 || (KSMEM == 1 && j >= 1 && j <= 5); };
+    auto k_off = [](int j, int i) { return ((KSMEM == 2 ? j : j - 1) * 4 + i) * THREADS; };
+    auto Kg = [&](int j, int i) -> double { return in_smem(j) ? ks[k_off(j, i)] : Kr[j][i]; };
+    auto Ks = [&](int j, int i, double v) { if (in_smem(j)) ks[k_off(j, i)] = v; else Kr[j][i] = v; };
     const tcr_params& p = cx.p;
     const int lane = threadIdx.x & 31;
     const double* ftab = nullptr;
@@ -657,10 +660,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
     bool rejected = false, new_step = false, any_v = false;
     double hbl = 0.0, t = 0.0, h = 0.0, h_abs = 0.0, t_new = 0.0, g = 0.0, min_step = 0.0;
     double h0 = 0.0, d1 = 0.0;
-    double y[4] = {0, 0, 0, 0}, yn[4] = {0, 0, 0, 0};
-    double K0[4] = {0, 0, 0, 0}, K6[4] = {0, 0, 0, 0};
+    double y[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int j = 1; j <= 5; ++j)
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) Ks(j, i, 0.0);
     double* trk = nullptr;
@@ -758,36 +760,36 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 case 0:
                     te = t + RK_C1 * h;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) ye[i] = fma(K0[i] * RK_A10, h, y[i]);
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(Kg(0, i) * RK_A10, h, y[i]);
                     break;
                 case 1:
                     te = t + RK_C2 * h;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(Kg(1, i), RK_A21, K0[i] * RK_A20), h, y[i]);
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(Kg(1, i), RK_A21, Kg(0, i) * RK_A20), h, y[i]);
                     break;
                 case 2:
                     te = t + RK_C3 * h;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(Kg(2, i), RK_A32, fma(Kg(1, i), RK_A31, K0[i] * RK_A30)), h, y[i]);
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(Kg(2, i), RK_A32, fma(Kg(1, i), RK_A31, Kg(0, i) * RK_A30)), h, y[i]);
                     break;
                 case 3:
                     te = t + RK_C4 * h;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        ye[i] = fma(fma(Kg(3, i), RK_A43, fma(Kg(2, i), RK_A42, fma(Kg(1, i), RK_A41, K0[i] * RK_A40))), h, y[i]);
+                        ye[i] = fma(fma(Kg(3, i), RK_A43, fma(Kg(2, i), RK_A42, fma(Kg(1, i), RK_A41, Kg(0, i) * RK_A40))), h, y[i]);
                     break;
                 case 4:
                     te = t + 1.0 * h;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        ye[i] = fma(fma(Kg(4, i), RK_A54, fma(Kg(3, i), RK_A53, fma(Kg(2, i), RK_A52, fma(Kg(1, i), RK_A51, K0[i] * RK_A50)))), h, y[i]);
+                        ye[i] = fma(fma(Kg(4, i), RK_A54, fma(Kg(3, i), RK_A53, fma(Kg(2, i), RK_A52, fma(Kg(1, i), RK_A51, Kg(0, i) * RK_A50)))), h, y[i]);
                     break;
                 default:
                     te = t + h;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        yn[i] = fma(h, fma(Kg(5, i), RK_B5, fma(Kg(4, i), RK_B4, fma(Kg(3, i), RK_B3, fma(Kg(2, i), RK_B2, K0[i] * RK_B0)))), y[i]);
-                        ye[i] = yn[i];
+                        ye[i] = fma(h, fma(Kg(5, i), RK_B5, fma(Kg(4, i), RK_B4, fma(Kg(3, i), RK_B3, fma(Kg(2, i), RK_B2, Kg(0, i) * RK_B0)))), y[i]);
+                        Ks(7, i, ye[i]);
                     }
                     break;
                 }
@@ -798,7 +800,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
             } else if (mode == M_INIT1) {
                 ev = true; te = 0.0 + h0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ye[i] = yn[i];
+                for (int i = 0; i < 4; ++i) ye[i] = Kg(7, i);
             }
 
             double dy[4] = {0, 0, 0, 0};
@@ -813,7 +815,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 case 2: Ks(3, 0, dy[0]); Ks(3, 1, dy[1]); Ks(3, 2, dy[2]); Ks(3, 3, dy[3]); break;
                 case 3: Ks(4, 0, dy[0]); Ks(4, 1, dy[1]); Ks(4, 2, dy[2]); Ks(4, 3, dy[3]); break;
                 case 4: Ks(5, 0, dy[0]); Ks(5, 1, dy[1]); Ks(5, 2, dy[2]); Ks(5, 3, dy[3]); break;
-                default: K6[0] = dy[0]; K6[1] = dy[1]; K6[2] = dy[2]; K6[3] = dy[3]; break;
+                default: Ks(6, 0, dy[0]); Ks(6, 1, dy[1]); Ks(6, 2, dy[2]); Ks(6, 3, dy[3]); break;
                 }
             } else if (mode == M_INIT0) {
                 /* ventilation pre-check (coupled_fast.py:238-244); the evaluation at (0, y0) is
@@ -830,7 +832,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                     double sa[4], sb[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        K0[i] = dy[i];
+                        Ks(0, i, dy[i]);
                         double scale = atol + fabs(y[i]) * rtol;
                         sa[i] = y[i] / scale; sb[i] = dy[i] / scale;
                     }
@@ -839,7 +841,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                     if (d0 < 1e-5 || d1 < 1e-5) h0 = 1e-6; else h0 = 0.01 * d0 / d1;
                     if (t_bound < h0) h0 = t_bound;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) yn[i] = fma(h0, K0[i], y[i]);
+                    for (int i = 0; i < 4; ++i) Ks(7, i, fma(h0, dy[i], y[i]));
                     mode = M_INIT1;
                 }
             } else if (mode == M_INIT1) {
@@ -847,7 +849,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     double scale = atol + fabs(y[i]) * rtol;
-                    sc[i] = (dy[i] - K0[i]) / scale;
+                    sc[i] = (dy[i] - Kg(0, i)) / scale;
                 }
                 double d2 = tcr_rms4(sc) / h0, h1;
                 if (d1 <= 1e-15 && d2 <= 1e-15) { h1 = h0 * 1e-3; if (h1 < 1e-6) h1 = 1e-6; }
@@ -865,12 +867,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
         /* ---- end of the RK attempt: error control, events, dense output ---- */
         if (mode == M_RK) {
             double en[4];
+            const double ynl[4] = {Kg(7, 0), Kg(7, 1), Kg(7, 2), Kg(7, 3)};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                double ay = fabs(y[i]), an = fabs(yn[i]);
+                double ay = fabs(y[i]), an = fabs(ynl[i]);
                 double mx = (tcr_isnan(ay) || tcr_isnan(an)) ? NAN : (ay > an ? ay : an);
                 double scale = atol + mx * rtol;
-                double e = fma(K6[i], RK_E6, fma(Kg(5, i), RK_E5, fma(Kg(4, i), RK_E4, fma(Kg(3, i), RK_E3, fma(Kg(2, i), RK_E2, K0[i] * RK_E0)))));
+                double e = fma(Kg(6, i), RK_E6, fma(Kg(5, i), RK_E5, fma(Kg(4, i), RK_E4, fma(Kg(3, i), RK_E3, fma(Kg(2, i), RK_E2, Kg(0, i) * RK_E0)))));
                 en[i] = (e * h) / scale;
             }
             const double err = tcr_rms4(en);
@@ -883,7 +886,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 /* accepted */
                 const double t_old = t;
                 if (t_new - t_bound >= 0.0) status = TCR_STATUS_FINISHED;
-                const double g_new = tcr_event(p, yn);
+                const double g_new = tcr_event(p, ynl);
                 const bool active = ((g <= 0.0) && (g_new >= 0.0)) || ((g >= 0.0) && (g_new <= 0.0));
                 double t_emit = t_new;
                 if (active) { status = TCR_STATUS_EVENT; if (g == 0.0) t_emit = t_old; }
@@ -894,11 +897,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                     double Q1[4], Q2[4], Q3[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        Q1[i] = fma(K6[i], RK_P61, fma(Kg(5, i), RK_P51, fma(Kg(4, i), RK_P41, fma(Kg(3, i), RK_P31, fma(Kg(2, i), RK_P21, K0[i] * RK_P01)))));
-                        Q2[i] = fma(K6[i], RK_P62, fma(Kg(5, i), RK_P52, fma(Kg(4, i), RK_P42, fma(Kg(3, i), RK_P32, fma(Kg(2, i), RK_P22, K0[i] * RK_P02)))));
-                        Q3[i] = fma(K6[i], RK_P63, fma(Kg(5, i), RK_P53, fma(Kg(4, i), RK_P43, fma(Kg(3, i), RK_P33, fma(Kg(2, i), RK_P23, K0[i] * RK_P03)))));
+                        Q1[i] = fma(Kg(6, i), RK_P61, fma(Kg(5, i), RK_P51, fma(Kg(4, i), RK_P41, fma(Kg(3, i), RK_P31, fma(Kg(2, i), RK_P21, Kg(0, i) * RK_P01)))));
+                        Q2[i] = fma(Kg(6, i), RK_P62, fma(Kg(5, i), RK_P52, fma(Kg(4, i), RK_P42, fma(Kg(3, i), RK_P32, fma(Kg(2, i), RK_P22, Kg(0, i) * RK_P02)))));
+                        Q3[i] = fma(Kg(6, i), RK_P63, fma(Kg(5, i), RK_P53, fma(Kg(4, i), RK_P43, fma(Kg(3, i), RK_P33, fma(Kg(2, i), RK_P23, Kg(0, i) * RK_P03)))));
                     }
                     const double hd = t_new - t_old, yhd = tcr_rcp_seed(hd);
+                    const double k0l[4] = {Kg(0, 0), Kg(0, 1), Kg(0, 2), Kg(0, 3)};
                     /* four samples per trip, computed unconditionally (the last trip repeats its final
                      * sample) so that the four dependent chains interleave; only the stores are guarded */
                     for (int k0 = n_out; k0 < i_new; k0 += 4) {
@@ -910,7 +914,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                             double p2 = x * x, p3 = p2 * x, p4 = p3 * x;
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                double acc = (K0[i] * 1.0) * x;
+                                double acc = (k0l[i] * 1.0) * x;
                                 acc = fma(Q1[i], p2, acc);
                                 acc = fma(Q2[i], p3, acc);
                                 acc = fma(Q3[i], p4, acc);
@@ -931,7 +935,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 }
                 t = t_new;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { y[i] = yn[i]; K0[i] = K6[i]; }
+                for (int i = 0; i < 4; ++i) { y[i] = ynl[i]; Ks(0, i, Kg(6, i)); }
                 new_step = true;
                 if (status != 100) finalize(status);
             } else {

@@ -119,7 +119,7 @@ struct tcr_handle {
     AxisBuf ax_lon_b, ax_lat_b, ax_lon_l, ax_lat_l, ax_lon_m, ax_lat_m;
     bool have_static = false, have_masks = false;
     /* tuning */
-    int integ_variant = 6, oversub_permille = 1020, interp_variant = 0;
+    int integ_variant = 17, oversub_permille = 1020, interp_variant = 0;
     /* survival statistics of earlier tcr_run_years calls on this handle: size the first wave */
     double hint_kept_rate = 0.0, hint_pass_rate = 0.0;
     std::vector<double> hint_year_rate;     /* per year slot of the previous call (same n_years): survival differs by year */
@@ -302,7 +302,7 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 {
     if (!h) return set_err("null handle");
     if (integ_variant > 0) {
-        if (integ_variant > 16) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
+        if (integ_variant > 21) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
         h->integ_variant = integ_variant - 1;
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
@@ -602,7 +602,7 @@ static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned i
 
 }  // extern "C"
 
-template <int THREADS, int MINB, bool KSMEM, int LOCKSTEP = 0>
+template <int THREADS, int MINB, int KSMEM, int LOCKSTEP = 0>
 static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_upper)
 {
     const int warps_per_cta = THREADS / 32;
@@ -611,7 +611,7 @@ static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_uppe
     int grid = (int)std::max<int64_t>(1, std::min(max_ctas, want_ctas));
     int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
     a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
-    const size_t smem = KSMEM ? (size_t)20 * THREADS * sizeof(double) : 0;
+    const size_t smem = KSMEM == 2 ? (size_t)32 * THREADS * sizeof(double) : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
     cudaFuncSetAttribute(k_integrate<THREADS, MINB, KSMEM, LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     LaunchTimer lt_(h, TCR_K_INTEGRATE);
     k_integrate<THREADS, MINB, KSMEM, LOCKSTEP><<<grid, THREADS, smem, h->stream>>>(h->ctx, a);
@@ -620,22 +620,27 @@ static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_uppe
 static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
 {
     switch (h->integ_variant) {
-    case 0: launch_integrate_variant<256, 1, false>(h, a, n_upper); break;
-    case 1: launch_integrate_variant<128, 3, false>(h, a, n_upper); break;
-    case 2: launch_integrate_variant<128, 4, true>(h, a, n_upper); break;
-    case 3: launch_integrate_variant<160, 2, false>(h, a, n_upper); break;
-    case 4: launch_integrate_variant<128, 3, true>(h, a, n_upper); break;
-    case 5: launch_integrate_variant<192, 2, true>(h, a, n_upper); break;
-    case 6: launch_integrate_variant<192, 2, true, 63>(h, a, n_upper); break;
-    case 7: launch_integrate_variant<256, 1, false, 63>(h, a, n_upper); break;
-    case 8: launch_integrate_variant<288, 1, true, 63>(h, a, n_upper); break;
-    case 9: launch_integrate_variant<384, 1, true, 63>(h, a, n_upper); break;
-    case 10: launch_integrate_variant<512, 1, true, 63>(h, a, n_upper); break;
-    case 11: launch_integrate_variant<128, 3, true, 63>(h, a, n_upper); break;
-    case 12: launch_integrate_variant<224, 1, false, 63>(h, a, n_upper); break;
-    case 13: launch_integrate_variant<192, 2, true, 21>(h, a, n_upper); break;      /* re-align at slots 0, 2, 4 */
-    case 14: launch_integrate_variant<192, 2, true, 9>(h, a, n_upper); break;       /* slots 0, 3 */
-    case 15: launch_integrate_variant<192, 2, true, 1>(h, a, n_upper); break;       /* slot 0 only */
+    case 0: launch_integrate_variant<256, 1, 0>(h, a, n_upper); break;
+    case 1: launch_integrate_variant<128, 3, 0>(h, a, n_upper); break;
+    case 2: launch_integrate_variant<128, 4, 1>(h, a, n_upper); break;
+    case 3: launch_integrate_variant<160, 2, 0>(h, a, n_upper); break;
+    case 4: launch_integrate_variant<128, 3, 1>(h, a, n_upper); break;
+    case 5: launch_integrate_variant<192, 2, 1>(h, a, n_upper); break;
+    case 6: launch_integrate_variant<192, 2, 1, 63>(h, a, n_upper); break;
+    case 7: launch_integrate_variant<256, 1, 0, 63>(h, a, n_upper); break;
+    case 8: launch_integrate_variant<288, 1, 1, 63>(h, a, n_upper); break;
+    case 9: launch_integrate_variant<384, 1, 1, 63>(h, a, n_upper); break;
+    case 10: launch_integrate_variant<512, 1, 1, 63>(h, a, n_upper); break;
+    case 11: launch_integrate_variant<128, 3, 1, 63>(h, a, n_upper); break;
+    case 12: launch_integrate_variant<224, 1, 0, 63>(h, a, n_upper); break;
+    case 13: launch_integrate_variant<192, 2, 1, 21>(h, a, n_upper); break;      /* re-align at slots 0, 2, 4 */
+    case 14: launch_integrate_variant<192, 2, 1, 9>(h, a, n_upper); break;       /* slots 0, 3 */
+    case 15: launch_integrate_variant<192, 2, 1, 1>(h, a, n_upper); break;       /* slot 0 only */
+    case 16: launch_integrate_variant<256, 2, 2, 63>(h, a, n_upper); break;      /* all stage storage in smem: 128 registers */
+    case 17: launch_integrate_variant<192, 2, 2, 63>(h, a, n_upper); break;
+    case 18: launch_integrate_variant<192, 3, 2, 63>(h, a, n_upper); break;      /* 96 registers, 18 warps/SM */
+    case 19: launch_integrate_variant<224, 2, 2, 63>(h, a, n_upper); break;      /* 144 registers, 14 warps/SM */
+    case 20: launch_integrate_variant<384, 1, 2, 63>(h, a, n_upper); break;      /* one 12-warp CTA per SM */
     default: return set_err("unknown integrate variant %d", h->integ_variant);
     }
     CKK(h);
