@@ -190,7 +190,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, n_steps):
@@ -409,7 +409,7 @@ def run_gpu_arm(args):
                           "gen_track + post-processing of every attempt (%.1f s, %d threads)" % (
                               args.basin, BASE_YEAR, RUN_SEED, n_att, dt, threads),
                 "rhs_per_s": st["rhs_evals"] / dt}
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -478,7 +478,27 @@ def bench_poi(eng, torch, dev, peak, peak_src, ns, n_rows=400000):
             "l2": "3 x %d MB track arrays, streamed" % (samples * 8 >> 20)}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries print there too (NCCL's version banner,
+    for one): keep the real stdout for the result line and point file descriptor 1 at stderr."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
