@@ -1483,18 +1483,40 @@ __global__ void __launch_bounds__(256) k_poi_vmax(int64_t n_rows, int n_steps, c
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double band_deg = radius_km / r_km * (180.0 / TCR_PI) * 1.01 + 1e-9;
+    const float cos_poi = cosf((float)(poi_lat * TCR_DEG2RAD));
+    const float s_half = sinf((float)fmin(0.5 * radius_km / r_km, 1.5));
+    const float a_max = s_half * s_half * 1.02f + 1e-12f;          /* sin^2(radius / 2R) with slack */
     for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
         const size_t base = (size_t)row * n_steps;
         double best = -INFINITY;
         bool have = false;
-        for (int k = lane; k < n_steps; k += 32) {
-            const double la = __ldcs(lat + base + k);
-            if (fabs(la - poi_lat) > band_deg) continue;            /* also false for NaN: falls through */
-            const double lo = __ldcs(lon + base + k);
-            const double d = tcr_haversine_r(r_km, poi_lon, poi_lat, lo, la);
-            if (d <= radius_km) {
-                const double v = __ldcs(vmax + base + k);
-                if (!tcr_isnan(v)) { have = true; if (v > best) best = v; }
+        /* the latitude stream is the only mandatory read: four independent 256-byte loads per warp in
+         * flight per trip (a dependent one-load loop leaves the memory system idle) */
+        for (int k0 = lane; k0 < n_steps; k0 += 128) {
+            double la4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + 32 * u;
+                la4[u] = k < n_steps ? __ldcs(lat + base + k) : INFINITY;     /* +inf is outside every band */
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double la = la4[u];
+                if (fabs(la - poi_lat) > band_deg) continue;        /* also false for NaN: falls through */
+                const int k = k0 + 32 * u;
+                const double lo = __ldcs(lon + base + k);
+                /* second, cheap exclusion in float32: the haversine argument is at least its longitude term
+                 * cos(lat1) cos(lat2) sin^2(dlon/2); 2 % slack covers the float32 error many times over */
+                {
+                    const float c2 = __cosf((float)(la * TCR_DEG2RAD));
+                    const float sh = __sinf((float)((lo - poi_lon) * (0.5 * TCR_DEG2RAD)));
+                    if (cos_poi * c2 * sh * sh > a_max) continue;
+                }
+                const double d = tcr_haversine_r(r_km, poi_lon, poi_lat, lo, la);
+                if (d <= radius_km) {
+                    const double v = __ldcs(vmax + base + k);
+                    if (!tcr_isnan(v)) { have = true; if (v > best) best = v; }
+                }
             }
         }
 #pragma unroll
