@@ -1,0 +1,37 @@
+#!/bin/bash
+# compute-sanitizer (memcheck, then racecheck) over a small end-to-end slice of the hot path:
+# uploads, both sampler kernels, explicit seeds through the integrator + post-processing, one small year.
+OUT=gpurun_out/${1:-san}
+mkdir -p $OUT
+cat > /tmp/san_slice.py <<'PY'
+import sys, numpy as np
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+from tropical_cyclone_risk_b200.workload import Workload
+from tropical_cyclone_risk_b200.engine import Engine
+w = Workload("NA", [2001], months=[8, 9])
+eng = Engine(w.p, device=0)
+w.upload(eng)
+rng = np.random.default_rng(0)
+n = 3000
+ym = rng.integers(0, 2, n).astype(np.int32); lon = rng.uniform(255, 365, n); lat = rng.uniform(-5, 65, n)
+for v in (0, 4, 5):
+    eng.set_interp_variant(v); eng.env_interp(ym, lon, lat)
+eng.set_interp_variant(0)
+n = 700
+ym = rng.integers(0, 2, n).astype(np.int32)
+o = eng.integrate(ym, rng.uniform(285, 345, n), rng.uniform(8, 32, n), 5 + rng.standard_normal(n), rng.uniform(.13, .32, n),
+                  np.full(n, 1400.0), rng.random((n, 60)))
+print("integrate ok", int(o["n_time"].sum()))
+w2 = Workload("NA", [2002])
+eng2 = Engine(w2.p, device=0); w2.upload(eng2)
+r = eng2.run_years([0], [2002], 7, 6)
+print("run_years ok", r["stats"][0]["storm_steps"])
+print("poi", np.isfinite(eng2.poi_vmax(r["lon"][0], r["lat"][0], r["vmax"][0], 300.0, 25.0, 500.0)).sum())
+eng.close(); eng2.close()
+PY
+for tool in memcheck racecheck; do
+  echo "== compute-sanitizer --tool $tool"
+  timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_slice.py > $OUT/sanitizer_$tool.log 2>&1
+  echo "exit $?" >> $OUT/sanitizer_$tool.log
+  tail -6 $OUT/sanitizer_$tool.log
+done

@@ -106,3 +106,36 @@ def test_tracks(na_case):
                 if k > 1:
                     assert _rel(o["vmax"][i, :k, None], g["vmax"][i, :k, None]).max() < 1e-4
     assert n_tight >= 0.7 * n_cmp, (n_tight, n_cmp)
+
+
+def test_ordered_selection_equals_the_sequential_loop(na_year):
+    """orc.run_year (chunked ordered selection over the indexed attempt stream) against a literal
+    transcription of the reference's control flow, util/compute.py:134-209: walk the attempts one by
+    one; count a seed before integrating it (:167); keep a storm only if it is a TC and its vmax
+    reaches the threshold (:185-205); stop at the n_tracks-th kept storm."""
+    p, env, masks = na_year.p, na_year.env, na_year.masks
+    n_tracks, run_seed, year = 12, 424242, 2001
+    want = orc.run_year(p, env, 0, masks, run_seed, year, n_tracks, chunk=700, n_threads=4)
+    nt, k = 0, 0
+    n_seeds = np.zeros((7, 12))
+    rows, months, basins, attempts = [], [], [], []
+    while nt < n_tracks:                                            # compute.py:134
+        o = orc.run_attempts(p, env, 0, masks, run_seed, year, k, 1, want_tracks=True)
+        code = int(o["code"][0])
+        if code in (1, 2):                                          # a counted seed (:166-167)
+            n_seeds[o["basin"][0], o["month"][0] - 1] += 1
+        if code == 2 and (o["flags"][0] & 2):                       # integrated, is_tc and nanmax(vmax) >= 18
+            n = int(o["n_time"][0])
+            rows.append((o["track"][0, :n], o["vmax"][0, :n], o["env"][0, :n]))
+            months.append(o["month"][0]); basins.append(o["basin"][0]); attempts.append(k)
+            nt += 1
+        k += 1
+    assert want["stats"]["attempts"] == k
+    assert np.array_equal(want["attempt"], attempts)
+    assert np.array_equal(want["n_seeds"], n_seeds)
+    assert np.array_equal(want["tc_month"], months) and np.array_equal(want["tc_basin"], basins)
+    for r, (trk, vm, ev) in enumerate(rows):
+        n = trk.shape[0]
+        assert np.array_equal(want["lon"][r, :n], trk[:, 0]) and np.isnan(want["lon"][r, n:]).all()
+        assert np.array_equal(want["v"][r, :n], trk[:, 2]) and np.array_equal(want["vmax"][r, :n], vm)
+        assert np.array_equal(want["env"][r, :n], ev)
