@@ -548,7 +548,8 @@ __global__ void k_coef_from_philox(const __grid_constant__ TcrCtx cx, const unsi
 /* storms whose coefficients sit in shared memory (broadcast reads); stores are coalesced:     */
 /* adjacent threads write adjacent 32-byte nodes.                                              */
 /* ======================================================================================== */
-#define FT_THREADS 128
+#define FT_THREADS 96
+#define FT_NODES 2                     /* output nodes per thread: every coefficient fetched from shared memory feeds 2 x 2 DFMA */
 #define FT_STORMS 16
 __global__ void __launch_bounds__(FT_THREADS) k_fourier_table(const __grid_constant__ TcrCtx cx, int64_t n,
                                                               const unsigned int* __restrict__ n_dev,
@@ -557,11 +558,14 @@ __global__ void __launch_bounds__(FT_THREADS) k_fourier_table(const __grid_const
     __shared__ __align__(16) double2 cfs[2][FT_STORMS][TCR_N_PHASES];      /* double-buffered coefficient tiles */
     const int64_t count = n_dev ? (int64_t)*n_dev : n;
     const int ns = cx.p.n_steps;
-    const int j = blockIdx.x * FT_THREADS + threadIdx.x;
-    double2 sc[TCR_N_HARM];
-    if (j < ns) {
+    int jn[FT_NODES];
+    double2 sc[FT_NODES][TCR_N_HARM];
 #pragma unroll
-        for (int k = 0; k < TCR_N_HARM; ++k) sc[k] = __ldg(cx.sc + (size_t)j * TCR_N_HARM + k);
+    for (int u = 0; u < FT_NODES; ++u) {
+        jn[u] = blockIdx.x * (FT_THREADS * FT_NODES) + u * FT_THREADS + threadIdx.x;
+        const int jj = min(jn[u], ns - 1);                                 /* out-of-range nodes compute a duplicate, never store */
+#pragma unroll
+        for (int k = 0; k < TCR_N_HARM; ++k) sc[u][k] = __ldg(cx.sc + (size_t)jj * TCR_N_HARM + k);
     }
     const int64_t stride = (int64_t)gridDim.y * FT_STORMS;
     /* asynchronous copy (LDGSTS) of one tile's coefficients: the next tile lands while this one is used */
@@ -582,22 +586,32 @@ __global__ void __launch_bounds__(FT_THREADS) k_fourier_table(const __grid_const
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
         const int nst = (int)min((int64_t)FT_STORMS, count - s0);
-        if (j < ns) {
-#pragma unroll 2
+        if (jn[0] < ns) {
+#pragma unroll 1
             for (int st = 0; st < nst; ++st) {
-                double F[4] = {0.0, 0.0, 0.0, 0.0};
+                double F[FT_NODES][4];
+#pragma unroll
+                for (int u = 0; u < FT_NODES; ++u) { F[u][0] = F[u][1] = F[u][2] = F[u][3] = 0.0; }
 #pragma unroll
                 for (int k = 0; k < TCR_N_HARM; ++k) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const double2 ab = cfs[buf][st][i * TCR_N_HARM + k];
-                        F[i] = fma(ab.x, sc[k].x, F[i]);
-                        F[i] = fma(ab.y, sc[k].y, F[i]);
+#pragma unroll
+                        for (int u = 0; u < FT_NODES; ++u) {
+                            F[u][i] = fma(ab.x, sc[u][k].x, F[u][i]);
+                            F[u][i] = fma(ab.y, sc[u][k].y, F[u][i]);
+                        }
                     }
                 }
-                double2* dst = reinterpret_cast<double2*>(ftab + ((size_t)(s0 + st) * ns + j) * 4);
-                __stcs(dst, make_double2(F[0], F[1]));
-                __stcs(dst + 1, make_double2(F[2], F[3]));
+#pragma unroll
+                for (int u = 0; u < FT_NODES; ++u) {
+                    if (jn[u] < ns) {
+                        double2* dst = reinterpret_cast<double2*>(ftab + ((size_t)(s0 + st) * ns + jn[u]) * 4);
+                        __stcs(dst, make_double2(F[u][0], F[u][1]));
+                        __stcs(dst + 1, make_double2(F[u][2], F[u][3]));
+                    }
+                }
             }
         }
         __syncthreads();                       /* tile `buf` is free for the prefetch of the iteration after next */

@@ -590,7 +590,7 @@ static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned i
 {
     Workspace& w = h->ws;
     const int ns = h->ctx.p.n_steps;
-    dim3 grid((unsigned)((ns + FT_THREADS - 1) / FT_THREADS),
+    dim3 grid((unsigned)((ns + FT_THREADS * FT_NODES - 1) / (FT_THREADS * FT_NODES)),
               (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_upper + FT_STORMS - 1) / FT_STORMS, (int64_t)h->num_sms * 8)));
     {
         LaunchTimer lt_(h, TCR_K_FTABLE);
