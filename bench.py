@@ -43,6 +43,9 @@ B_PER_RHS = 300            # 4 corners x 18 ch x 4 B + 4 x 2 B bathymetry + 4 x 
 B_PER_QUERY = 396          # stand-alone sampler: 300 B + 16 B query + 80 B result
 B_PER_STEP_TRACK = 32      # lon, lat, v, m float64 written by the integrator per emitted sample
 B_PER_STORM_PICKUP = 1004  # 60 double2 Fourier coefficients + 5 doubles + 1 int per integrated seed
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
+# workload (profiles/r01_prof_integrate_summary.txt, profiles/r01_prof_interp_summary.txt); None for other workloads
+NCU_TRAFFIC = {"k_integrate": 2.082e9 + 1.820e9, "k_env_interp": 10.151e9 + 5.611e9}
 
 
 def load_peaks():
@@ -392,8 +395,11 @@ def run_gpu_arm(args):
         storms_all = acc["integrated"] + acc["wasted_integrated"]
         ki_bytes = B_PER_RHS * rhs_all + B_PER_STEP_TRACK * steps_all + B_PER_STORM_PICKUP * storms_all
         ki_ach = ki_bytes / max(ki_n, 1) / (ki_ms / max(ki_n, 1) * 1e-3) / 1e9 if ki_ms > 0 else 0.0
+        std_cfg = args.basin == "NA" and args.years == 10 and args.tracks == 1000
         roof = {"kernel": "k_integrate", "bound": "hbm", "achieved": ki_ach, "peak": peak, "unit": "GB/s",
-                "frac": ki_ach / peak, "traffic": None, "peak_source": peak_src,
+                "frac": ki_ach / peak, "traffic": NCU_TRAFFIC["k_integrate"] if std_cfg else None,
+                "traffic_source": "profiles/r01_prof_integrate_summary.txt (ncu --set full, one launch of this workload)",
+                "algorithmic_bytes_per_launch": ki_bytes / max(ki_n, 1), "peak_source": peak_src,
                 "launches": ki_n, "avg_launch_ms": ki_ms / max(ki_n, 1),
                 "share_of_step": ki_ms / ms, "rhs_per_s": rhs_all / (ki_ms * 1e-3) if ki_ms > 0 else 0.0,
                 "note": "latency / fp64-issue bound kernel (SURVEY 8d): HBM fraction reported for honesty, "
@@ -461,8 +467,11 @@ def bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args):
         res[name] = {"achieved": ach, "frac": ach / peak, "avg_launch_ms": ms / cnt, "launches": cnt}
     eng.set_interp_variant(0)
     best = max(res, key=lambda k: res[k]["achieved"])
+    std_cfg = args.basin == "NA" and args.years == 10 and n == (1 << 25)
     return {"kernel": best, "bound": "hbm", "achieved": res[best]["achieved"], "peak": peak, "unit": "GB/s",
-            "frac": res[best]["frac"], "traffic": None, "peak_source": peak_src, "queries_per_launch": n,
+            "frac": res[best]["frac"], "traffic": NCU_TRAFFIC["k_env_interp"] if std_cfg else None,
+            "traffic_source": "profiles/r01_prof_interp_summary.txt (ncu --set full, one launch of this workload)",
+            "peak_source": peak_src, "queries_per_launch": n,
             "algorithmic_bytes_per_query": B_PER_QUERY, "moved_bytes_per_query": 320 + 12 + 20 + 168,
             "table_bytes": int(wl.n_ym * (wl.lat.size - 1) * (wl.lon.size - 1) * 320), "variants": res,
             "l2": "random queries over all %d month tables (>> 126 MB L2) + %d MB streamed output" % (wl.n_ym, n * 168 >> 20)}
