@@ -32,6 +32,14 @@ def launch_table(path):
     for n, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append("%-48s %7d %12.3f %6.1f%%" % (n[:48], c, ms, 100 * ms / tot))
     out.append("%-48s %7s %12.3f" % ("total", "", tot))
+    step = ("k_integrate", "k_fourier_table", "k_postprocess", "k_select", "k_seed", "k_coef_from_philox", "k_gather",
+            "k_wave_stats", "k_assign_slots", "k_scan_counts")
+    sub = {n: v for n, v in agg.items() if any(k in n for k in step)}
+    st = sum(v[1] for v in sub.values())
+    out.append("")
+    out.append("# kernels of the timed step only (what bench.py's kernel_share_of_step covers)")
+    for n, (c, ms) in sorted(sub.items(), key=lambda kv: -kv[1][1]):
+        out.append("%-48s %7d %12.3f %6.1f%%" % (n[:48], c, ms, 100 * ms / st))
     return "\n".join(out)
 
 
