@@ -444,8 +444,21 @@ def test_year_pipeline_matches_blocking_call(na_year, na_year_eng):
                     assert _same(got[key], want[key]), (sd, key)
                 assert st[0]["storm_steps"] == want["stats"][0]["storm_steps"]
         pipe.drain()
+        # a second set of table slots filled on the copy stream gives the same year as the first set
+        want = na_year_eng.run_years([0], [2001], 6, 40)
+        na_year_eng.alloc_tables(24, na_year.lon, na_year.lat)
+        na_year_eng.upload_months(0, na_year.planes)
+        pipe.upload_tables_async(12, na_year.planes)
+        pipe.tables_ready()
+        t, _ = pipe.submit([12], [2001], 6)
+        got = pipe.result(t)
+        for key in ("lon", "vmax", "env", "n_seeds"):
+            assert _same(np.array(got[key]), want[key]), key
     finally:
         na_year_eng.set_stream(0)
+        na_year_eng.alloc_tables(12, na_year.lon, na_year.lat)
+        na_year_eng.upload_months(0, na_year.planes)
+        na_year_eng.synchronize()
 
 
 # ---------------------------------------------------------------------------------------------

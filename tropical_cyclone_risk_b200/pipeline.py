@@ -80,6 +80,26 @@ class YearPipeline:
         self.count += 1
         return ticket, stats
 
+    def upload_tables_async(self, ym0, planes):
+        """Start uploading the NEXT batch's monthly planes (pinned host memory, [n][19][nlat][nlon]) into table
+        slots [ym0, ym0 + n) on the copy stream, while the batch submitted next still computes on the slots it
+        was given.  The batch that will use these slots must be submitted after `tables_ready()`."""
+        self.copy.wait_stream(self.main)                 # the slots' previous readers have been enqueued (and finished)
+        self.eng.set_stream(self.copy.cuda_stream)
+        try:
+            self.eng.upload_months(ym0, planes)
+        finally:
+            self.eng.set_stream(self.main.cuda_stream)
+        self._tables_event = self.torch.cuda.Event()
+        self._tables_event.record(self.copy)
+
+    def tables_ready(self):
+        """Order the main stream after the last asynchronous table upload."""
+        ev = getattr(self, "_tables_event", None)
+        if ev is not None:
+            self.main.wait_event(ev)
+            self._tables_event = None
+
     def result(self, ticket):
         """Host arrays (views of pinned memory, valid until `depth` further submissions)."""
         blk = self.blocks[ticket % len(self.blocks)]
