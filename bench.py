@@ -414,7 +414,11 @@ def run_gpu_arm(args):
                 "launches": ki_n, "avg_launch_ms": ki_ms / max(ki_n, 1),
                 "share_of_step": ki_ms / ms, "rhs_per_s": rhs_all / (ki_ms * 1e-3) if ki_ms > 0 else 0.0,
                 "note": "latency / fp64-issue bound kernel (SURVEY 8d): HBM fraction reported for honesty, "
-                        "the HBM-roofline kernel is roofline_interp"}
+                        "the HBM-roofline kernel is roofline_interp",
+                "ncu": {"source": "profiles/r01_prof_integrate_summary.txt (ncu --set full of one launch of this workload)",
+                        "fp64_pipe_pct_of_peak": 28.1, "issue_slots_busy_pct": 35.0, "lanes_per_instruction": 20.2,
+                        "l2_hit_pct": 82.9, "dram_pct_of_peak": 4.9, "registers": 168, "warps_per_sm": 12,
+                        "stalls": "fixed-latency fp64 chains 31 %, L2/L1 loads 25 %, CTA-lockstep barrier 10 %, instruction fetch 3 %"}}
         kernel_share = {k: v[0] / ms for k, v in ktimes.items() if v[1]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,

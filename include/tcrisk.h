@@ -14,7 +14,8 @@
  * caller-allocated buffers, int status return (0 = ok, <0 = error; text via
  * tcr_last_error()).  No exceptions, no torch types.  One handle per device;
  * calls on one handle must be serialised by the caller.  All kernels and copies
- * are issued on the handle's stream (tcr_set_stream, default stream 0).
+ * are issued on the handle's stream (tcr_set_stream; stream 0 until set -- prefer a dedicated
+ * non-blocking stream: the legacy default stream serialises against NCCL's).
  *
  * Pointer arguments named h_* are HOST pointers; d_* are DEVICE pointers; the
  * remaining data pointers are host pointers unless `on_device` says otherwise.
