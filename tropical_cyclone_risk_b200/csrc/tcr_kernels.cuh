@@ -633,6 +633,7 @@ struct IntegArgs {
     unsigned long long* queue;         /* work counter, zeroed by the host                    */
     int32_t* cand_list; unsigned int* cand_count;   /* TC candidates (NULL: not collected)    */
     int lane_cap;                      /* lanes per warp that take storms (small batches)     */
+    int pack;                          /* drain-phase packing of the surviving storms on/off  */
 };
 
 enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
@@ -710,6 +711,63 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
     for (;;) {
         /* ---- macro-step boundary: open the next RK attempt (RungeKutta._step_impl) ---- */
         if (mode == M_WAIT) { mode = M_RK; new_step = true; }
+        if constexpr (CTA_LOCKSTEP != 0 && KSMEM == 2) {
+            /* ---- drain phase: pack the surviving storms into as few warps as possible ----
+             * Once the queue is empty every warp keeps issuing the full RHS instruction stream for
+             * however few lanes it has left, and twelve thin warps per SM run each other's tail at a
+             * third of the speed one warp would have alone.  Whenever packing frees at least one warp,
+             * the live storms (17 words each: y, K0, t, h, g, ...) move through shared memory to the
+             * lowest threads of the CTA; emptied warps then only meet the slot barriers. */
+            const unsigned idle_b = __ballot_sync(TCR_FULL, mode == M_IDLE);
+            if (A.pack && __syncthreads_and(drained || idle_b == 0u)) {
+                __shared__ int w_act[THREADS / 32];
+                const int wid = threadIdx.x >> 5;
+                const unsigned act_b = ~idle_b;
+                if (lane == 0) w_act[wid] = __popc(act_b);
+                __syncthreads();
+                int total = 0, warps_used = 0, before = 0;
+#pragma unroll
+                for (int w = 0; w < THREADS / 32; ++w) {
+                    const int c = w_act[w];
+                    total += c; warps_used += (c > 0); if (w < wid) before += c;
+                }
+                if (total > 0 && total <= 32 * (warps_used - 1)) {
+                    double* stg = k_smem + 32 * THREADS;                 /* [17][THREADS] staging behind the stage vectors */
+                    if (mode != M_IDLE) {
+                        const int r = before + __popc(act_b & ((1u << lane) - 1u));
+                        double* d = stg + r;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { d[i * THREADS] = y[i]; d[(4 + i) * THREADS] = Kg(0, i); }
+                        d[8 * THREADS] = t; d[9 * THREADS] = h_abs; d[10 * THREADS] = g; d[11 * THREADS] = hbl;
+                        d[12 * THREADS] = min_step;
+                        d[13 * THREADS] = __longlong_as_double((long long)sid);
+                        d[14 * THREADS] = __hiloint2double(ym, nfev);
+                        d[15 * THREADS] = __hiloint2double(n_out, n_attempts);
+                        d[16 * THREADS] = __hiloint2double(mode, (rejected ? 1 : 0) | (new_step ? 2 : 0) | (any_v ? 4 : 0));
+                    }
+                    __syncthreads();
+                    if ((int)threadIdx.x < total) {
+                        const double* d = stg + threadIdx.x;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { y[i] = d[i * THREADS]; Ks(0, i, d[(4 + i) * THREADS]); }
+                        t = d[8 * THREADS]; h_abs = d[9 * THREADS]; g = d[10 * THREADS]; hbl = d[11 * THREADS];
+                        min_step = d[12 * THREADS];
+                        sid = (int64_t)__double_as_longlong(d[13 * THREADS]);
+                        ym = __double2hiint(d[14 * THREADS]); nfev = __double2loint(d[14 * THREADS]);
+                        n_out = __double2hiint(d[15 * THREADS]); n_attempts = __double2loint(d[15 * THREADS]);
+                        mode = __double2hiint(d[16 * THREADS]);
+                        const int fl = __double2loint(d[16 * THREADS]);
+                        rejected = fl & 1; new_step = (fl & 2) != 0; any_v = (fl & 4) != 0;
+                        status = 100;
+                        ftab = A.ftab + (size_t)sid * ns * 4;
+                        trk = A.track + (size_t)sid * ns * 4;
+                    } else {
+                        mode = M_IDLE;
+                    }
+                    __syncthreads();                                     /* staging reusable by the next packing */
+                }
+            }
+        }
         if (mode == M_RK) {
             if (new_step) {
                 min_step = 10.0 * (tcr_bits2d(tcr_d2bits(t) + 1) - t);

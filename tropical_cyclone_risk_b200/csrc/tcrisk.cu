@@ -611,7 +611,9 @@ static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_uppe
     int grid = (int)std::max<int64_t>(1, std::min(max_ctas, want_ctas));
     int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
     a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
-    const size_t smem = KSMEM == 2 ? (size_t)32 * THREADS * sizeof(double) : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
+    { static const int pack_on = getenv("TCR_NO_PACK") ? 0 : 1; a.pack = pack_on; }
+    /* KSMEM 2: eight stage vectors + the 17-word staging area of the drain-phase packing */
+    const size_t smem = KSMEM == 2 ? (size_t)(32 + 17) * THREADS * sizeof(double) : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
     cudaFuncSetAttribute(k_integrate<THREADS, MINB, KSMEM, LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     LaunchTimer lt_(h, TCR_K_INTEGRATE);
     k_integrate<THREADS, MINB, KSMEM, LOCKSTEP><<<grid, THREADS, smem, h->stream>>>(h->ctx, a);
