@@ -440,6 +440,7 @@ def run_gpu_arm(args):
         if not args.no_interp:
             line["roofline_interp"] = bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args)
             line["roofline_poi"] = bench_poi(eng, torch, dev, peak, peak_src, ns)
+            line["roofline_windstats"] = bench_windstats(eng, torch, dev, peak, peak_src)
         if world == 1 and not args.no_cpu:
             threads = cpu_threads()
             n_att = args.cpu_attempts or 60000 * threads
@@ -521,6 +522,44 @@ def bench_poi(eng, torch, dev, peak, peak_src, ns, n_rows=400000):
             "note": "bytes = 8 B latitude per sample + 16 B (lon, vmax) for the %.1f %% of samples inside the latitude band of "
                     "the point + 8 B per track; the notebook's dense formulation would read 24 B per sample" % (100.0 * in_band / samples),
             "l2": "3 x %d MB track arrays, streamed" % (samples * 8 >> 20)}
+
+
+def bench_windstats(eng, torch, dev, peak, peak_src, nlat=721, nlon=1440, n_days=31):
+    """Monthly wind mean / covariance reduction (track/env_wind.py:169-228) on the native
+    0.25-degree ERA5 grid, device-resident float32 (time, level, lat, lon) blocks with the two steering
+    levels: (a) the reference's own input, 2 x daily samples with no daily averaging; (b) 4 x daily
+    samples averaged per day first.  A streaming pass: 16 B read per (sample, grid point), 112 B
+    written per grid point."""
+    n_pts = nlat * nlon
+    g = torch.Generator(device=dev); g.manual_seed(13)
+    out = torch.empty((14, n_pts), dtype=torch.float64, device=dev)
+    res = {}
+    for name, spd, grouped in (("2x_daily_ungrouped", 2, False), ("4x_daily_daily_means", 4, True)):
+        n_time = n_days * spd
+        ua = torch.randn((n_time, 2, n_pts), generator=g, device=dev, dtype=torch.float32) * 8.0
+        va = torch.randn((n_time, 2, n_pts), generator=g, device=dev, dtype=torch.float32) * 6.0
+        gs = np.arange(0, n_time + 1, spd if grouped else 1, dtype=np.int32)
+        series = [ua.data_ptr(), va.data_ptr(), ua.data_ptr() + 4 * n_pts, va.data_ptr() + 4 * n_pts]
+        for _ in range(3):
+            eng.wind_stats_dev(n_time, n_pts, 2 * n_pts, series, gs, out.data_ptr())
+        torch.cuda.synchronize()
+        eng.set_timing(True)
+        for _ in range(10):
+            eng.wind_stats_dev(n_time, n_pts, 2 * n_pts, series, gs, out.data_ptr())
+        ms, cnt = eng.kernel_times()["windstat"]
+        eng.set_timing(False)
+        moved = 16.0 * n_time * n_pts + 112.0 * n_pts
+        ach = moved / (ms / cnt * 1e-3) / 1e9
+        res[name] = {"achieved": ach, "frac": ach / peak, "avg_launch_ms": ms / cnt, "launches": cnt, "n_time": n_time,
+                     "n_groups": int(gs.size - 1), "algorithmic_bytes": moved}
+        del ua, va
+    head = res["2x_daily_ungrouped"]
+    return {"kernel": "k_wind_stats", "bound": "hbm", "achieved": head["achieved"], "peak": peak, "unit": "GB/s",
+            "frac": head["frac"], "traffic": None, "peak_source": peak_src, "avg_launch_ms": head["avg_launch_ms"],
+            "launches": head["launches"], "grid": "%d x %d (0.25 deg)" % (nlat, nlon), "cases": res,
+            "note": "bytes = 16 B per (sample, grid point) read once + 14 x 8 B per grid point written",
+            "l2": "inputs %d MB and %d MB, streamed (>> L2)" % (res["2x_daily_ungrouped"]["algorithmic_bytes"] / 2**20,
+                                                               res["4x_daily_daily_means"]["algorithmic_bytes"] / 2**20)}
 
 
 _JSON_OUT = None

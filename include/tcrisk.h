@@ -229,7 +229,9 @@ int64_t tcr_launch_count(tcr_handle* h);
 #define TCR_K_BUILD        7
 #define TCR_K_FTABLE       8
 #define TCR_K_POI          9
-#define TCR_N_KERNEL_CLASSES 10
+#define TCR_K_WINDSTAT     10
+#define TCR_K_THERMO       11
+#define TCR_N_KERNEL_CLASSES 12
 int tcr_set_timing(tcr_handle* h, int enable);
 int tcr_kernel_time(tcr_handle* h, int kernel_class, double* ms, int64_t* launches);
 /* tcr_env_interp implementation: 0 = per-lane LDG.128 gathers, 1 = TMA bulk copies
@@ -245,6 +247,20 @@ int tcr_poi_vmax(tcr_handle* h, int64_t n_rows, int n_steps, const double* lon, 
 /* replaces: cell 17 -- exceedance_count[b] = sum(vmax_at_poi >= vmax_bins[b]); n_bins <= 64;
  * v host or device per on_device, bins and counts host                                        */
 int tcr_exceedance(tcr_handle* h, int64_t n, const double* v, int n_bins, const double* bins, int64_t* counts, int on_device);
+
+/* ---- monthly wind mean / covariance reduction (SURVEY 8f "next" row N3, first half) ------ */
+/* replaces: calc_wnd_stat (track/env_wind.py:169-228) for one month: the samples of the month
+ * (ua, va at the upper = 250 hPa and lower = 850 hPa steering level, float32, sample t of grid
+ * point p at x[t * t_stride + p] -- so a (time, level, lat, lon) array is passed by level-slice
+ * pointers with t_stride = n_level * n_pts, no copy) are averaged per day
+ * (groupby("time.day").mean, :188-190; day g = samples [group_start[g], group_start[g+1]); daily
+ * or coarser data: one sample per group), then reduced to the 14 statistics in the reference's
+ * order (:206-216): ua250, va250, ua850, va850 means; then the lower triangle row by row with
+ * .var (ddof 0, :211) on the diagonal and xr.cov (ddof 1, :213) off it.  NaNs are skipped the way
+ * xarray's skipna reductions do.  out [14][n_pts] float64.  Pointers host or device per on_device. */
+int tcr_wind_stats(tcr_handle* h, int n_time, int64_t n_pts, int64_t t_stride,
+                   const float* ua_upper, const float* va_upper, const float* ua_lower, const float* va_lower,
+                   int n_groups, const int32_t* group_start /* host, [n_groups + 1] */, double* out, int on_device);
 
 /* page-locked host memory for the caller's input planes / result arrays (the reference's
  * NumPy arrays of util/compute.py:126-133 become views of this block): makes the host<->device

@@ -1,0 +1,65 @@
+"""CPU oracle of the pre-processing kernels -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline legs may import this module.
+
+wind_stats(): NumPy restatement of calc_wnd_stat (track/env_wind.py:169-228).  The reference
+runs on xarray, which is NOT installed in this container and whose version environment.yml does
+not pin -- **parity unpinned** against the reference for this function.  What is restated is
+xarray's published reduction semantics:
+  * ``.groupby("time.day").mean(dim="time")``  -> per day: nanmean (skipna default for floats)
+  * ``.mean(dim)``                             -> nanmean
+  * ``.var(dim)``  (ddof = 0)                  -> numpy.nanvar: mean of (x - nanmean)^2 over valid x
+  * ``xr.cov(a, b, dim)`` (ddof = 1)           -> xarray/computation.py::_cov_corr:
+        valid = a.notnull() & b.notnull(); a, b = a.where(valid), b.where(valid)
+        cov = ((a - a.mean()) * (b - b.mean())).sum(skipna=True, min_count=1) / (valid.sum() - ddof)
+and it is pinned against numpy.mean / numpy.var / numpy.cov on NaN-free input
+(tests/test_preproc.py).  Arithmetic: float32 samples widened to float64, every reduction a
+sequential float64 sum in time order (what NumPy does for axis-0 reductions of a C-contiguous
+array), so the CUDA kernel can be compared bit for bit.
+"""
+import numpy as np
+
+N_STATS = 14
+# lower triangle, row by row (env_wind.py:30-42, 215): (i, j) with j <= i
+PAIRS = [(i, j) for i in range(4) for j in range(i + 1)]
+
+
+def _nansum0(x):
+    """Sequential sum over axis 0 with NaNs replaced by zero (numpy.nansum semantics)."""
+    return np.add.reduce(np.where(np.isnan(x), 0.0, x), axis=0)
+
+
+def daily_means(x, group_start):
+    """x [n_time, n_pts] float32 -> [n_groups, n_pts] float64, nanmean of each day's samples."""
+    x = np.asarray(x, dtype=np.float64)
+    out = np.empty((len(group_start) - 1, x.shape[1]))
+    for g in range(len(group_start) - 1):
+        blk = x[group_start[g]:group_start[g + 1]]
+        cnt = np.add.reduce(~np.isnan(blk), axis=0)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out[g] = np.where(cnt > 0, _nansum0(blk) / cnt, np.nan)
+    return out
+
+
+def wind_stats(series, group_start):
+    """series: four arrays [n_time, n_pts] float32 in the order ua250, va250, ua850, va850
+    (env_wind.py:200-201); group_start [n_groups + 1].  Returns [14, n_pts] float64 in the
+    reference's order: 4 means, then var / cov over the lower triangle row by row."""
+    dm = [daily_means(s, group_start) for s in series]
+    n_pts = dm[0].shape[1]
+    out = np.empty((N_STATS, n_pts))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for k, (i, j) in enumerate(PAIRS):
+            valid = ~np.isnan(dm[i]) & ~np.isnan(dm[j])
+            cnt = np.add.reduce(valid, axis=0).astype(np.float64)
+            a = np.where(valid, dm[i], np.nan)
+            b = np.where(valid, dm[j], np.nan)
+            mi = _nansum0(a) / cnt
+            mj = _nansum0(b) / cnt
+            acc = _nansum0((a - mi) * (b - mj))
+            if i == j:
+                out[i] = mi                                   # .mean(dim)        env_wind.py:207
+                out[4 + k] = acc / cnt                        # .var(dim), ddof 0  env_wind.py:211
+            else:
+                out[4 + k] = np.where(cnt > 0, acc / (cnt - 1.0), np.nan)   # xr.cov, ddof 1  env_wind.py:213
+    return out

@@ -1,0 +1,178 @@
+"""Pre-processing kernels.
+
+Wind mean / covariance reduction (track/env_wind.py:169-228): the reference runs on xarray, which
+this container does not have, so the oracle (oracle/preproc_oracle.py) restates xarray's published
+reduction semantics and is pinned here against numpy.mean / numpy.var / numpy.cov; the CUDA kernel
+(tcr_wind_stats) must match the oracle bit for bit."""
+import datetime
+import os
+
+import numpy as np
+import pytest
+
+from oracle import preproc_oracle as po
+
+
+def synth_winds(n_time, n_lvl, nlat, nlon, seed=0, nan_frac=0.0):
+    """ERA5-like (time, level, lat, lon) float32 winds: smooth jets + day-to-day synoptic noise."""
+    rng = np.random.default_rng(seed)
+    lat = np.linspace(-90, 90, nlat)[None, None, :, None]
+    lon = np.linspace(0, 360, nlon, endpoint=False)[None, None, None, :]
+    lvl = np.arange(n_lvl)[None, :, None, None]
+    t = np.arange(n_time)[:, None, None, None]
+    ua = 12 * np.cos(np.deg2rad(3 * lat)) * (1 + 0.3 * lvl) + 3 * np.sin(np.deg2rad(lon) + 0.2 * t)
+    va = 2 * np.sin(np.deg2rad(2 * lon) + 0.3 * t) * np.cos(np.deg2rad(lat)) + 0.5 * lvl
+    ua = (ua + rng.normal(0, 4, (n_time, n_lvl, nlat, nlon))).astype(np.float32)
+    va = (va + 0.5 * ua + rng.normal(0, 3, (n_time, n_lvl, nlat, nlon))).astype(np.float32)
+    if nan_frac:
+        ua[rng.random(ua.shape) < nan_frac] = np.nan
+        va[rng.random(va.shape) < nan_frac] = np.nan
+    return ua, va
+
+
+def series_of(ua, va, iu, il):
+    n_time = ua.shape[0]
+    return [a[:, k].reshape(n_time, -1) for k in (iu, il) for a in (ua, va)]
+
+
+def test_oracle_matches_numpy_on_nan_free_input():
+    ua, va = synth_winds(62, 3, 13, 24, seed=1)
+    s = series_of(ua, va, 0, 2)
+    got = po.wind_stats(s, np.arange(63))
+    x = np.stack([a.astype(np.float64) for a in s])                  # [4, n_time, n_pts]
+    assert np.array_equal(got[:4], x.mean(axis=1))                    # .mean(dim)          env_wind.py:207
+    k = 4
+    for i in range(4):
+        for j in range(i + 1):
+            if i == j:
+                assert np.array_equal(got[k], x[i].var(axis=0))       # .var(dim), ddof 0   env_wind.py:211
+            else:
+                want = np.array([np.cov(x[i][:, p], x[j][:, p], ddof=1)[0, 1] for p in range(x.shape[2])])
+                np.testing.assert_allclose(got[k], want, rtol=1e-11, atol=1e-12)   # xr.cov, ddof 1   :213
+            k += 1
+    assert k == po.N_STATS
+
+
+def test_oracle_daily_grouping_and_nan_policy():
+    ua, va = synth_winds(20, 2, 3, 5, seed=2, nan_frac=0.15)
+    s = series_of(ua, va, 0, 1)
+    gs = np.arange(0, 21, 4)                                           # 5 days x 4 samples
+    got = po.wind_stats(s, gs)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        dm = [np.nanmean(a.astype(np.float64).reshape(5, 4, -1), axis=1) for a in s]
+        np.testing.assert_allclose(got[0], np.nanmean(dm[0], axis=0), rtol=1e-14)
+        np.testing.assert_allclose(got[4], np.nanvar(dm[0], axis=0), rtol=1e-13)
+        # xr.cov: only the days on which BOTH variables are valid
+        a, b = dm[1].copy(), dm[0].copy()
+        both = ~np.isnan(a) & ~np.isnan(b)
+        a[~both] = np.nan
+        b[~both] = np.nan
+        want = np.nansum((a - np.nanmean(a, 0)) * (b - np.nanmean(b, 0)), axis=0) / (both.sum(0) - 1)
+    ok = both.sum(0) > 1
+    np.testing.assert_allclose(got[5][ok], want[ok], rtol=1e-12)
+
+
+def test_month_samples_literal_and_intent():
+    from tropical_cyclone_risk_b200 import preproc
+    t0 = datetime.datetime(2001, 8, 30)
+    times = [t0 + datetime.timedelta(hours=12 * k) for k in range(80)]   # 2 x daily, Aug 30 .. Oct 8
+    idx, gs = preproc.month_samples(times, datetime.datetime(2001, 9, 15))
+    assert idx[0] == 4 and idx.size == 60                                 # September: 30 days x 2
+    assert np.array_equal(gs, np.arange(61))                              # literal reference: no daily averaging
+    idx, gs = preproc.month_samples(times, datetime.datetime(2001, 9, 15), group_sub_daily=True)
+    assert np.array_equal(gs, np.arange(0, 61, 2))
+    times5 = [datetime.datetime(2001, 1, 1) + datetime.timedelta(days=5 * k) for k in range(30)]
+    idx, gs = preproc.month_samples(np.array(times5, dtype="datetime64[s]"), datetime.datetime(2001, 3, 15))
+    assert idx.size == 6 and np.array_equal(gs, np.arange(7))            # one sample per day group
+    with pytest.raises(ValueError):
+        preproc.month_samples(times, datetime.datetime(2003, 1, 15))
+
+
+def test_names_match_table_channels():
+    from tropical_cyclone_risk_b200 import layout, preproc
+    assert preproc.wind_mean_vector_names() + preproc.wind_cov_matrix_names() == list(layout.FIELD_NAMES[:14])
+    assert preproc.level_index([1000, 850, 250], "hPa", 250) == 2
+    assert preproc.level_index([100000, 85000, 25000], "Pa", 850) == 1
+
+
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def engine():
+    from tropical_cyclone_risk_b200 import namelist as nl
+    from tropical_cyclone_risk_b200.engine import Engine
+    from tropical_cyclone_risk_b200.params import params_from_namelist
+    eng = Engine(params_from_namelist(nl, "NA"), device=0)
+    yield eng
+    eng.close()
+
+
+WS_VARIANTS_SINGLE = [None, 10, 11, 12, 13, 14]
+WS_VARIANTS_GROUPED = [None, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9]
+
+
+def _with_variant(v, fn):
+    old = os.environ.pop("TCR_WS_VARIANT", None)
+    try:
+        if v is not None:
+            os.environ["TCR_WS_VARIANT"] = str(v)
+        return fn()
+    finally:
+        os.environ.pop("TCR_WS_VARIANT", None)
+        if old is not None:
+            os.environ["TCR_WS_VARIANT"] = old
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,nan_frac", [((181, 360), 0.0), ((7, 143), 0.1), ((1, 3), 0.0), ((33, 128), 0.3)])
+def test_gpu_wind_stats_ungrouped_bit_exact(engine, shape, nan_frac):
+    """The reference's own case: 2 x daily samples, no daily averaging (62 single-sample groups);
+    ragged / unaligned rows (n_pts = 1001, 3) take the register path."""
+    ua, va = synth_winds(62, 3, shape[0], shape[1], seed=3, nan_frac=nan_frac)
+    gs = np.arange(63, dtype=np.int32)
+    want = po.wind_stats(series_of(ua, va, 2, 0), gs)
+    for v in WS_VARIANTS_SINGLE:
+        got = _with_variant(v, lambda: engine.wind_stats(ua, va, 2, 0, gs))
+        assert np.array_equal(got, want, equal_nan=True), "variant %s" % v
+    assert not np.isnan(want[:, 0]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,nan_frac", [((91, 180), 0.0), ((5, 77), 0.2)])
+def test_gpu_wind_stats_daily_groups_bit_exact(engine, shape, nan_frac):
+    """Daily means first (4 x daily, ragged first and last day), every kernel variant."""
+    ua, va = synth_winds(118, 2, shape[0], shape[1], seed=4, nan_frac=nan_frac)
+    gs = np.r_[0, np.arange(2, 118, 4), 118].astype(np.int32)             # 2 + 29 x 4 (the last one 4) samples
+    assert np.all(np.diff(gs) > 0)
+    want = po.wind_stats(series_of(ua, va, 0, 1), gs)
+    for v in WS_VARIANTS_GROUPED:
+        got = _with_variant(v, lambda: engine.wind_stats(ua, va, 0, 1, gs))
+        assert np.array_equal(got, want, equal_nan=True), "variant %s" % v
+
+
+@pytest.mark.gpu
+def test_gpu_calc_wnd_stat_mirror(engine):
+    """calc_wnd_stat through the reference-shaped host function: month selection out of a longer record."""
+    from tropical_cyclone_risk_b200 import preproc
+    t0 = datetime.datetime(2001, 8, 30)
+    times = [t0 + datetime.timedelta(hours=12 * k) for k in range(80)]
+    ua, va = synth_winds(80, 4, 19, 36, seed=5)
+    levels = [1000, 850, 500, 250]
+    got = preproc.calc_wnd_stat(engine, ua, va, times, levels, datetime.datetime(2001, 9, 15))
+    want = po.wind_stats(series_of(ua[4:64], va[4:64], 3, 1), np.arange(61))
+    assert got.shape == (14, 19, 36)
+    assert np.array_equal(got.reshape(14, -1), want)
+    got = preproc.calc_wnd_stat(engine, ua, va, times, levels, datetime.datetime(2001, 9, 15), group_sub_daily=True)
+    want = po.wind_stats(series_of(ua[4:64], va[4:64], 3, 1), np.arange(0, 61, 2))
+    assert np.array_equal(got.reshape(14, -1), want)
+
+
+@pytest.mark.gpu
+def test_gpu_wind_stats_rejects_bad_groups(engine):
+    from tropical_cyclone_risk_b200._lib import TcrError
+    ua, va = synth_winds(8, 2, 4, 8)
+    with pytest.raises(TcrError):
+        engine.wind_stats(ua, va, 0, 1, np.array([0, 4, 4, 8], np.int32))      # empty day
+    with pytest.raises(TcrError):
+        engine.wind_stats(ua, va, 0, 1, np.array([0, 4, 7], np.int32))         # does not end at n_time

@@ -9,11 +9,13 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "tcr_kernels.cuh"
+#include "tcr_preproc.cuh"
 
 #define TCR_VERSION 100
 
@@ -1189,4 +1191,98 @@ int tcr_prepare_month(tcr_handle* h, int ym, const tcr_prep_spec* sp, const floa
     return 0;
 }
 
+/* ---- monthly wind mean / covariance reduction (track/env_wind.py:169-228) --------- */
 }  // extern "C"
+
+template <int VEC, int KSPLIT, int U>
+static int launch_wind_stats(tcr_handle* h, const WindStatArgs& a)
+{
+    constexpr int P = 32 * VEC;
+    const size_t smem = (size_t)(a.n_groups + 1) * 4 * P * sizeof(double);
+    if (smem > h->smem_optin) return set_err("tcr_wind_stats: %d day groups need %zu B of shared memory (limit %zu)", a.n_groups, smem, h->smem_optin);
+    CK(cudaFuncSetAttribute(k_wind_stats<VEC, KSPLIT, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (a.n_pts + P - 1) / P;
+    if (grid > 0x7fffffffLL) return set_err("tcr_wind_stats: too many grid points");
+    LaunchTimer lt_(h, TCR_K_WINDSTAT);
+    k_wind_stats<VEC, KSPLIT, U><<<(unsigned)grid, 128 * KSPLIT, smem, h->stream>>>(a);
+    return 0;
+}
+
+template <int P, int NT>
+static int launch_wind_stats_single(tcr_handle* h, const WindStatArgs& a)
+{
+    const size_t smem = (size_t)a.n_groups * 4 * P * sizeof(float) + (size_t)4 * P * sizeof(double);
+    if (smem > h->smem_optin) return set_err("tcr_wind_stats: %d samples need %zu B of shared memory (limit %zu)", a.n_groups, smem, h->smem_optin);
+    CK(cudaFuncSetAttribute(k_wind_stats_single<P, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t grid = (a.n_pts + P - 1) / P;
+    if (grid > 0x7fffffffLL) return set_err("tcr_wind_stats: too many grid points");
+    LaunchTimer lt_(h, TCR_K_WINDSTAT);
+    k_wind_stats_single<P, NT><<<(unsigned)grid, NT, smem, h->stream>>>(a);
+    return 0;
+}
+
+extern "C" {
+
+int tcr_wind_stats(tcr_handle* h, int n_time, int64_t n_pts, int64_t t_stride,
+                   const float* ua_upper, const float* va_upper, const float* ua_lower, const float* va_lower,
+                   int n_groups, const int32_t* group_start, double* out, int on_device)
+{
+    if (!h) return set_err("null handle");
+    if (n_time <= 0 || n_pts <= 0 || n_groups <= 0 || n_groups > n_time || t_stride < n_pts) return set_err("tcr_wind_stats: bad shape");
+    if (!ua_upper || !va_upper || !ua_lower || !va_lower || !group_start || !out) return set_err("tcr_wind_stats: null argument");
+    if (group_start[0] != 0 || group_start[n_groups] != n_time) return set_err("tcr_wind_stats: group_start must run from 0 to n_time");
+    for (int g = 0; g < n_groups; ++g)
+        if (group_start[g + 1] <= group_start[g]) return set_err("tcr_wind_stats: day group %d is empty or out of order", g);
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const float* hsrc[4] = {ua_upper, va_upper, ua_lower, va_lower};
+    DevBuf in, o, gs;
+    if (gs.ensure((size_t)(n_groups + 1) * 4)) return -1;
+    CK(cudaMemcpyAsync(gs.p, group_start, (size_t)(n_groups + 1) * 4, cudaMemcpyHostToDevice, s));
+    WindStatArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_pts = n_pts; a.n_time = n_time; a.n_groups = n_groups; a.gstart = gs.as<int32_t>();
+    if (on_device) {
+        for (int v = 0; v < 4; ++v) a.src[v] = hsrc[v];
+        a.t_stride = t_stride; a.out = out;
+    } else {
+        const size_t plane = (size_t)n_time * n_pts;
+        if (in.ensure(plane * 4 * sizeof(float)) || o.ensure((size_t)n_pts * 14 * sizeof(double))) { in.release(); o.release(); gs.release(); return -1; }
+        for (int v = 0; v < 4; ++v) {
+            CK(cudaMemcpy2DAsync(in.as<float>() + plane * v, (size_t)n_pts * 4, hsrc[v], (size_t)t_stride * 4, (size_t)n_pts * 4, n_time, cudaMemcpyHostToDevice, s));
+            a.src[v] = in.as<float>() + plane * v;
+        }
+        a.t_stride = n_pts; a.out = o.as<double>();
+    }
+    const char* ws_env = getenv("TCR_WS_VARIANT");                       /* tuning sweeps only */
+    const int variant = ws_env ? atoi(ws_env) : -1;
+    const bool single = n_groups == n_time;
+    int rc;
+    switch (variant >= 0 ? variant : single ? 10 : 9) {
+    case 10: rc = launch_wind_stats_single<32, 64>(h, a); break;
+    case 11: rc = launch_wind_stats_single<64, 128>(h, a); break;
+    case 12: rc = launch_wind_stats_single<32, 128>(h, a); break;
+    case 13: rc = launch_wind_stats_single<64, 256>(h, a); break;
+    case 14: rc = launch_wind_stats_single<128, 256>(h, a); break;
+    case 0: rc = launch_wind_stats<1, 1, 8>(h, a); break;
+    case 1: rc = launch_wind_stats<2, 1, 8>(h, a); break;
+    default:
+    case 2: rc = launch_wind_stats<2, 2, 8>(h, a); break;
+    case 3: rc = launch_wind_stats<4, 2, 4>(h, a); break;
+    case 4: rc = launch_wind_stats<1, 2, 8>(h, a); break;
+    case 5: rc = launch_wind_stats<2, 2, 4>(h, a); break;
+    case 6: rc = launch_wind_stats<4, 4, 4>(h, a); break;
+    case 7: rc = launch_wind_stats<1, 1, 16>(h, a); break;
+    case 8: rc = launch_wind_stats<1, 2, 4>(h, a); break;
+    case 9: rc = launch_wind_stats<2, 4, 4>(h, a); break;
+    }
+    if (rc) { in.release(); o.release(); gs.release(); return rc; }
+    CKK(h);
+    if (!on_device) CK(cudaMemcpyAsync(out, a.out, (size_t)n_pts * 14 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    in.release(); o.release(); gs.release();
+    return 0;
+}
+
+}  // extern "C"
+

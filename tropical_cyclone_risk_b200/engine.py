@@ -88,7 +88,7 @@ class Engine:
         return int(self.lib.tcr_launch_count(self._h))
 
     KERNEL_CLASSES = ("env_interp", "integrate", "postprocess", "seed", "coef", "select", "gather", "build", "ftable",
-                      "poi")
+                      "poi", "windstat", "thermo")
 
     def set_timing(self, enable=True):
         """CUDA-event accounting of every kernel class on the handle's stream (resets the totals)."""
@@ -253,6 +253,32 @@ class Engine:
         return [{f: getattr(s, f) for f, _ in TcrYearStats._fields_} for s in stats]
 
     # -- return-period reduction (notebooks/sample_analysis.ipynb cells 13-17) -----------------------
+    # -- pre-processing -----------------------------------------------------------
+    def wind_stats(self, ua, va, i_upper, i_lower, group_start):
+        """calc_wnd_stat (track/env_wind.py:169-228) on the month's samples ua, va
+        [n_time, n_level, ...grid] float32 (C-contiguous; the two steering levels are passed as
+        level-slice pointers, no copy).  Returns [14, n_pts] float64."""
+        ua, va = _arr(ua, np.float32), _arr(va, np.float32)
+        gs = _arr(group_start, np.int32)
+        n_time, n_lvl = ua.shape[0], ua.shape[1]
+        n_pts = int(np.prod(ua.shape[2:]))
+        out = np.empty((14, n_pts))
+        base_u, base_v = ua.ctypes.data, va.ctypes.data
+        vp = C.c_void_p
+        _lib.check(self.lib.tcr_wind_stats(
+            self._h, n_time, n_pts, n_lvl * n_pts,
+            vp(base_u + 4 * n_pts * i_upper), vp(base_v + 4 * n_pts * i_upper),
+            vp(base_u + 4 * n_pts * i_lower), vp(base_v + 4 * n_pts * i_lower),
+            gs.size - 1, _ptr(gs), _ptr(out), 0))
+        return out
+
+    def wind_stats_dev(self, n_time, n_pts, t_stride, d_series, group_start, d_out):
+        """Same on device pointers: d_series = four device addresses (ua250, va250, ua850, va850)."""
+        gs = _arr(group_start, np.int32)
+        vp = C.c_void_p
+        _lib.check(self.lib.tcr_wind_stats(self._h, int(n_time), int(n_pts), int(t_stride), vp(d_series[0]), vp(d_series[1]),
+                                           vp(d_series[2]), vp(d_series[3]), gs.size - 1, _ptr(gs), vp(d_out), 1))
+
     def poi_vmax(self, lon, lat, vmax, poi_lon, poi_lat, radius_km=100.0, r_earth_m=6378000.0):
         """Per-track maximum of vmax while within radius_km of (poi_lon, poi_lat); NaN if never."""
         lon, lat, vmax = (_arr(x, np.float64) for x in (lon, lat, vmax))
