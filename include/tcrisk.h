@@ -262,6 +262,22 @@ int tcr_wind_stats(tcr_handle* h, int n_time, int64_t n_pts, int64_t t_stride,
                    const float* ua_upper, const float* va_upper, const float* ua_lower, const float* va_lower,
                    int n_groups, const int32_t* group_start /* host, [n_groups + 1] */, double* out, int on_device);
 
+/* ---- potential intensity, saturation deficit, mid-level humidity (second half) ---- */
+/* replaces: one time sample of compute_thermo (thermo/calc_thermo.py:60-69) --
+ *   vmax = thermo.CAPE_PI_vectorized(sst, psl, lvl, ta, hus)              (thermo/thermo.py:266-412)
+ *   chi = clip(thermo.sat_deficit(sst, psl, ta_mid, p_mid, hus_mid), 0, 10)   (thermo.py:92-104)
+ *   rh_mid = thermo.conv_q_to_rh(ta_mid, hus_mid, p_mid)                      (thermo.py:42-47)
+ * for namelist.select_thermo = 1, select_interp = 2.  tcr_set_entropy_table uploads the look-up table
+ * the reference loads from thermo/entropy_table.npz (p [np] Pa ascending, s [ns] ascending, T [np][ns];
+ * thermo.py:274-278, 317).  ta, hus [nlev][n_pts] float32 with the lowest model level first
+ * (calc_thermo.py:50-55), p_env [nlev] in Pa (host), sst [n_pts] K already on the atmospheric grid
+ * (calc_thermo.py:38-42), psl [n_pts] Pa, k_mid = the level nearest namelist.p_midlevel; outputs
+ * float64 [n_pts].  Field pointers host or device per on_device.                                  */
+int tcr_set_entropy_table(tcr_handle* h, int np, int ns, const double* p_look, const double* s_look, const double* T_lookup);
+int tcr_thermo_month(tcr_handle* h, int64_t n_pts, int nlev, const double* p_env, const float* ta, const float* hus,
+                     const double* sst, const double* psl, double ck_over_cd, int k_mid,
+                     double* vmax, double* chi, double* rh_mid, int on_device);
+
 /* page-locked host memory for the caller's input planes / result arrays (the reference's
  * NumPy arrays of util/compute.py:126-133 become views of this block): makes the host<->device
  * copies of tcr_upload_month / tcr_run_years run at PCIe speed                               */

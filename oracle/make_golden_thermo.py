@@ -1,0 +1,50 @@
+"""Golden vectors of the thermodynamic pre-processing from the UNMODIFIED reference:
+thermo.CAPE_PI_vectorized / sat_deficit / conv_q_to_rh exactly as thermo/calc_thermo.py:60-69 calls
+them, on synthetic ERA5-shaped soundings.  Build container only (needs /root/reference):
+
+    python oracle/make_golden_thermo.py      ->  tests/golden/ref_thermo.npz
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as rh                                  # noqa: E402
+from tropical_cyclone_risk_b200 import synth_thermo                   # noqa: E402
+
+N = 2048
+K_MID = 13                                                            # 600 hPa = namelist.p_midlevel (nearest level)
+
+
+def main():
+    if not rh.available():
+        raise SystemExit("reference tree not present")
+    ref = rh.load_reference()
+    th, nl = ref.thermo, ref.namelist
+    assert nl.select_thermo == 1 and nl.select_interp == 2
+    p, ta, hus, sst, psl = synth_thermo.soundings(N, seed=7)
+    assert p[K_MID] == nl.p_midlevel
+    nlat, nlon = 32, N // 32
+    shp = (nlat, nlon)
+    ta64 = ta.astype(np.float64).reshape((p.size,) + shp)
+    hus64 = hus.astype(np.float64).reshape((p.size,) + shp)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        vmax = th.CAPE_PI_vectorized(sst.reshape(shp), psl.reshape(shp), p.copy(), ta64, hus64)       # calc_thermo.py:60-61
+        chi = np.minimum(np.maximum(th.sat_deficit(sst.reshape(shp), psl.reshape(shp), ta64[K_MID], float(p[K_MID]),
+                                                   hus64[K_MID]), 0), 10)                                # :66-68
+        rh_mid = th.conv_q_to_rh(ta64[K_MID], hus64[K_MID], float(p[K_MID]))                            # :69
+    with np.load(os.path.join(rh.REF_ROOT, "thermo", "entropy_table.npz")) as t:
+        crc = int(np.frombuffer(t["T"].tobytes(), dtype=np.uint32).sum() & 0xffffffff)
+    out = os.path.join(ROOT, "tests", "golden", "ref_thermo.npz")
+    np.savez_compressed(out, p=p, ta=ta, hus=hus, sst=sst, psl=psl, k_mid=K_MID, cecd=nl.Ck / nl.Cd,
+                        vmax=vmax.reshape(-1), chi=chi.reshape(-1), rh_mid=rh_mid.reshape(-1), table_crc=crc)
+    print("wrote", out, os.path.getsize(out), "bytes; PI>0 in %d of %d columns, max %.1f m/s" %
+          ((vmax > 0).sum(), N, np.nanmax(vmax)))
+
+
+if __name__ == "__main__":
+    main()

@@ -63,3 +63,33 @@ def wind_stats(series, group_start):
             else:
                 out[4 + k] = np.where(cnt > 0, acc / (cnt - 1.0), np.nan)   # xr.cov, ddof 1  env_wind.py:213
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# thermodynamic pre-processing: ctypes front end of preproc_oracle.c (thermo/thermo.py restated)
+# ---------------------------------------------------------------------------------------------
+def thermo(p_env, ta, hus, sst, psl, table, cecd, k_mid):
+    """vmax (potential intensity), chi, rh_mid for every column -- one time sample of compute_thermo
+    (thermo/calc_thermo.py:60-69).  ta, hus [nlev, n] float32 (lowest level first), p_env [nlev] Pa,
+    sst / psl [n]; table = (p_look, s_look, T_lookup) of thermo/entropy_table.npz."""
+    import ctypes as C
+    from oracle import tcr_oracle
+    lib = tcr_oracle.lib()
+    p_env = np.ascontiguousarray(p_env, dtype=np.float64)
+    ta = np.ascontiguousarray(ta, dtype=np.float32)
+    hus = np.ascontiguousarray(hus, dtype=np.float32)
+    sst = np.ascontiguousarray(sst, dtype=np.float64).reshape(-1)
+    psl = np.ascontiguousarray(psl, dtype=np.float64).reshape(-1)
+    pl, sl, tl = (np.ascontiguousarray(a, dtype=np.float64) for a in table)
+    nlev, n = p_env.size, sst.size
+    ta = ta.reshape(nlev, n)
+    hus = hus.reshape(nlev, n)
+    out = [np.empty(n) for _ in range(3)]
+    vp = C.c_void_p
+    lib.orc_thermo.restype = None
+    lib.orc_thermo.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_double, C.c_int,
+                               C.c_double] + [vp] * 3
+    lib.orc_thermo(n, nlev, p_env.ctypes.data, ta.ctypes.data, hus.ctypes.data, sst.ctypes.data, psl.ctypes.data,
+                   pl.size, sl.size, pl.ctypes.data, sl.ctypes.data, tl.ctypes.data, float(cecd), int(k_mid),
+                   float(p_env[k_mid]), *[o.ctypes.data for o in out])
+    return tuple(out)

@@ -49,12 +49,13 @@ def load_reference():
         from track import bam_track, env_wind                 # noqa: E402
         from util import basins, mat, sphere                  # noqa: E402
         from wind import tc_wind                              # noqa: E402
+        from thermo import thermo as thermo_mod               # noqa: E402
         sys.modules.update(shadow)
     finally:
         sys.path[:] = saved
     bam_track.random_seed = lambda: None                      # kill wall-clock reseeding (bam_track.py:37)
     _REF = Ref(namelist=namelist, coupled_fast=coupled_fast, bam_track=bam_track, env_wind=env_wind,
-               basins=basins, mat=mat, sphere=sphere, tc_wind=tc_wind)
+               basins=basins, mat=mat, sphere=sphere, tc_wind=tc_wind, thermo=thermo_mod)
     return _REF
 
 

@@ -37,9 +37,9 @@ class OrcEnv(C.Structure):
 def build():
     """Compile liborc.so if missing or stale (gcc only; seconds)."""
     so = os.path.join(_HERE, "liborc.so")
-    src = os.path.join(_HERE, "tcr_oracle.c")
+    srcs = [os.path.join(_HERE, f) for f in ("tcr_oracle.c", "preproc_oracle.c")]
     hdrs = [os.path.join(_HERE, "..", "include", h) for h in ("tcrisk.h", "tcr_libm.h")]
-    newest = max(os.path.getmtime(f) for f in [src] + hdrs)
+    newest = max(os.path.getmtime(f) for f in srcs + hdrs)
     if (not os.path.exists(so)) or os.path.getmtime(so) < newest:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so

@@ -176,3 +176,130 @@ def test_gpu_wind_stats_rejects_bad_groups(engine):
         engine.wind_stats(ua, va, 0, 1, np.array([0, 4, 4, 8], np.int32))      # empty day
     with pytest.raises(TcrError):
         engine.wind_stats(ua, va, 0, 1, np.array([0, 4, 7], np.int32))         # does not end at n_time
+
+
+# ================================================================================================
+# Thermodynamics (thermo/thermo.py, thermo/calc_thermo.py): the C oracle is pinned against golden
+# vectors produced by the UNMODIFIED reference (oracle/make_golden_thermo.py); the CUDA kernel must
+# match the oracle bit for bit and the reference to 1e-9.
+# ================================================================================================
+def _thermo_golden():
+    from conftest import golden
+    g, t = golden("ref_thermo.npz"), golden("entropy_table.npz")
+    return g, (t["p"], t["s"], t["T"])
+
+
+def _assert_close_to_reference(got, want, rtol, atol, what):
+    assert np.array_equal(np.isnan(got), np.isnan(want)), what
+    ok = ~np.isnan(want)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=rtol, atol=atol, err_msg=what)
+
+
+def test_thermo_oracle_matches_reference_golden():
+    """2048 synthetic ERA5-shaped soundings incl. land (sst = 0 K), dry, super-saturated, isothermal and
+    NaN-level columns: identical NaN pattern, PI within 1e-11 relative of the live reference."""
+    g, table = _thermo_golden()
+    assert int(np.frombuffer(table[2].tobytes(), dtype=np.uint32).sum() & 0xffffffff) == int(g["table_crc"])
+    v, c, r = po.thermo(g["p"], g["ta"], g["hus"], g["sst"], g["psl"], table, float(g["cecd"]), int(g["k_mid"]))
+    _assert_close_to_reference(v, g["vmax"], 1e-11, 1e-11, "vmax")
+    _assert_close_to_reference(c, g["chi"], 1e-10, 1e-12, "chi")
+    _assert_close_to_reference(r, g["rh_mid"], 1e-13, 0, "rh_mid")
+    assert (g["vmax"] > 30).sum() > 500 and (g["vmax"] == 0).sum() > 50           # both regimes are covered
+
+
+def test_thermo_oracle_against_live_reference_if_present():
+    """Fresh soundings through the reference itself when /root/reference exists (build container only)."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not present")
+    import warnings
+    from tropical_cyclone_risk_b200 import synth_thermo
+    ref = rh.load_reference()
+    _, table = _thermo_golden()
+    p, ta, hus, sst, psl = synth_thermo.soundings(512, seed=99)
+    shp = (16, 32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = ref.thermo.CAPE_PI_vectorized(sst.reshape(shp), psl.reshape(shp), p.copy(),
+                                             ta.astype(np.float64).reshape((-1,) + shp), hus.astype(np.float64).reshape((-1,) + shp))
+    v, _, _ = po.thermo(p, ta, hus, sst, psl, table, ref.namelist.Ck / ref.namelist.Cd, 13)
+    _assert_close_to_reference(v, want.reshape(-1), 1e-11, 1e-11, "vmax")
+
+
+def test_order_levels():
+    from tropical_cyclone_risk_b200 import preproc
+    ta = np.arange(2 * 3 * 2 * 2, dtype=np.float32).reshape(2, 3, 2, 2)
+    p_env, k_mid, ta2, _ = preproc.order_levels([250, 600, 1000], "hPa", ta, ta, 60000.0)
+    assert np.array_equal(p_env, [100000.0, 60000.0, 25000.0]) and k_mid == 1
+    assert np.array_equal(ta2[:, 0], ta[:, 2])
+    p_env, k_mid, ta2, _ = preproc.order_levels([100000, 85000, 60000], "Pa", ta, ta, 60000.0)
+    assert k_mid == 2 and ta2 is not None and np.array_equal(ta2, ta)
+
+
+@pytest.mark.gpu
+def test_gpu_thermo_bit_exact_vs_oracle_and_close_to_reference(engine):
+    g, table = _thermo_golden()
+    engine.set_entropy_table(*table)
+    got = engine.thermo_month(g["p"], g["ta"], g["hus"], g["sst"], g["psl"], float(g["cecd"]), int(g["k_mid"]))
+    want = po.thermo(g["p"], g["ta"], g["hus"], g["sst"], g["psl"], table, float(g["cecd"]), int(g["k_mid"]))
+    for name, a, b in zip(("vmax", "chi", "rh_mid"), got, want):
+        assert np.array_equal(a, b, equal_nan=True), name
+    _assert_close_to_reference(got[0], g["vmax"], 1e-9, 1e-9, "vmax vs reference")
+    _assert_close_to_reference(got[1], g["chi"], 1e-9, 1e-12, "chi vs reference")
+    _assert_close_to_reference(got[2], g["rh_mid"], 1e-12, 0, "rh_mid vs reference")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nlev_cut", [(1, 0), (129, 0), (5000, 6), (40000, 0)])
+def test_gpu_thermo_other_shapes(engine, n, nlev_cut):
+    """Ragged column counts, fewer levels (the top ones dropped), fresh soundings."""
+    from tropical_cyclone_risk_b200 import synth_thermo
+    _, table = _thermo_golden()
+    engine.set_entropy_table(*table)
+    p, ta, hus, sst, psl = synth_thermo.soundings(n, seed=n, edge_cases=n >= 64)
+    if nlev_cut:
+        p, ta, hus = p[:-nlev_cut], ta[:-nlev_cut], hus[:-nlev_cut]
+    got = engine.thermo_month(p, ta, hus, sst, psl, 0.9, 11)
+    want = po.thermo(p, ta, hus, sst, psl, table, 0.9, 11)
+    for name, a, b in zip(("vmax", "chi", "rh_mid"), got, want):
+        assert np.array_equal(a, b, equal_nan=True), name
+
+
+@pytest.mark.gpu
+def test_gpu_compute_thermo_mirror(engine):
+    """compute_thermo through the reference-shaped host function: ascending hPa levels (flipped like
+    calc_thermo.py:50-55), Celsius SST on its own coarser grid, two time samples."""
+    from tropical_cyclone_risk_b200 import fields, preproc, synth_thermo
+    from tropical_cyclone_risk_b200 import namelist as nl
+    _, table = _thermo_golden()
+    engine.set_entropy_table(*table)
+    nlat, nlon = 12, 20
+    p, ta, hus, sst, psl = synth_thermo.soundings(2 * nlat * nlon, seed=5, edge_cases=False)
+    ta = ta.reshape(-1, 2, nlat, nlon).transpose(1, 0, 2, 3)
+    hus = hus.reshape(-1, 2, nlat, nlon).transpose(1, 0, 2, 3)
+    psl = psl.reshape(2, nlat, nlon)
+    lat, lon = np.linspace(-30, 30, nlat), np.linspace(100, 160, nlon)
+    slat, slon = np.linspace(-32, 32, 9), np.linspace(98, 162, 14)
+    sst_c = (28.0 - 0.01 * slat[:, None] ** 2 + 0.02 * slon[None, :]).astype(np.float32)[None].repeat(2, 0)
+    sst_c[0, 0, 0] = np.nan
+    levels = (p / 100.0)[::-1]
+    got = preproc.compute_thermo(engine, sst_c, psl, ta[:, ::-1], hus[:, ::-1], levels, nl, "hPa", "degC", slon, slat, lon, lat)
+    for i in range(2):
+        s = fields.regrid(slon, slat, np.nan_to_num(sst_c[i].astype(np.float64)), lon, lat) + 273.15
+        want = po.thermo(p, ta[i], hus[i], s, psl[i], table, nl.Ck / nl.Cd, 13)
+        for a, b in zip(got, want):
+            assert np.array_equal(a[i].reshape(-1), b, equal_nan=True)
+    assert got[0].shape == (2, nlat, nlon) and (got[0] > 0).any()
+
+
+@pytest.mark.gpu
+def test_gpu_thermo_rejects_bad_input(engine):
+    from tropical_cyclone_risk_b200._lib import TcrError
+    from tropical_cyclone_risk_b200 import synth_thermo
+    _, table = _thermo_golden()
+    engine.set_entropy_table(*table)
+    p, ta, hus, sst, psl = synth_thermo.soundings(64, seed=1)
+    with pytest.raises(TcrError):
+        engine.thermo_month(p[::-1], ta, hus, sst, psl, 1.0, 13)             # top level first
+    with pytest.raises(TcrError):
+        engine.thermo_month(p, ta, hus, sst, psl, 1.0, 99)

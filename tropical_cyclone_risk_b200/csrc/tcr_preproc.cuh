@@ -262,3 +262,277 @@ __global__ void __launch_bounds__(128 * KSPLIT) k_wind_stats(const WindStatArgs 
     __syncthreads();
     ws_moments<double, P, NT>(ws_dm, sx, A.n_groups, cta0, A.n_pts, A.out);
 }
+
+/* ======================================================================================== */
+/* k_thermo: potential intensity, saturation deficit and mid-level relative humidity of every   */
+/* grid column -- one time sample of compute_thermo (thermo/calc_thermo.py:60-69):              */
+/*   vmax   = thermo.CAPE_PI_vectorized(sst, psl, p_env, ta, hus)          thermo.py:266-412    */
+/*   chi    = clip(thermo.sat_deficit(sst, psl, T_mid, p_mid, q_mid), 0, 10) thermo.py:92-104   */
+/*   rh_mid = thermo.conv_q_to_rh(T_mid, q_mid, p_mid)                     thermo.py:42-47      */
+/* for the namelist defaults select_thermo = 1 (pseudoadiabatic), select_interp = 2 (entropy     */
+/* look-up table through RectBivariateSpline(kx=1, ky=1).ev, i.e. FITPACK clamped bilinear).     */
+/* ======================================================================================== */
+/* The reference builds seven (level, lat, lon) profile arrays and then scans them for the levels
+ * of neutral buoyancy.  Here one thread owns one column and walks its levels ONCE, bottom up:
+ * the parcel profiles exist only as the current level's scalars; "the last level where the parcel is
+ * at least as dense-warm as the environment" (thermo.py:361-362) is tracked by snapshotting, at every
+ * level that qualifies, the running CAPE sum and the two temperatures the outflow interpolation
+ * (thermo.py:372-396) needs, and completing the snapshot with the next level's values one iteration
+ * later.  Everything that depends on the level only (log-pressure increments, the dry-adiabat factor,
+ * the pressure-axis cell and weights of the look-up table) is computed once by k_thermo_levels and read
+ * from shared memory; the entropy-axis cell of each parcel is located once per column.  Loads of
+ * ta / hus are coalesced across the warp's 32 columns (one 128-byte line per level and variable):
+ * 8 B per (level, column) + 16 B per column read, 24 B per column written.  The kernel is bound by the
+ * float64 pipe (two exp, ~8 divisions per level), not by HBM.                                       */
+#define TH_RD 287.04                      /* util/constants.py:10-13, 17-18 */
+#define TH_RV 461.5
+#define TH_CP (718 + 287.04)
+#define TH_EPS (TH_RD / TH_RV)
+#define TH_L0 2.555e6
+#define TH_TTRIP 273.16
+#define TH_MAX_LEVELS 64
+
+struct ThLevel {            /* per pressure level, column independent */
+    double p;               /* Pa                                                        */
+    double mdlnp;           /* -dlnp[k]                    (thermo.py:302-303, 401-404)  */
+    double dry;             /* (p / p_ns)^(Rd/cp)          (thermo.py:328)               */
+    double wp0, wp1;        /* table weights on the pressure axis                        */
+    int ip, pad;            /* table cell on the pressure axis                           */
+};
+
+struct ThermoArgs {
+    int64_t n_pts;
+    int nlev, k_mid;
+    const float* ta; const float* hus;        /* [nlev][n_pts], lowest model level first  */
+    const double* sst; const double* psl;     /* [n_pts]                                  */
+    const double* p_env;                      /* [nlev] Pa                                */
+    ThLevel* lev;                             /* [nlev]                                   */
+    int np, ns;
+    const double* p_look; const double* s_look; const double* T_look;    /* entropy table [np][ns] */
+    double cecd, p_mid;
+    double* vmax; double* chi; double* rh_mid;
+};
+
+/* FITPACK fpbisp interval + degree-1 fpbspl weights with the argument clamped to the axis */
+__device__ __forceinline__ void th_locate(const double* __restrict__ ax, int n, double arg, int& i0, double& w0, double& w1)
+{
+    double a = arg;
+    if (a < __ldg(ax)) a = __ldg(ax);
+    if (a > __ldg(ax + n - 1)) a = __ldg(ax + n - 1);
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(ax + mid) <= a) lo = mid; else hi = mid;
+    }
+    if (lo > n - 2) lo = n - 2;
+    const double x0 = __ldg(ax + lo), x1 = __ldg(ax + lo + 1);
+    const double f = 1.0 / (x1 - x0);
+    i0 = lo;
+    w0 = f * (x1 - a);
+    w1 = f * (a - x0);
+}
+
+__global__ void k_thermo_levels(const ThermoArgs A)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.nlev) return;
+    const double p = A.p_env[k];
+    const double lnp = tcr_log(p);
+    double dlnp;
+    if (k + 1 < A.nlev) dlnp = tcr_log(A.p_env[k + 1]) - lnp;
+    else dlnp = (2 * lnp - tcr_log(A.p_env[k - 1])) - lnp;          /* np.diff(lnp, append = 2 lnp[-1] - lnp[-2]) */
+    ThLevel L;
+    L.p = p;
+    L.mdlnp = -dlnp;
+    L.dry = tcr_pow(p / A.p_env[0], TH_RD / TH_CP);
+    th_locate(A.p_look, A.np, p, L.ip, L.wp0, L.wp1);
+    L.pad = 0;
+    A.lev[k] = L;
+}
+
+__device__ __forceinline__ double th_fmax(double a, double b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }   /* np.maximum */
+__device__ __forceinline__ double th_fmin(double a, double b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }   /* np.minimum */
+
+/* sat_thermo (thermo.py:29-39): Bolton; a NaN temperature gives es = 0 */
+__device__ __forceinline__ void th_sat(double T, double p, double& es, double& rs)
+{
+    double e = 0.0;
+    if (T == T) {
+        const double Tc = T - 273;
+        double x = (17.625 * Tc) / (Tc + 243.04);
+        if (!(x <= 10)) x = (x != x) ? x : 10;
+        e = 610.94 * tcr_exp(x);
+    }
+    es = e;
+    rs = TH_RD / TH_RV * e / (p - e);
+}
+
+__device__ __forceinline__ double th_t_rho(double T, double rv) { return T * (1 + rv / TH_EPS) / (1 + rv); }
+
+__device__ __forceinline__ double th_s_unsat(double T, double p, double r)
+{
+    double es, rs;
+    th_sat(T, p, es, rs);
+    const double rh = th_fmax(r / rs * (1 + rs / TH_EPS) / (1 + r / TH_EPS), 0);
+    return TH_CP * tcr_log(T) - TH_RD * tcr_log(p - es * rh) + TH_L0 * r / T - r * TH_RV * tcr_log(rh);
+}
+
+__device__ __forceinline__ double th_s_sat(double T, double p)
+{
+    double es, rs;
+    th_sat(T, p, es, rs);
+    T = th_fmax(T, 1e-4);
+    return TH_CP * tcr_log(T) - TH_RD * tcr_log(th_fmax(p - es, 1e-4)) + TH_L0 * rs / T;
+}
+
+/* real branch -1 of the Lambert W function on [-1/e, 0): scipy.special.lambertw(z, -1) as get_LCL uses it
+ * (thermo.py:124): first guess log(-z), Halley steps to the routine's default tolerance 1e-8 */
+__device__ __forceinline__ double th_lambertw_m1(double z)
+{
+    if (z != z) return NAN;
+    if (z == 0.0) return -INFINITY;
+    if (!(z < 0.0) || z < -0.36787944117144233) return NAN;
+    double w = tcr_log(-z);
+    for (int i = 0; i < 100; ++i) {
+        const double ew = tcr_exp(w);
+        const double wew = w * ew;
+        const double wewz = wew - z;
+        const double wn = w - wewz / (wew + ew - (w + 2) * wewz / (2 * w + 2));
+        if (fabs(wn - w) <= 1e-8 * fabs(wn)) return wn;
+        w = wn;
+    }
+    return NAN;
+}
+
+/* one parcel's bookkeeping of "the last level with T_rho_parcel >= T_rho_env" */
+struct ThParcel {
+    int out;                 /* that level, -1: none so far              */
+    double cape, cape_at;    /* running sum; its value at level `out`    */
+    double dT1, dT2, Te1, Te2;
+    __device__ __forceinline__ void init() { out = -1; cape = cape_at = 0.0; dT1 = dT2 = Te1 = Te2 = 0.0; }
+    __device__ __forceinline__ void level(int k, double Trp, double Tre, double Te, double mdlnp)
+    {
+        const double dT = Trp - Tre;
+        if (out == k - 1 && k > 0) { dT2 = dT; Te2 = Te; }             /* completes the snapshot of level k-1 */
+        cape += TH_RD * dT * mdlnp;
+        if (Trp >= Tre) { out = k; dT1 = dT; Te1 = Te; cape_at = cape; }
+    }
+};
+
+__global__ void __launch_bounds__(128) k_thermo(const ThermoArgs A)
+{
+    __shared__ ThLevel lev[TH_MAX_LEVELS];
+    for (int i = threadIdx.x; i < A.nlev * (int)(sizeof(ThLevel) / 8); i += blockDim.x)
+        reinterpret_cast<double*>(lev)[i] = reinterpret_cast<const double*>(A.lev)[i];
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= A.n_pts) return;
+    const int nlev = A.nlev, ns = A.ns;
+    const double sst = A.sst[c], p_surf = A.psl[c];
+    const double T_ns = (double)__ldcs(A.ta + c), r_ns = (double)__ldcs(A.hus + c), p_ns = lev[0].p;
+
+    double ess, rs;
+    th_sat(sst, p_surf, ess, rs);                                                       /* thermo.py:293 */
+    const double rh = r_ns / rs * (1 + rs / TH_EPS) / (1 + r_ns / TH_EPS);              /* :295 */
+    const double s_ns = th_s_unsat(T_ns, p_ns, r_ns);                                   /* :298 */
+    const double ss = th_s_sat(sst, p_surf);                                            /* :300 */
+    /* get_LCL (thermo.py:107-127) */
+    double pLCL;
+    {
+        const double E0v = 2.3740e6, cvv = 1418, cvl = 4119, cpv = cvv + TH_RV;
+        const double q = r_ns / (1 + r_ns);
+        const double Rm = (1 - q) * TH_RD + q * TH_RV;
+        const double cpm = (1 - q) * TH_CP + q * cpv;
+        const double a = cpm / Rm + (cvl - cpv) / TH_RV;
+        const double b = -(E0v - (cvv - cvl) * TH_TTRIP) / (TH_RV * T_ns);
+        const double cc = b / a;
+        const double T_lcl = cc * T_ns / th_lambertw_m1(tcr_pow(rh, 1 / a) * cc * tcr_exp(cc));
+        pLCL = p_ns * tcr_pow(T_lcl / T_ns, cpm / Rm);
+    }
+    /* entropy-axis cells of the two parcels */
+    int is_a, is_s;
+    double wa0, wa1, wsa0, wsa1;
+    th_locate(A.s_look, ns, s_ns, is_a, wa0, wa1);
+    th_locate(A.s_look, ns, ss, is_s, wsa0, wsa1);
+
+    ThParcel pa, ps;
+    pa.init(); ps.init();
+    bool cond = false;                         /* at or above the first level with pLCL > p (the last level counts, :322) */
+    double Tm = 0.0, qm = 0.0;
+    float t_next = __ldcs(A.ta + c), q_next = __ldcs(A.hus + c);
+    for (int k = 0; k < nlev; ++k) {
+        const float t_cur = t_next, q_cur = q_next;
+        if (k + 1 < nlev) {                                                              /* next level's line in flight during this level's arithmetic */
+            t_next = __ldcs(A.ta + (size_t)(k + 1) * A.n_pts + c);
+            q_next = __ldcs(A.hus + (size_t)(k + 1) * A.n_pts + c);
+        }
+        const ThLevel& L = lev[k];
+        const double Te = (double)t_cur, re = (double)q_cur;
+        if (k == A.k_mid) { Tm = Te; qm = re; }
+        const double Tre = th_t_rho(Te, re);                                             /* :304 */
+        cond = cond || (pLCL > L.p) || (k == nlev - 1);
+        const double* t0 = A.T_look + (size_t)L.ip * ns;
+        double Ta, ra;
+        if (cond) {                                                                      /* :333-340: moist adiabat from the table */
+            const double* r0 = t0 + is_a;
+            const double* r1 = r0 + ns;
+            double sp = 0.0;
+            sp = sp + __ldg(r0) * L.wp0 * wa0;
+            sp = sp + __ldg(r0 + 1) * L.wp0 * wa1;
+            sp = sp + __ldg(r1) * L.wp1 * wa0;
+            sp = sp + __ldg(r1 + 1) * L.wp1 * wa1;
+            Ta = sp;
+            double es_;
+            th_sat(Ta, L.p, es_, ra);
+        } else {                                                                         /* :328-330: dry adiabat, constant mixing ratio */
+            Ta = T_ns * L.dry;
+            ra = r_ns;
+        }
+        double Ts, rsp;
+        {
+            const double* r0 = t0 + is_s;                                                /* :342 */
+            const double* r1 = r0 + ns;
+            double sp = 0.0;
+            sp = sp + __ldg(r0) * L.wp0 * wsa0;
+            sp = sp + __ldg(r0 + 1) * L.wp0 * wsa1;
+            sp = sp + __ldg(r1) * L.wp1 * wsa0;
+            sp = sp + __ldg(r1 + 1) * L.wp1 * wsa1;
+            Ts = sp;
+            double es_;
+            th_sat(Ts, L.p, es_, rsp);                                                   /* :355 */
+        }
+        pa.level(k, th_t_rho(Ta, ra), Tre, Te, L.mdlnp);                                 /* :357, 361, 401-402 */
+        ps.level(k, th_t_rho(Ts, rsp), Tre, Te, L.mdlnp);                                /* :358, 362, 403-404 */
+    }
+    /* outflow level by linear interpolation between `out` and the level above it (:372-396) */
+    double T_out_s = NAN, add_a = 0.0, add_s = 0.0;
+    if (ps.out >= 0 && ps.out < nlev - 1) {
+        const double p1 = lev[ps.out].p, p2 = lev[ps.out + 1].p;
+        const double p_out = (p1 * ps.dT2 - p2 * ps.dT1) / (ps.dT2 - ps.dT1);
+        T_out_s = (ps.Te1 * (p_out - p2) + ps.Te2 * (p1 - p_out)) / (p1 - p2);
+        add_s = TH_RD * ps.dT1 * (p1 - p_out) / (p1 + p_out);
+    }
+    if (pa.out >= 0 && pa.out < nlev - 1) {
+        const double p1 = lev[pa.out].p, p2 = lev[pa.out + 1].p;
+        const double p_out = (p1 * pa.dT2 - p2 * pa.dT1) / (pa.dT2 - pa.dT1);
+        add_a = TH_RD * pa.dT1 * (p1 - p_out) / (p1 + p_out);
+    }
+    double cape = (pa.out >= 0 ? pa.cape_at : pa.cape) + add_a;                           /* none qualifies: argmax of all-False = 0 -> the top level */
+    const double capes = (ps.out >= 0 ? ps.cape_at : ps.cape) + add_s;
+    cape = th_fmax(cape, 0);                                                             /* :408-409 */
+    if (cape != cape) cape = 0;
+    const double cape_diff = capes - cape;
+    double pi = sqrt(th_fmax(A.cecd * (sst / T_out_s) * cape_diff, 0));                  /* :411 */
+    if (pi != pi) pi = 0;                                                                /* :412 */
+    __stcs(A.vmax + c, pi);
+
+    /* sat_deficit (thermo.py:92-104) clipped to [0, 10] (calc_thermo.py:68); conv_q_to_rh (thermo.py:42-47) */
+    const double sp_ = th_s_unsat(Tm, A.p_mid, qm);
+    const double sps = th_s_sat(Tm, A.p_mid);
+    const double spss = ss;                                                              /* s_sat(sst, psl): the same call as :300 */
+    __stcs(A.chi + c, th_fmin(th_fmax((sps - sp_) / (spss - sps), 0), 10));
+    double es, rsm;
+    th_sat(Tm, A.p_mid, es, rsm);
+    const double qs = rsm / (1 + rsm);
+    __stcs(A.rh_mid + c, th_fmin(th_fmax(qm / qs, 1e-5), 1));
+}

@@ -118,6 +118,8 @@ struct tcr_handle {
     DevBuf sincos;               /* [n_steps][15] double2, storm-independent harmonics */
     /* static */
     DevBuf bathy, land, masks;
+    DevBuf etab;                 /* entropy look-up table of the thermo kernel: p_look | s_look | T_lookup */
+    int etab_np = 0, etab_ns = 0;
     AxisBuf ax_lon_b, ax_lat_b, ax_lon_l, ax_lat_l, ax_lon_m, ax_lat_m;
     bool have_static = false, have_masks = false;
     /* tuning */
@@ -1284,5 +1286,79 @@ int tcr_wind_stats(tcr_handle* h, int n_time, int64_t n_pts, int64_t t_stride,
     return 0;
 }
 
+/* ---- potential intensity / saturation deficit / mid-level humidity (thermo/) ------ */
+int tcr_set_entropy_table(tcr_handle* h, int np, int ns, const double* p_look, const double* s_look, const double* T_lookup)
+{
+    if (!h) return set_err("null handle");
+    if (np < 2 || ns < 2 || !p_look || !s_look || !T_lookup) return set_err("tcr_set_entropy_table: bad argument");
+    for (int i = 1; i < np; ++i) if (!(p_look[i] > p_look[i - 1])) return set_err("tcr_set_entropy_table: pressure axis must ascend");
+    for (int i = 1; i < ns; ++i) if (!(s_look[i] > s_look[i - 1])) return set_err("tcr_set_entropy_table: entropy axis must ascend");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)np + ns + (size_t)np * ns;
+    if (h->etab.ensure(n * sizeof(double))) return -1;
+    double* d = h->etab.as<double>();
+    CK(cudaMemcpyAsync(d, p_look, (size_t)np * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + np, s_look, (size_t)ns * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + np + ns, T_lookup, (size_t)np * ns * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->etab_np = np; h->etab_ns = ns;
+    return 0;
+}
+
+int tcr_thermo_month(tcr_handle* h, int64_t n_pts, int nlev, const double* p_env, const float* ta, const float* hus,
+                     const double* sst, const double* psl, double ck_over_cd, int k_mid,
+                     double* vmax, double* chi, double* rh_mid, int on_device)
+{
+    if (!h) return set_err("null handle");
+    if (!h->etab.p) return set_err("tcr_thermo_month: call tcr_set_entropy_table first");
+    if (n_pts <= 0 || nlev < 2 || nlev > TH_MAX_LEVELS || k_mid < 0 || k_mid >= nlev) return set_err("tcr_thermo_month: bad shape (2..%d levels)", TH_MAX_LEVELS);
+    if (!p_env || !ta || !hus || !sst || !psl || !vmax || !chi || !rh_mid) return set_err("tcr_thermo_month: null argument");
+    for (int k = 1; k < nlev; ++k)
+        if (!(p_env[k] < p_env[k - 1])) return set_err("tcr_thermo_month: levels must run from the lowest model level (highest pressure) upwards");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    DevBuf lv, in, o;
+    const size_t b_lv = (size_t)nlev * (sizeof(ThLevel) + 8);
+    if (lv.ensure(b_lv)) return -1;
+    double* d_p = reinterpret_cast<double*>(lv.as<char>() + (size_t)nlev * sizeof(ThLevel));
+    CK(cudaMemcpyAsync(d_p, p_env, (size_t)nlev * 8, cudaMemcpyHostToDevice, s));
+    ThermoArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_pts = n_pts; a.nlev = nlev; a.k_mid = k_mid; a.p_env = d_p; a.lev = lv.as<ThLevel>();
+    a.np = h->etab_np; a.ns = h->etab_ns;
+    a.p_look = h->etab.as<double>(); a.s_look = a.p_look + a.np; a.T_look = a.s_look + a.ns;
+    a.cecd = ck_over_cd; a.p_mid = p_env[k_mid];
+    if (on_device) {
+        a.ta = ta; a.hus = hus; a.sst = sst; a.psl = psl; a.vmax = vmax; a.chi = chi; a.rh_mid = rh_mid;
+    } else {
+        const size_t col = (size_t)nlev * n_pts * sizeof(float);
+        if (in.ensure(2 * col + (size_t)n_pts * 16) || o.ensure((size_t)n_pts * 24)) { lv.release(); in.release(); o.release(); return -1; }
+        char* b = in.as<char>();
+        CK(cudaMemcpyAsync(b + 2 * col, sst, (size_t)n_pts * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b + 2 * col + (size_t)n_pts * 8, psl, (size_t)n_pts * 8, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b, ta, col, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b + col, hus, col, cudaMemcpyHostToDevice, s));
+        a.ta = reinterpret_cast<float*>(b); a.hus = reinterpret_cast<float*>(b + col);
+        a.sst = reinterpret_cast<double*>(b + 2 * col); a.psl = a.sst + n_pts;
+        a.vmax = o.as<double>(); a.chi = a.vmax + n_pts; a.rh_mid = a.chi + n_pts;
+    }
+    {
+        LaunchTimer lt_(h, TCR_K_THERMO);
+        k_thermo_levels<<<1, TH_MAX_LEVELS, 0, s>>>(a);
+        k_thermo<<<(unsigned)((n_pts + 127) / 128), 128, 0, s>>>(a);
+    }
+    CKK(h);
+    h->launches++;
+    if (!on_device) {
+        CK(cudaMemcpyAsync(vmax, a.vmax, (size_t)n_pts * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(chi, a.chi, (size_t)n_pts * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(rh_mid, a.rh_mid, (size_t)n_pts * 8, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    lv.release(); in.release(); o.release();
+    return 0;
+}
+
 }  // extern "C"
+
 

@@ -279,6 +279,33 @@ class Engine:
         _lib.check(self.lib.tcr_wind_stats(self._h, int(n_time), int(n_pts), int(t_stride), vp(d_series[0]), vp(d_series[1]),
                                            vp(d_series[2]), vp(d_series[3]), gs.size - 1, _ptr(gs), vp(d_out), 1))
 
+    def set_entropy_table(self, p_look, s_look, T_lookup):
+        """The entropy inversion table of thermo/entropy_table.npz (thermo.py:274-278)."""
+        p_look, s_look, T_lookup = (_arr(a, np.float64) for a in (p_look, s_look, T_lookup))
+        if T_lookup.shape != (p_look.size, s_look.size):
+            raise ValueError("T_lookup must be [len(p), len(s)]")
+        _lib.check(self.lib.tcr_set_entropy_table(self._h, p_look.size, s_look.size, _ptr(p_look), _ptr(s_look), _ptr(T_lookup)))
+
+    def thermo_month(self, p_env, ta, hus, sst, psl, ck_over_cd, k_mid):
+        """vmax, chi, rh_mid of one time sample (thermo/calc_thermo.py:60-69); ta, hus [nlev, ...grid] float32,
+        lowest model level first; returns three float64 arrays shaped like sst."""
+        p_env = _arr(p_env, np.float64)
+        ta, hus = _arr(ta, np.float32), _arr(hus, np.float32)
+        sst, psl = _arr(sst, np.float64), _arr(psl, np.float64)
+        n = sst.size
+        if ta.shape[0] != p_env.size or ta.size != p_env.size * n or hus.shape != ta.shape or psl.size != n:
+            raise ValueError("inconsistent shapes")
+        out = [np.empty(sst.shape) for _ in range(3)]
+        _lib.check(self.lib.tcr_thermo_month(self._h, n, p_env.size, _ptr(p_env), _ptr(ta), _ptr(hus), _ptr(sst), _ptr(psl),
+                                             float(ck_over_cd), int(k_mid), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), 0))
+        return tuple(out)
+
+    def thermo_month_dev(self, n_pts, p_env, d_ta, d_hus, d_sst, d_psl, ck_over_cd, k_mid, d_vmax, d_chi, d_rh):
+        p_env = _arr(p_env, np.float64)
+        vp = C.c_void_p
+        _lib.check(self.lib.tcr_thermo_month(self._h, int(n_pts), p_env.size, _ptr(p_env), vp(d_ta), vp(d_hus), vp(d_sst), vp(d_psl),
+                                             float(ck_over_cd), int(k_mid), vp(d_vmax), vp(d_chi), vp(d_rh), 1))
+
     def poi_vmax(self, lon, lat, vmax, poi_lon, poi_lat, radius_km=100.0, r_earth_m=6378000.0):
         """Per-track maximum of vmax while within radius_km of (poi_lon, poi_lat); NaN if never."""
         lon, lat, vmax = (_arr(x, np.float64) for x in (lon, lat, vmax))

@@ -32,9 +32,12 @@ total_track_time_days = 15
 tracks_per_year = 20
 
 # --- thermodynamic scaling (reference namelist.py:55-60) --------------------
+p_midlevel = 60000                    # Pa, mid-level of the saturation deficit
 PI_reduc = 0.80
 Ck = 1.2e-3
 Cd = 1.2e-3
+select_thermo = 1                     # 1 pseudoadiabatic (the only mode the device kernel implements)
+select_interp = 2                     # 2 entropy look-up table (ditto)
 
 # --- track / intensity constants (reference namelist.py:70-94) --------------
 steering_levels = [250, 850]

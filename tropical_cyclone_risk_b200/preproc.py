@@ -86,3 +86,52 @@ def calc_wnd_stat(engine, ua, va, times, levels, dt, level_units="hPa", group_su
     t0, t1 = int(idx[0]), int(idx[-1]) + 1
     out = engine.wind_stats(ua[t0:t1], va[t0:t1], iu, il, group_start)
     return out.reshape((14,) + ua.shape[2:])
+
+
+# ---------------------------------------------------------------------------------------------
+# thermodynamics: thermo/calc_thermo.py:24-72 (compute_thermo) on the device
+# ---------------------------------------------------------------------------------------------
+def load_entropy_table(path):
+    """thermo/entropy_table.npz of a reference checkout (thermo.py:274-278): (p_look, s_look, T_lookup)."""
+    with np.load(path) as t:
+        return np.array(t["p"], dtype=np.float64), np.array(t["s"], dtype=np.float64), np.array(t["T"], dtype=np.float64)
+
+
+def order_levels(levels, level_units, ta, hus, p_midlevel_pa):
+    """calc_thermo.py:50-59: lowest model level first, pressures in Pa, index of the level nearest p_midlevel.
+    ta, hus are (level, lat, lon) or (time, level, lat, lon); the level axis is flipped as a view."""
+    lvl = np.array(levels, dtype=np.float64)
+    axis = ta.ndim - 3
+    if lvl[0] - lvl[1] < 0:                                            # calc_thermo.py:51
+        lvl = lvl[::-1]
+        ta, hus = np.flip(ta, axis=axis), np.flip(hus, axis=axis)
+    p_env = lvl * 100.0 if level_units in ("millibars", "hPa") else lvl.copy()
+    k_mid = int(np.argmin(np.abs(p_env - p_midlevel_pa)))              # .sel(method='nearest')
+    return p_env, k_mid, ta, hus
+
+
+def compute_thermo(engine, sst, psl, ta, hus, levels, namelist, level_units="hPa", sst_units="K",
+                   sst_lon=None, sst_lat=None, lon=None, lat=None):
+    """compute_thermo (thermo/calc_thermo.py:24-72) for every time sample.
+
+    sst (time, lat_s, lon_s), psl (time, lat, lon), ta / hus (time, level, lat, lon).  When the SST grid
+    differs from the atmospheric grid pass both axis pairs: the SST is regridded like
+    mat.interp_2d_grid(nan_to_num(sst)) (calc_thermo.py:38-40).  Returns (vmax, chi, rh_mid), each
+    (time, lat, lon) float64.  engine.set_entropy_table must have been called."""
+    from . import fields
+    if namelist.select_thermo != 1 or namelist.select_interp != 2:
+        raise NotImplementedError("the device kernel implements select_thermo = 1, select_interp = 2 (the namelist defaults)")
+    sst, psl = np.asarray(sst), np.asarray(psl)
+    p_env, k_mid, ta, hus = order_levels(levels, level_units, np.asarray(ta), np.asarray(hus), float(namelist.p_midlevel))
+    n_time = psl.shape[0]
+    out = [np.zeros(psl.shape) for _ in range(3)]                      # calc_thermo.py:33-35
+    for i in range(n_time):
+        s = np.nan_to_num(np.asarray(sst[i], dtype=np.float64))        # calc_thermo.py:39
+        if sst_lon is not None:
+            s = fields.regrid(sst_lon, sst_lat, s, lon, lat)
+        if "C" in sst_units:                                           # calc_thermo.py:41-42
+            s = s + 273.15
+        v, c, r = engine.thermo_month(p_env, ta[i], hus[i], s, psl[i], namelist.Ck / namelist.Cd, k_mid)
+        out[0][i], out[1][i], out[2][i] = v, c, r
+    return tuple(out)
+
