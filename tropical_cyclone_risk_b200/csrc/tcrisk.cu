@@ -1260,7 +1260,7 @@ int tcr_wind_stats(tcr_handle* h, int n_time, int64_t n_pts, int64_t t_stride,
     const int variant = ws_env ? atoi(ws_env) : -1;
     const bool single = n_groups == n_time;
     int rc;
-    switch (variant >= 0 ? variant : single ? 10 : 9) {
+    switch (variant >= 0 ? variant : single ? 11 : 9) {
     case 10: rc = launch_wind_stats_single<32, 64>(h, a); break;
     case 11: rc = launch_wind_stats_single<64, 128>(h, a); break;
     case 12: rc = launch_wind_stats_single<32, 128>(h, a); break;
