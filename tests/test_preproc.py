@@ -303,3 +303,71 @@ def test_gpu_thermo_rejects_bad_input(engine):
         engine.thermo_month(p[::-1], ta, hus, sst, psl, 1.0, 13)             # top level first
     with pytest.raises(TcrError):
         engine.thermo_month(p, ta, hus, sst, psl, 1.0, 99)
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-rank drivers: months / time samples sharded over ranks, one all-gather (gloo, world 2, CPU)
+# ------------------------------------------------------------------------------------------------
+class _OracleEngine:
+    """Stands in for the CUDA engine in the gloo test (no GPU here): same methods, oracle arithmetic."""
+
+    def wind_stats(self, ua, va, iu, il, gs):
+        return po.wind_stats(series_of(ua, va, iu, il), gs)
+
+    def thermo_month(self, p_env, ta, hus, sst, psl, cecd, k_mid):
+        _, table = _thermo_golden()
+        out = po.thermo(p_env, ta, hus, sst, psl, table, cecd, k_mid)
+        return tuple(o.reshape(np.shape(sst)) for o in out)
+
+
+def _driver_inputs():
+    from tropical_cyclone_risk_b200 import synth_thermo
+    t0 = datetime.datetime(2001, 1, 1)
+    times = [t0 + datetime.timedelta(hours=12 * k) for k in range(2 * 151)]         # Jan .. May, 2 x daily
+    ua, va = synth_winds(len(times), 2, 5, 8, seed=8)
+    months = [datetime.datetime(2001, m, 15) for m in range(1, 6)]
+    p, ta, hus, sst, psl = synth_thermo.soundings(3 * 4 * 6, seed=3, edge_cases=False)
+    ta = ta.reshape(-1, 3, 4, 6).transpose(1, 0, 2, 3)
+    hus = hus.reshape(-1, 3, 4, 6).transpose(1, 0, 2, 3)
+    return times, ua, va, months, p, ta, hus, sst.reshape(3, 4, 6), psl.reshape(3, 4, 6)
+
+
+def _run_drivers():
+    from tropical_cyclone_risk_b200 import preproc
+    from tropical_cyclone_risk_b200 import namelist as nl
+    times, ua, va, months, p, ta, hus, sst, psl = _driver_inputs()
+    eng = _OracleEngine()
+    w = preproc.gen_wind_mean_cov(eng, ua, va, times, [250, 850], months)
+    v, c, r = preproc.gen_thermo(eng, sst, psl, ta, hus, p / 100.0, nl)
+    return w, v, c, r
+
+
+def _driver_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        q.put((rank, _run_drivers()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_preproc_drivers_gloo_world2_match_single_rank():
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_driver_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = _run_drivers()
+    assert want[0].shape == (5, 14, 5, 8) and want[1].shape == (3, 4, 6)
+    for r in (0, 1):
+        for a, b in zip(got[r], want):
+            assert np.array_equal(a, b, equal_nan=True)

@@ -135,3 +135,76 @@ def compute_thermo(engine, sst, psl, ta, hus, levels, namelist, level_units="hPa
         out[0][i], out[1][i], out[2][i] = v, c, r
     return tuple(out)
 
+
+
+# ---------------------------------------------------------------------------------------------
+# drivers over the whole record: months / time samples shard over torch.distributed ranks the way the
+# reference spreads them over dask workers (env_wind.py:97-101, calc_thermo.py:88-93); no data-path
+# collective, one all-gather of the finished statistics.
+# ---------------------------------------------------------------------------------------------
+def shard_items(n, rank, world):
+    """Round-robin item indices of this rank."""
+    return list(range(rank, n, world))
+
+
+def gather_items(local, n, rank, world, device=None):
+    """local: float64 [len(shard_items(n, rank, world)), ...] -> [n, ...] in item order on every rank
+    (equal-sized slots, unused ones NaN; NCCL on GPUs, gloo on CPU)."""
+    local = np.ascontiguousarray(local, dtype=np.float64)
+    if world == 1:
+        return local
+    import torch
+    import torch.distributed as dist
+    n_slots = (n + world - 1) // world
+    item_shape = local.shape[1:]
+    block = np.full((n_slots,) + item_shape, np.nan)
+    block[:local.shape[0]] = local
+    t = torch.from_numpy(block.reshape(n_slots, -1))
+    if device is not None:
+        t = t.to(device, non_blocking=True)
+    g = torch.empty((world * n_slots, t.shape[1]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(g, t)
+    allb = g.cpu().numpy().reshape((world, n_slots) + item_shape)
+    return np.stack([allb[i % world, i // world] for i in range(n)])
+
+
+def _rank_world():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dev = None
+            if dist.get_backend() == "nccl":
+                import torch
+                dev = torch.device("cuda", torch.cuda.current_device())
+            return dist.get_rank(), dist.get_world_size(), dev
+    except ImportError:
+        pass
+    return 0, 1, None
+
+
+def gen_wind_mean_cov(engine, ua, va, times, levels, months, level_units="hPa", group_sub_daily=False):
+    """gen_wind_mean_cov / wnd_stat_wrapper (env_wind.py:84-166) over a list of months (datetimes): returns
+    wnd_stats [n_months, 14, lat, lon]; months are sharded over the ranks of torch.distributed."""
+    rank, world, dev = _rank_world()
+    mine = shard_items(len(months), rank, world)
+    shape = (14,) + tuple(np.shape(ua)[2:])
+    local = np.empty((len(mine),) + shape)
+    for k, i in enumerate(mine):
+        local[k] = calc_wnd_stat(engine, ua, va, times, levels, months[i], level_units, group_sub_daily)
+    return gather_items(local, len(months), rank, world, dev)
+
+
+def gen_thermo(engine, sst, psl, ta, hus, levels, namelist, **kw):
+    """gen_thermo (calc_thermo.py:74-117) without the file I/O: compute_thermo on this rank's time samples,
+    all-gathered; returns (vmax, chi, rh_mid), each (time, lat, lon)."""
+    rank, world, dev = _rank_world()
+    n = np.shape(psl)[0]
+    mine = shard_items(n, rank, world)
+    if mine:
+        loc = compute_thermo(engine, np.asarray(sst)[mine], np.asarray(psl)[mine], np.asarray(ta)[mine], np.asarray(hus)[mine],
+                             levels, namelist, **kw)
+        local = np.stack(loc, axis=1)                                   # [n_mine, 3, lat, lon]
+    else:
+        local = np.empty((0, 3) + tuple(np.shape(psl)[1:]))
+    g = gather_items(local, n, rank, world, dev)
+    return g[:, 0], g[:, 1], g[:, 2]
