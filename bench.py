@@ -45,7 +45,8 @@ B_PER_STEP_TRACK = 32      # lon, lat, v, m float64 written by the integrator pe
 B_PER_STORM_PICKUP = 1004  # 60 double2 Fourier coefficients + 5 doubles + 1 int per integrated seed
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
 # workload (profiles/r01_prof_integrate_summary.txt, profiles/r01_prof_interp_summary.txt); None for other workloads
-NCU_TRAFFIC = {"k_integrate": 2.082e9 + 1.820e9, "k_env_interp": 10.151e9 + 5.611e9}
+NCU_TRAFFIC = {"k_integrate": 2.062e9 + 1.820e9, "k_env_interp": 10.157e9 + 5.612e9,
+               "k_wind_stats": 1.030e9 + 0.111e9, "k_thermo": 0.2493e9 + 0.0078e9}
 
 
 def load_peaks():
@@ -416,9 +417,9 @@ def run_gpu_arm(args):
                 "note": "latency / fp64-issue bound kernel (SURVEY 8d): HBM fraction reported for honesty, "
                         "the HBM-roofline kernel is roofline_interp",
                 "ncu": {"source": "profiles/r01_prof_integrate_summary.txt (ncu --set full of one launch of this workload)",
-                        "fp64_pipe_pct_of_peak": 28.1, "issue_slots_busy_pct": 35.0, "lanes_per_instruction": 20.2,
-                        "l2_hit_pct": 82.9, "dram_pct_of_peak": 4.9, "registers": 168, "warps_per_sm": 12,
-                        "stalls": "fixed-latency fp64 chains 31 %, L2/L1 loads 25 %, CTA-lockstep barrier 10 %, instruction fetch 3 %"}}
+                        "fp64_pipe_pct_of_peak": 25.1, "issue_slots_busy_pct": 31.4, "lanes_per_instruction": 23.1,
+                        "l2_hit_pct": 83.4, "dram_pct_of_peak": 4.9, "registers": 168, "warps_per_sm": 12,
+                        "stalls": "fixed-latency fp64 chains 28 %, L2/L1 loads 24 %, CTA barriers (lockstep + drain packing) 18 %, instruction fetch 3 %"}}
         kernel_share = {k: v[0] / ms for k, v in ktimes.items() if v[1]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
@@ -556,7 +557,9 @@ def bench_windstats(eng, torch, dev, peak, peak_src, nlat=721, nlon=1440, n_days
         del ua, va
     head = res["2x_daily_ungrouped"]
     return {"kernel": "k_wind_stats", "bound": "hbm", "achieved": head["achieved"], "peak": peak, "unit": "GB/s",
-            "frac": head["frac"], "traffic": None, "peak_source": peak_src, "avg_launch_ms": head["avg_launch_ms"],
+            "frac": head["frac"], "traffic": NCU_TRAFFIC["k_wind_stats"] if (nlat, nlon, n_days) == (721, 1440, 31) else None,
+            "traffic_source": "profiles/r01_prof_windstats_summary.txt (ncu --set full, one launch of this workload)",
+            "peak_source": peak_src, "avg_launch_ms": head["avg_launch_ms"],
             "launches": head["launches"], "grid": "%d x %d (0.25 deg)" % (nlat, nlon), "cases": res,
             "note": "bytes = 16 B per (sample, grid point) read once + 14 x 8 B per grid point written",
             "l2": "inputs %d MB and %d MB, streamed (>> L2)" % (res["2x_daily_ungrouped"]["algorithmic_bytes"] / 2**20,
@@ -593,7 +596,10 @@ def bench_thermo(eng, torch, dev, peak, peak_src, nlat=721, nlon=1440, cpu=False
     moved = (8.0 * p.size + 16.0 + 24.0) * n_pts
     ach = moved / (ms / cnt * 1e-3) / 1e9
     res = {"kernel": "k_thermo", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-           "traffic": None, "peak_source": peak_src, "avg_launch_ms": ms / cnt, "launches": cnt,
+           "traffic": NCU_TRAFFIC["k_thermo"] if (nlat, nlon) == (721, 1440) else None,
+           "traffic_source": "profiles/r01_prof_thermo_summary.txt (ncu --set full, one launch of this workload; the 25 MB of results were still in L2 when the kernel ended)",
+           "ncu": {"fp64_pipe_pct_of_peak": 52.2, "issue_slots_busy_pct": 64.9, "dram_pct_of_peak": 3.7, "registers": 94},
+           "peak_source": peak_src, "avg_launch_ms": ms / cnt, "launches": cnt,
            "columns": n_pts, "levels": int(p.size), "columns_per_s": n_pts / (ms / cnt * 1e-3), "algorithmic_bytes": moved,
            "note": "fp64-pipe bound per-column kernel: 8 B per (level, column) + 16 B per column read, 24 B per column written",
            "check_vmax_mean": float(out[0].mean().item())}

@@ -58,18 +58,26 @@ def main():
             f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 3 --no-cpu --interp-queries 4194304\n")
             f.write("# per-launch times are cold-cache and serialised: compare SHARES with bench.py's kernel_share_of_step\n")
             f.write(launch_table(lc) + "\n")
-    for rep, args in (("prof_integrate", []), ("prof_interp", []), ("prof_others", None)):
+    for rep, args in (("prof_integrate", []), ("prof_interp", []), ("prof_windstats", []), ("prof_thermo", []), ("prof_others", None)):
         path = os.path.join(src, rep + ".ncu-rep")
-        if not os.path.exists(path):
+        pre_made = os.path.join(src, rep + "_summary.txt")         # summarised on the GPU box (gpu_round.sh)
+        pre_raw = os.path.join(src, rep + "_raw.csv")
+        if not (os.path.exists(path) or os.path.exists(pre_made) or os.path.exists(pre_raw)):
             continue
         if args is not None:
-            txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), path, "40"],
-                                 capture_output=True, text=True).stdout
+            if os.path.exists(pre_made):
+                txt = open(pre_made).read()
+            else:
+                txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), path, "40"],
+                                     capture_output=True, text=True).stdout
             open(os.path.join(dst, "%s_%s_summary.txt" % (pre, rep)), "w").write(
                 "# ncu --set full --clock-control none --import-source on ; summarised by scripts/ncu_summary.py\n" + txt)
         else:
             # several kernels in one report: one raw-metric block each
-            raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+            if os.path.exists(pre_raw):
+                raw = open(pre_raw).read()
+            else:
+                raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
             rows = list(csv.reader(raw.splitlines()))
             hdr, units = rows[0], rows[1]
             keys = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",

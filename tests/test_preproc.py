@@ -371,3 +371,50 @@ def test_preproc_drivers_gloo_world2_match_single_rank():
     for r in (0, 1):
         for a, b in zip(got[r], want):
             assert np.array_equal(a, b, equal_nan=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size runs (native 0.25-degree ERA5 grid): every output of a random sample of grid points is
+# checked against the oracle run on just those points -- the kernels are point-wise, so the result
+# of a point must not depend on the size or tiling of the launch.
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("spd,grouped", [(2, False), (4, True)])
+def test_gpu_wind_stats_full_grid_sampled_oracle(engine, spd, grouped):
+    nlat, nlon, n_days = 721, 1440, 31
+    n_time, n_pts = n_days * spd, nlat * nlon
+    rng = np.random.default_rng(17)
+    ua = rng.normal(0, 8, (n_time, 2, n_pts)).astype(np.float32)
+    va = (0.4 * ua + rng.normal(0, 5, (n_time, 2, n_pts))).astype(np.float32)
+    ua[rng.integers(0, n_time, 50), 0, rng.integers(0, n_pts, 50)] = np.nan
+    gs = np.arange(0, n_time + 1, spd if grouped else 1, dtype=np.int32)
+    got = engine.wind_stats(ua, va, 0, 1, gs)
+    pick = np.unique(np.r_[0, 1, 63, 64, n_pts - 1, n_pts - 65, rng.integers(0, n_pts, 6000),
+                           np.flatnonzero(np.isnan(ua[:, 0]).any(axis=0))])
+    want = po.wind_stats([a[:, k][:, pick] for k in (0, 1) for a in (ua, va)], gs)
+    assert np.array_equal(got[:, pick], want, equal_nan=True)
+    assert np.isfinite(got).all(axis=0).mean() > 0.999
+    # a covariance matrix: symmetric by construction, so check positive variances and |corr| <= 1 everywhere
+    ok = np.isfinite(got).all(axis=0)
+    var_u, var_v, cov_uv = got[4][ok], got[6][ok], got[5][ok]
+    assert (var_u > 0).all() and (var_v > 0).all()
+    n = gs.size - 1
+    assert (np.abs(cov_uv) * (n - 1) / n <= np.sqrt(var_u * var_v) * (1 + 1e-12)).all()      # ddof 1 vs ddof 0 (env_wind.py:211,213)
+
+
+@pytest.mark.gpu
+def test_gpu_thermo_full_grid_sampled_oracle(engine):
+    from tropical_cyclone_risk_b200 import synth_thermo
+    _, table = _thermo_golden()
+    engine.set_entropy_table(*table)
+    n_pts, base = 721 * 1440, 16384
+    p, ta, hus, sst, psl = synth_thermo.soundings(base, seed=23)
+    rng = np.random.default_rng(5)
+    perm = rng.integers(0, base, n_pts)                                   # every column of the grid = one of the soundings
+    got = engine.thermo_month(p, ta[:, perm], hus[:, perm], sst[perm], psl[perm], 1.0, 13)
+    want = po.thermo(p, ta, hus, sst, psl, table, 1.0, 13)                # the oracle on the 16384 distinct soundings
+    for name, a, b in zip(("vmax", "chi", "rh_mid"), got, want):
+        assert np.array_equal(a, b[perm], equal_nan=True), name
+    assert (got[0] >= 0).all() and (got[0] > 30).mean() > 0.2
+    ok = ~np.isnan(got[1])
+    assert (got[1][ok] >= 0).all() and (got[1][ok] <= 10).all() and (got[2] >= 1e-5).all() and (got[2] <= 1).all()
