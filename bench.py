@@ -172,7 +172,7 @@ def run_reference_arm(args):
         return
     from tropical_cyclone_risk_b200.workload import Workload
     threads = cpu_threads()
-    wl = Workload(args.basin, [BASE_YEAR], full_res=True)
+    wl = Workload(args.basin, [BASE_YEAR], full_res=True, namelist=bench_namelist(args))
     n_att = args.cpu_attempts or 20000 * threads
     for i in range(args.warmup):
         cpu_sample(wl, max(1024, n_att // 8), threads, RUN_SEED + 1000 + i)
@@ -195,6 +195,17 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def bench_namelist(args):
+    """The package namelist, with output_interval_s overridden by --interval."""
+    import types
+    from tropical_cyclone_risk_b200 import namelist as nl
+    if not getattr(args, "interval", 0):
+        return nl
+    cfg = types.SimpleNamespace(**{k: getattr(nl, k) for k in dir(nl) if not k.startswith("__")})
+    cfg.output_interval_s = int(args.interval)
+    return cfg
 
 
 def workload_config(args, n_steps):
@@ -235,7 +246,7 @@ def run_gpu_arm(args):
 
     ny, nt = args.years, args.tracks
     years = [BASE_YEAR + rank * ny + i for i in range(ny)]
-    wl = Workload(args.basin, years, full_res=True, pinned_alloc=PinnedPool.empty)
+    wl = Workload(args.basin, years, full_res=True, pinned_alloc=PinnedPool.empty, namelist=bench_namelist(args))
     ns = int(wl.p.n_steps)
     eng = Engine(wl.p, device=local)
     # a dedicated non-blocking stream for the library, torch and NCCL alike: the legacy default
@@ -645,6 +656,7 @@ def main():
     ap.add_argument("--basin", default="NA")
     ap.add_argument("--years", type=int, default=10, help="years per GPU")
     ap.add_argument("--tracks", type=int, default=1000, help="tracks per year")
+    ap.add_argument("--interval", type=int, default=0, help="output_interval_s (0 = namelist default 3600; 900 gives the 1441-step tracks of configs[4])")
     ap.add_argument("--interp-queries", type=float, default=float(1 << 25))
     ap.add_argument("--cpu-attempts", type=int, default=0, help="seed attempts per CPU sample (default scales with threads)")
     ap.add_argument("--integ-variant", type=int, default=0, help="integrate-kernel register variant (0 = library default)")

@@ -52,6 +52,10 @@ namespace {
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }          /* early error returns (CK) must not leak call-local scratch */
     int ensure(size_t need)
     {
         if (need <= bytes) return 0;
