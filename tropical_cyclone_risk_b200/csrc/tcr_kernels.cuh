@@ -618,6 +618,106 @@ __global__ void __launch_bounds__(FT_THREADS) k_fourier_table(const __grid_const
     }
 }
 
+/* ---- the same tables on the FP64 tensor cores -------------------------------------------------
+ * Per storm the tabulation is the dense product  F[n_steps x 4] = SC[n_steps x 30] . CF[30 x 4]  with
+ * SC[j][2k], SC[j][2k+1] = {sin, cos} of harmonic k at node j and CF[2k][i], CF[2k+1][i] the storm's
+ * coefficient pair of series i -- and the specification's summation order (one fma chain per (node,
+ * series) over K = 0..29) is exactly what DMMA.8x8x4 computes: measured on B200, mma.sync.m8n8k4.f64
+ * equals d = fma(a3,b3, fma(a2,b2, fma(a1,b1, fma(a0,b0,c)))) bit for bit (scripts/probes/dmma_order.cu,
+ * 1.28 M elements), and chaining eight of them through the accumulator continues the chain (K padded
+ * from 30 to 32 with zero terms, which leave the sum unchanged).  One mma covers 8 nodes x (2 storms x
+ * 4 series) x 4 K.  Warp w of the CTA owns node groups of 32 (four 8-node tiles whose A fragments --
+ * 32 doubles per lane -- stay in registers; for n_steps <= 384 once for the whole kernel), the CTA walks
+ * double-buffered tiles of 16 storms whose coefficients arrive by cp.async; per storm pair a lane reads
+ * its 8 B-fragment doubles from shared memory, issues 32 DMMA and writes four 16-byte pieces of
+ * ftab[storm][node][series pair] (a warp store covers two 256-byte runs).                          */
+#define FTM_WARPS 12
+#define FTM_THREADS (FTM_WARPS * 32)
+__global__ void __launch_bounds__(FTM_THREADS, 1) k_fourier_table_mma(const __grid_constant__ TcrCtx cx, int64_t n,
+                                                                      const unsigned int* __restrict__ n_dev,
+                                                                      const double2* __restrict__ coef, double* __restrict__ ftab)
+{
+    __shared__ __align__(16) double2 cfs[2][FT_STORMS][TCR_N_PHASES];
+    const int64_t count = n_dev ? (int64_t)*n_dev : n;
+    const int ns = cx.p.n_steps;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = lane >> 2, kq = lane & 3;                   /* A: node row / K offset;  B: column n = row, K offset kq */
+    const int n_jg = (ns + 31) >> 5;                            /* node groups of 32 */
+    const bool hoist = n_jg <= FTM_WARPS;                       /* each warp has at most one group: its A fragments are loaded once */
+    const double* scd = reinterpret_cast<const double*>(cx.sc); /* [n_steps][15][2] = SC[j][K], K = 0..29 */
+
+    double a[4][8];
+    auto load_a = [&](int jg) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int j = min(jg * 32 + t * 8 + row, ns - 1);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int K = c * 4 + kq;
+                a[t][c] = K < 2 * TCR_N_HARM ? __ldg(scd + (size_t)j * (2 * TCR_N_HARM) + K) : 0.0;
+            }
+        }
+    };
+    if (hoist && warp < n_jg) load_a(warp);
+
+    auto prefetch = [&](int64_t s0, int buf) {
+        if (s0 < count) {
+            const int nst = (int)min((int64_t)FT_STORMS, count - s0);
+            for (int i = threadIdx.x; i < nst * TCR_N_PHASES; i += FTM_THREADS)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(&cfs[buf][0][0] + i)),
+                             "l"(coef + (size_t)s0 * TCR_N_PHASES + i) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int64_t stride = (int64_t)gridDim.x * FT_STORMS;
+    int64_t s0 = (int64_t)blockIdx.x * FT_STORMS;
+    int buf = 0;
+    prefetch(s0, 0);
+    for (; s0 < count; s0 += stride, buf ^= 1) {
+        prefetch(s0 + stride, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const int nst = (int)min((int64_t)FT_STORMS, count - s0);
+        for (int jg = warp; jg < n_jg; jg += FTM_WARPS) {
+            if (!hoist) load_a(jg);
+            for (int sp = 0; sp * 2 < nst; ++sp) {
+                /* B fragment: column n = row -> storm 2 sp + (n >> 2), series n & 3; element K of that column is
+                 * double number K of the series' 15 coefficient pairs */
+                const int st_b = min(2 * sp + (row >> 2), nst - 1);
+                const double* cfd = reinterpret_cast<const double*>(&cfs[buf][st_b][(row & 3) * TCR_N_HARM]);
+                double b[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int K = c * 4 + kq;
+                    b[c] = K < 2 * TCR_N_HARM ? cfd[K] : 0.0;
+                }
+                double d[4][2];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) { d[t][0] = 0.0; d[t][1] = 0.0; }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t)
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(d[t][0]), "+d"(d[t][1]) : "d"(a[t][c]), "d"(b[c]));
+                }
+                /* D: row = node, columns 2 kq, 2 kq + 1 -> storm 2 sp + (kq >> 1), series 2 (kq & 1) + {0, 1} */
+                const int st_d = 2 * sp + (kq >> 1);
+                if (st_d < nst) {
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int j = jg * 32 + t * 8 + row;
+                        if (j < ns)
+                            __stcs(reinterpret_cast<double2*>(ftab + ((size_t)(s0 + st_d) * ns + j) * 4 + 2 * (kq & 1)),
+                                   make_double2(d[t][0], d[t][1]));
+                    }
+                }
+            }
+        }
+        __syncthreads();                       /* tile `buf` is free for the prefetch of the iteration after next */
+    }
+}
+
 /* ======================================================================================== */
 /* the integrator: Coupled_FAST.gen_track (coupled_fast.py:229-267) incl. scipy's RK45        */
 /* driver loop, t_eval dense output and the terminal event                                    */

@@ -600,9 +600,16 @@ static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned i
     const int ns = h->ctx.p.n_steps;
     dim3 grid((unsigned)((ns + FT_THREADS * FT_NODES - 1) / (FT_THREADS * FT_NODES)),
               (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_upper + FT_STORMS - 1) / FT_STORMS, (int64_t)h->num_sms * 8)));
+    static const int use_mma = getenv("TCR_FTAB_MMA") ? atoi(getenv("TCR_FTAB_MMA")) : 1;
     {
         LaunchTimer lt_(h, TCR_K_FTABLE);
-        k_fourier_table<<<grid, FT_THREADS, 0, h->stream>>>(h->ctx, n_upper, n_dev, w.coef.as<double2>(), w.ftab.as<double>());
+        if (use_mma) {
+            const int64_t tiles = std::max<int64_t>(1, (n_upper + FT_STORMS - 1) / FT_STORMS);
+            const int g = (int)std::min<int64_t>(tiles, (int64_t)h->num_sms * use_mma);
+            k_fourier_table_mma<<<g, FTM_THREADS, 0, h->stream>>>(h->ctx, n_upper, n_dev, w.coef.as<double2>(), w.ftab.as<double>());
+        } else {
+            k_fourier_table<<<grid, FT_THREADS, 0, h->stream>>>(h->ctx, n_upper, n_dev, w.coef.as<double2>(), w.ftab.as<double>());
+        }
     }
     CKK(h);
     return 0;
