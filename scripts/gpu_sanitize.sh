@@ -1,6 +1,7 @@
 #!/bin/bash
 # compute-sanitizer (memcheck, then racecheck) over a small end-to-end slice of the hot path:
-# uploads, both sampler kernels, explicit seeds through the integrator + post-processing, one small year.
+# uploads, both sampler kernels, explicit seeds through the integrator + post-processing, one small year
+# (Fourier tables on the FP64 tensor cores), the return-period kernel, the pre-processing kernels.
 OUT=gpurun_out/${1:-san}
 mkdir -p $OUT
 cat > /tmp/san_slice.py <<'PY'
@@ -27,6 +28,17 @@ eng2 = Engine(w2.p, device=0); w2.upload(eng2)
 r = eng2.run_years([0], [2002], 7, 6)
 print("run_years ok", r["stats"][0]["storm_steps"])
 print("poi", np.isfinite(eng2.poi_vmax(r["lon"][0], r["lat"][0], r["vmax"][0], 300.0, 25.0, 500.0)).sum())
+# pre-processing kernels: ungrouped / grouped wind statistics (aligned and ragged rows), thermodynamics
+from tropical_cyclone_risk_b200 import synth_thermo
+for shape in ((19, 64), (7, 33)):
+    ua = rng.normal(0, 8, (24, 2) + shape).astype(np.float32); va = rng.normal(0, 6, (24, 2) + shape).astype(np.float32)
+    ua[3, 0, 2, 5] = np.nan
+    eng2.wind_stats(ua, va, 0, 1, np.arange(25, dtype=np.int32))
+    eng2.wind_stats(ua, va, 0, 1, np.arange(0, 25, 4, dtype=np.int32))
+with np.load("tests/golden/entropy_table.npz") as t:
+    eng2.set_entropy_table(t["p"], t["s"], t["T"])
+p, ta, hus, sst, psl = synth_thermo.soundings(700, seed=2)
+print("thermo", float(np.nanmean(eng2.thermo_month(p, ta, hus, sst, psl, 1.0, 13)[0])))
 eng.close(); eng2.close()
 PY
 for tool in memcheck racecheck; do
