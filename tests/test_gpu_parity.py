@@ -157,6 +157,21 @@ def test_integrate_random_bit_exact(na_case, na_eng, variant):
     assert (got["flags"] & 2).any()
 
 
+def test_fourier_tables_scalar_variant_bit_exact(na_case, na_eng):
+    """The default Fourier tabulation runs on the FP64 tensor cores (k_fourier_table_mma, checked by every other
+    integrator test); TCR_FTAB_MMA=0 selects the scalar fp64-pipe kernel, which must give the same tracks --
+    both against the oracle, odd storm count (a half-filled storm pair in the last mma tile)."""
+    import os
+    seeds = _random_seeds(na_case, 1001, 12)
+    os.environ["TCR_FTAB_MMA"] = "0"
+    try:
+        a = _check_integrate(na_eng, na_case, seeds)
+    finally:
+        del os.environ["TCR_FTAB_MMA"]
+    b = _check_integrate(na_eng, na_case, seeds)
+    assert _same(a["track"], b["track"]) and _same(a["vmax"], b["vmax"])
+
+
 def test_integrate_edge_cases(na_case, na_eng):
     ym, lon0, lat0, v0, m0, hbl, ph = _random_seeds(na_case, 64, 12)
     v0[:4] = [3.9, 4.0, 12.0, 20.0]            # event at t0, strong seeds

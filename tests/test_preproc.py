@@ -418,3 +418,19 @@ def test_gpu_thermo_full_grid_sampled_oracle(engine):
     assert (got[0] >= 0).all() and (got[0] > 30).mean() > 0.2
     ok = ~np.isnan(got[1])
     assert (got[1][ok] >= 0).all() and (got[1][ok] <= 10).all() and (got[2] >= 1e-5).all() and (got[2] <= 1).all()
+
+
+@pytest.mark.gpu
+def test_gpu_wind_stats_long_ungrouped_record_falls_back_to_smaller_tiles(engine):
+    """3-hourly samples, no daily averaging: 248 single-sample groups do not fit a 64-point tile (254 KB of
+    shared memory) -- the library picks 32-point tiles; an hourly month does not fit at all and says so."""
+    from tropical_cyclone_risk_b200._lib import TcrError
+    ua, va = synth_winds(248, 2, 9, 40, seed=6)
+    gs = np.arange(249, dtype=np.int32)
+    got = engine.wind_stats(ua, va, 0, 1, gs)
+    assert np.array_equal(got, po.wind_stats(series_of(ua, va, 0, 1), gs))
+    ua, va = synth_winds(744, 2, 2, 8, seed=6)
+    with pytest.raises(TcrError, match="daily groups"):
+        engine.wind_stats(ua, va, 0, 1, np.arange(745, dtype=np.int32))
+    got = engine.wind_stats(ua, va, 0, 1, np.arange(0, 745, 24, dtype=np.int32))          # ... but does as 31 daily groups
+    assert np.array_equal(got, po.wind_stats(series_of(ua, va, 0, 1), np.arange(0, 745, 24)))

@@ -600,7 +600,8 @@ static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned i
     const int ns = h->ctx.p.n_steps;
     dim3 grid((unsigned)((ns + FT_THREADS * FT_NODES - 1) / (FT_THREADS * FT_NODES)),
               (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_upper + FT_STORMS - 1) / FT_STORMS, (int64_t)h->num_sms * 8)));
-    static const int use_mma = getenv("TCR_FTAB_MMA") ? atoi(getenv("TCR_FTAB_MMA")) : 1;
+    const char* ft_env = getenv("TCR_FTAB_MMA");                         /* 0: scalar fp64-pipe variant (A/B runs, tests) */
+    const int use_mma = ft_env ? atoi(ft_env) : 1;
     {
         LaunchTimer lt_(h, TCR_K_FTABLE);
         if (use_mma) {
@@ -1225,7 +1226,7 @@ template <int P, int NT>
 static int launch_wind_stats_single(tcr_handle* h, const WindStatArgs& a)
 {
     const size_t smem = (size_t)a.n_groups * 4 * P * sizeof(float) + (size_t)4 * P * sizeof(double);
-    if (smem > h->smem_optin) return set_err("tcr_wind_stats: %d samples need %zu B of shared memory (limit %zu)", a.n_groups, smem, h->smem_optin);
+    if (smem > h->smem_optin) return set_err("tcr_wind_stats: %d ungrouped samples need %zu B of shared memory (limit %zu): pass daily groups (group_start) for records this long", a.n_groups, smem, h->smem_optin);
     CK(cudaFuncSetAttribute(k_wind_stats_single<P, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = (a.n_pts + P - 1) / P;
     if (grid > 0x7fffffffLL) return set_err("tcr_wind_stats: too many grid points");
@@ -1271,7 +1272,11 @@ int tcr_wind_stats(tcr_handle* h, int n_time, int64_t n_pts, int64_t t_stride,
     const int variant = ws_env ? atoi(ws_env) : -1;
     const bool single = n_groups == n_time;
     int rc;
-    switch (variant >= 0 ? variant : single ? 11 : 9) {
+    /* default kernels: 64 points per CTA when the month tile fits into shared memory, else 32 (long ungrouped records) */
+    int pick = single ? 11 : 9;
+    if (variant < 0 && single && ((size_t)n_groups * 4 * 64 + 8 * 64) * sizeof(float) > h->smem_optin) pick = 10;
+    if (variant < 0 && !single && (size_t)(n_groups + 1) * 4 * 64 * sizeof(double) > h->smem_optin) pick = 8;
+    switch (variant >= 0 ? variant : pick) {
     case 10: rc = launch_wind_stats_single<32, 64>(h, a); break;
     case 11: rc = launch_wind_stats_single<64, 128>(h, a); break;
     case 12: rc = launch_wind_stats_single<32, 128>(h, a); break;
