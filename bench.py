@@ -45,8 +45,8 @@ B_PER_STEP_TRACK = 32      # lon, lat, v, m float64 written by the integrator pe
 B_PER_STORM_PICKUP = 1004  # 60 double2 Fourier coefficients + 5 doubles + 1 int per integrated seed
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
 # workload (profiles/r01_prof_integrate_summary.txt, profiles/r01_prof_interp_summary.txt); None for other workloads
-NCU_TRAFFIC = {"k_integrate": 2.062e9 + 1.820e9, "k_env_interp": 10.157e9 + 5.612e9,
-               "k_wind_stats": 1.030e9 + 0.111e9, "k_thermo": 0.2493e9 + 0.0078e9}
+NCU_TRAFFIC = {"k_integrate": 2.061e9 + 1.818e9, "k_env_interp": 10.154e9 + 5.608e9,
+               "k_wind_stats": 1.030e9 + 0.113e9, "k_thermo": 0.2494e9 + 0.0074e9}
 
 
 def load_peaks():
