@@ -1505,6 +1505,7 @@ struct SelectArgs {
 };
 
 #define SEL_ITEMS 8
+#define SEL_WORDS 4
 __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
 {
     __shared__ int warp_tot[32];
@@ -1523,15 +1524,23 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
     for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) s_hist[i] = 0u;
     __syncthreads();
     /* pass 1: rank the kept storms in attempt order, find i* = attempt of the want-th kept.
-     * Each thread owns SEL_ITEMS consecutive attempts (one 8-byte load of kept flags when aligned). */
+     * Each thread owns SEL_WORDS x 8 consecutive attempts (8-byte loads of kept flags when aligned):
+     * 32768 attempts per trip of the CTA, so a year of ~360 000 attempts takes 11 block scans. */
     const uint8_t* kb = A.att_kept + off;
-    for (int64_t base = 0; base < W; base += (int64_t)blockDim.x * SEL_ITEMS) {
-        const int64_t i0 = base + (int64_t)tid * SEL_ITEMS;
-        unsigned long long bits = 0ull;
-        if (i0 + SEL_ITEMS <= W && (((uintptr_t)(kb + i0)) & 7) == 0) bits = *reinterpret_cast<const unsigned long long*>(kb + i0);
-        else
-            for (int j = 0; j < SEL_ITEMS; ++j) if (i0 + j < W) bits |= (unsigned long long)kb[i0 + j] << (8 * j);
-        const int cnt = __popcll(bits);
+    const bool al8 = (((uintptr_t)kb) & 7) == 0;
+    for (int64_t base = 0; base < W; base += (int64_t)blockDim.x * SEL_ITEMS * SEL_WORDS) {
+        const int64_t i0 = base + (int64_t)tid * SEL_ITEMS * SEL_WORDS;
+        unsigned long long bits[SEL_WORDS];
+        int cnt = 0;
+#pragma unroll
+        for (int w = 0; w < SEL_WORDS; ++w) {
+            const int64_t iw = i0 + w * SEL_ITEMS;
+            bits[w] = 0ull;
+            if (iw + SEL_ITEMS <= W && al8) bits[w] = *reinterpret_cast<const unsigned long long*>(kb + iw);
+            else
+                for (int j = 0; j < SEL_ITEMS; ++j) if (iw + j < W) bits[w] |= (unsigned long long)kb[iw + j] << (8 * j);
+            cnt += __popcll(bits[w]);
+        }
         int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(TCR_FULL, incl, d); if (lane >= d) incl += v; }
@@ -1546,18 +1555,21 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
         __syncthreads();
         int rank = s_running + warp_tot[wid] + incl - cnt;          /* kept storms before this thread's items */
         if (cnt) {
-            for (int j = 0; j < SEL_ITEMS; ++j) {
-                if (!((bits >> (8 * j)) & 1ull)) continue;
-                ++rank;                                              /* 1-based rank of this kept storm */
-                if (rank <= want) {
-                    const int64_t i = i0 + j;
-                    const int row = nt0 + rank - 1;
-                    const int slot = A.att_slot[off + i];
-                    A.row_slot[(size_t)yr * A.n_tracks + row] = slot;
-                    A.tc_month[(size_t)yr * A.n_tracks + row] = (double)A.month[off + i];
-                    A.tc_basin[(size_t)yr * A.n_tracks + row] = A.basin[off + i];
-                    atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot]);
-                    if (rank == want) s_istar = (int)i;
+            for (int w = 0; w < SEL_WORDS; ++w) {
+                if (!bits[w]) continue;
+                for (int j = 0; j < SEL_ITEMS; ++j) {
+                    if (!((bits[w] >> (8 * j)) & 1ull)) continue;
+                    ++rank;                                          /* 1-based rank of this kept storm */
+                    if (rank <= want) {
+                        const int64_t i = i0 + w * SEL_ITEMS + j;
+                        const int row = nt0 + rank - 1;
+                        const int slot = A.att_slot[off + i];
+                        A.row_slot[(size_t)yr * A.n_tracks + row] = slot;
+                        A.tc_month[(size_t)yr * A.n_tracks + row] = (double)A.month[off + i];
+                        A.tc_basin[(size_t)yr * A.n_tracks + row] = A.basin[off + i];
+                        atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot]);
+                        if (rank == want) s_istar = (int)i;
+                    }
                 }
             }
         }
