@@ -213,7 +213,7 @@ def workload_config(args, n_steps):
         "workload": "BASELINE configs[1] per GPU: %s basin, %d years, tracks_per_year=%d, %d output steps, "
                     "ERA5-shaped (1 deg) synthetic env fields, 1 m/s roughness" % (args.basin, args.years, args.tracks, n_steps),
         "basin": args.basin, "years_per_gpu": args.years, "tracks_per_year": args.tracks, "n_steps": int(n_steps),
-        "run_seed": RUN_SEED, "parallelism": "years sharded over ranks; NCCL all-gather of finished tracks at write-out",
+        "run_seed": RUN_SEED, "parallelism": "years sharded over ranks; NCCL all-gather of finished tracks at write-out (every step, inside the timed region)",
         "l2": "inputs larger than L2: cell-record tables %d months + result block, see l2_bytes" % (12 * args.years),
     }
 
@@ -281,6 +281,12 @@ def run_gpu_arm(args):
     step_no = [0]
 
     diag = os.environ.get("TCR_BENCH_DIAG") == "1"
+    # Write-out all-gather: by default the next step's kernels wait for it on the stream (0.6-0.8 ms at N = 2 over
+    # NVLink).  Letting it overlap the next step (TCR_BENCH_GATHER=overlap, two result blocks) was measured to cost
+    # MORE: the persistent integrator owns every SM's register file, NCCL's CTAs cannot become resident beside it,
+    # the gather ends up behind that integrator and the step after it waits for the block: 15.5-16.9 ms per step
+    # against 13.1 + 0.7 ms (profiles/r01_n2_gather_modes.txt).
+    gather_overlap = os.environ.get("TCR_BENCH_GATHER", "") == "overlap"
 
     def step_device(i):
         t0 = time.perf_counter()
@@ -292,7 +298,11 @@ def run_gpu_arm(args):
         st = eng.run_years_dev(ym_base, year_key, RUN_SEED + i, nt, dptrs[b])
         t1 = time.perf_counter()
         if world > 1:
-            pending[b] = dist.all_gather_into_tensor(gathered[b], res_blocks[b], async_op=True)
+            work = dist.all_gather_into_tensor(gathered[b], res_blocks[b], async_op=True)
+            if gather_overlap:
+                pending[b] = work                              # waited for two steps later, when block b is reused
+            else:
+                work.wait()                                    # stream-ordered: the next step's kernels start after the gather
         if diag:
             t2 = time.perf_counter()
             torch.cuda.synchronize()
