@@ -216,8 +216,8 @@ def test_thermo_oracle_against_live_reference_if_present():
     from tropical_cyclone_risk_b200 import synth_thermo
     ref = rh.load_reference()
     _, table = _thermo_golden()
-    p, ta, hus, sst, psl = synth_thermo.soundings(512, seed=99)
-    shp = (16, 32)
+    p, ta, hus, sst, psl = synth_thermo.soundings(8192, seed=99)
+    shp = (64, 128)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         want = ref.thermo.CAPE_PI_vectorized(sst.reshape(shp), psl.reshape(shp), p.copy(),
