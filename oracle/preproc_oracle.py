@@ -12,8 +12,8 @@ xarray's published reduction semantics:
   * ``xr.cov(a, b, dim)`` (ddof = 1)           -> xarray/computation.py::_cov_corr:
         valid = a.notnull() & b.notnull(); a, b = a.where(valid), b.where(valid)
         cov = ((a - a.mean()) * (b - b.mean())).sum(skipna=True, min_count=1) / (valid.sum() - ddof)
-and it is pinned against numpy.mean / numpy.var / numpy.cov on NaN-free input
-(tests/test_preproc.py).  Arithmetic: float32 samples widened to float64, every reduction a
+and it is pinned against numpy.mean / numpy.var / numpy.cov on NaN-free input and against pandas'
+groupby-mean / var / pairwise-complete DataFrame.cov on input with missing samples (tests/test_preproc.py).  Arithmetic: float32 samples widened to float64, every reduction a
 sequential float64 sum in time order (what NumPy does for axis-0 reductions of a C-contiguous
 array), so the CUDA kernel can be compared bit for bit.
 """

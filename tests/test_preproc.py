@@ -434,3 +434,27 @@ def test_gpu_wind_stats_long_ungrouped_record_falls_back_to_smaller_tiles(engine
         engine.wind_stats(ua, va, 0, 1, np.arange(745, dtype=np.int32))
     got = engine.wind_stats(ua, va, 0, 1, np.arange(0, 745, 24, dtype=np.int32))          # ... but does as 31 daily groups
     assert np.array_equal(got, po.wind_stats(series_of(ua, va, 0, 1), np.arange(0, 745, 24)))
+
+
+def test_wind_oracle_nan_policy_matches_pandas():
+    """An independent implementation of the same published semantics: pandas' groupby-mean (skipna),
+    var(ddof=0) and DataFrame.cov (pairwise-complete observations, ddof=1) -- what xarray's
+    groupby("time.day").mean / .var / xr.cov compute -- on series with missing samples."""
+    import pandas as pd
+    ua, va = synth_winds(40, 2, 2, 3, seed=12, nan_frac=0.2)
+    s = series_of(ua, va, 0, 1)
+    gs = np.arange(0, 41, 4)
+    got = po.wind_stats(s, gs)
+    day = np.repeat(np.arange(10), 4)
+    for pt in range(s[0].shape[1]):
+        df = pd.DataFrame({k: a[:, pt].astype(np.float64) for k, a in enumerate(s)})
+        dm = df.groupby(day).mean()                                   # daily means, NaN where a day has no valid sample
+        np.testing.assert_allclose(got[:4, pt], dm.mean().to_numpy(), rtol=1e-13, equal_nan=True)
+        cov = dm.cov(ddof=1).to_numpy()
+        var0 = dm.var(ddof=0).to_numpy()
+        k = 4
+        for i in range(4):
+            for j in range(i + 1):
+                want = var0[i] if i == j else cov[i, j]
+                np.testing.assert_allclose(got[k, pt], want, rtol=1e-11, atol=1e-12, equal_nan=True)
+                k += 1
