@@ -4,7 +4,9 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline legs may import
 
 wind_stats(): NumPy restatement of calc_wnd_stat (track/env_wind.py:169-228).  The reference
 runs on xarray, which is NOT installed in this container and whose version environment.yml does
-not pin -- **parity unpinned** against the reference for this function.  What is restated is
+not pin -- **parity unpinned** against xarray's own arithmetic (the reference's function body itself IS
+pinned: it runs unmodified over the NumPy-backed stand-in of oracle/xr_shim.py, fixtures in
+tests/golden/ref_windstats.npz).  What is restated is
 xarray's published reduction semantics:
   * ``.groupby("time.day").mean(dim="time")``  -> per day: nanmean (skipna default for floats)
   * ``.mean(dim)``                             -> nanmean

@@ -458,3 +458,54 @@ def test_wind_oracle_nan_policy_matches_pandas():
                 want = var0[i] if i == j else cov[i, j]
                 np.testing.assert_allclose(got[k, pt], want, rtol=1e-11, atol=1e-12, equal_nan=True)
                 k += 1
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's OWN calc_wnd_stat (unmodified function body, run over the NumPy-backed xarray
+# stand-in of oracle/xr_shim.py by oracle/make_golden_windstats.py): pins the month mask, the
+# day-grouping condition, the level selection, the order of the 14 statistics and their ddof.
+# ------------------------------------------------------------------------------------------------
+WINDSTAT_CASES = ["era5_2x_daily", "five_daily", "era5_with_nans"]
+
+
+def _windstat_case(name):
+    from conftest import golden
+    g = golden("ref_windstats.npz")
+    times = g[name + "_times"].astype("datetime64[s]")
+    month = g[name + "_month"]
+    return (g[name + "_ua"], g[name + "_va"], times, g[name + "_levels"], str(g[name + "_units"]),
+            datetime.datetime(int(month[0]), int(month[1]), 15), g[name + "_stats"])
+
+
+@pytest.mark.parametrize("name", WINDSTAT_CASES)
+def test_calc_wnd_stat_mirror_matches_reference_function(name):
+    from tropical_cyclone_risk_b200 import preproc
+    ua, va, times, levels, units, dt, want = _windstat_case(name)
+    got = preproc.calc_wnd_stat(_OracleEngine(), ua, va, times, levels, dt, level_units=units)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-13)
+
+
+def test_reference_calc_wnd_stat_live_if_present():
+    """Regenerates one fixture case through the live reference (build container only)."""
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not present")
+    from oracle import make_golden_windstats as mg
+    from oracle import xr_shim
+    ref = rh.load_reference()
+    xr_shim.install(ref.env_wind.xr)
+    ua, va, times, levels, units, dt, want = _windstat_case("era5_with_nans")
+    got = mg.reference_stats(ref, ua, va, times.astype("datetime64[ns]"), list(levels.astype(int)), units, dt)
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", WINDSTAT_CASES)
+def test_gpu_calc_wnd_stat_matches_reference_function(engine, name):
+    from tropical_cyclone_risk_b200 import preproc
+    ua, va, times, levels, units, dt, want = _windstat_case(name)
+    got = preproc.calc_wnd_stat(engine, ua, va, times, levels, dt, level_units=units)
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-13)
+    # and bit for bit what the oracle gives through the same host function
+    assert np.array_equal(got, preproc.calc_wnd_stat(_OracleEngine(), ua, va, times, levels, dt, level_units=units), equal_nan=True)
