@@ -56,3 +56,15 @@ def test_special_values():
     assert orc.libm_eval(FN["tanh"], [0.0])[0] == 0.0
     assert np.array_equal(orc.libm_eval(FN["asin"], [1.0, -1.0, 0.0]), [np.pi / 2, -np.pi / 2, 0.0])
     assert np.isnan(orc.libm_eval(FN["asin"], [1.0000001])[0])
+
+
+@pytest.mark.parametrize("name,ref,lo,hi", [
+    ("exp", np.exp, -20.0, 10.0),            # Bolton's saturation vapour pressure exp(min(17.625 Tc / (Tc + 243.04), 10)); Lambert-W iterates
+    ("log", np.log, 50.0, 1.1e5),            # log(T), log(p - es rh), log(p_env) of the thermodynamic kernel (thermo/thermo.py:50-76)
+    ("log", np.log, 1e-5, 1.0),              # log(rh); log(-z) of the Lambert-W first guess
+])
+def test_accuracy_on_thermo_ranges(name, ref, lo, hi):
+    rng = np.random.default_rng(int(abs(lo) * 10) + 3)
+    x = rng.uniform(lo, hi, 200000)
+    got = orc.libm_eval(FN[name], x)
+    assert _ulps(got, ref(x)).max() < 2.0, name
