@@ -27,15 +27,18 @@
  * NaN samples are skipped the way xarray's skipna reductions skip them (nanmean / nanvar per
  * variable; xr.cov on the days where both variables are valid).
  *
- * Mapping.  A CTA owns 32*VEC consecutive grid points for the whole month and reads every
- * sample of theirs exactly once.  Grouped input: warp (v, k) streams variable v for the days
- * g = k, k+KSPLIT, ..., each lane VEC consecutive points (one 128*VEC-byte row segment per warp load,
- * U independent loads in flight per lane, ld.global.cs).  Ungrouped input (SINGLE): the samples go
- * global -> shared as 16-byte cp.async copies, all in flight at once.  The daily means sit in shared
- * memory [day][variable][point] (float64; float32 samples when SINGLE); after one barrier two
- * threads per point read its day series back from shared memory twice (means, then demeaned products) and
- * write the 14 statistics with coalesced stores.  HBM traffic = the algorithmic minimum: 16 B per (sample, point) read once,
- * 112 B per point written.                                                                    */
+ * Mapping.  A CTA owns P consecutive grid points (64 by default) for the whole month and reads every
+ * sample of theirs exactly once.
+ *   ungrouped input (k_wind_stats_single -- the reference's own case): the samples go global -> shared
+ *     as 16-byte cp.async copies, all in flight at once, and stay float32 in shared memory;
+ *   grouped input (k_wind_stats): warp (v, k) streams variable v for the days g = k, k + KSPLIT, ...,
+ *     each lane VEC consecutive points (one 128*VEC-byte row segment per warp load, U independent loads
+ *     in flight per lane, ld.global.cs) and leaves the float64 daily means in shared memory.
+ * After one barrier two threads per point read its day series [day][variable][point] back from shared
+ * memory twice (sums, then demeaned products) and write the 14 statistics with coalesced stores.
+ * HBM traffic = the algorithmic minimum: 16 B per (sample, point) read once, 112 B per point written.
+ * The kernel needs ~2.2 fp64-pipe operations (DADD / DMUL / F2F.F64.F32) per byte against a machine
+ * balance of ~2.9: it meets the fp64 pipe and HBM at about the same time.       */
 struct WindStatArgs {
     const float* src[4];        /* variable v, sample t, point p at src[v][t * t_stride + p]        */
     int64_t t_stride;           /* elements between consecutive samples                            */
