@@ -593,9 +593,7 @@ def bench_thermo(eng, torch, dev, peak, peak_src, nlat=721, nlon=1440, cpu=False
     The kernel is bound by the float64 pipe (two exp and ~8 divisions per level and column), not by HBM; the
     HBM fraction is reported because the contract asks for it."""
     from tropical_cyclone_risk_b200 import synth_thermo
-    golden = os.path.join(ROOT, "tests", "golden", "entropy_table.npz")
-    with np.load(golden) as t:
-        table = (t["p"], t["s"], t["T"])
+    table = synth_thermo.fixture_table()
     eng.set_entropy_table(*table)
     n_pts = nlat * nlon
     base = 8192

@@ -37,11 +37,15 @@ def main():
         chi = np.minimum(np.maximum(th.sat_deficit(sst.reshape(shp), psl.reshape(shp), ta64[K_MID], float(p[K_MID]),
                                                    hus64[K_MID]), 0), 10)                                # :66-68
         rh_mid = th.conv_q_to_rh(ta64[K_MID], hus64[K_MID], float(p[K_MID]))                            # :69
+    # the entropy inversion table CAPE_PI_vectorized loaded (thermo.py:274-278) travels inside the fixture: it is an
+    # input of the computation, and the GPU box has no reference tree to read it from
     with np.load(os.path.join(rh.REF_ROOT, "thermo", "entropy_table.npz")) as t:
-        crc = int(np.frombuffer(t["T"].tobytes(), dtype=np.uint32).sum() & 0xffffffff)
+        tp, ts, tT = np.array(t["p"]), np.array(t["s"]), np.array(t["T"])
+        crc = int(np.frombuffer(tT.tobytes(), dtype=np.uint32).sum() & 0xffffffff)
     out = os.path.join(ROOT, "tests", "golden", "ref_thermo.npz")
     np.savez_compressed(out, p=p, ta=ta, hus=hus, sst=sst, psl=psl, k_mid=K_MID, cecd=nl.Ck / nl.Cd,
-                        vmax=vmax.reshape(-1), chi=chi.reshape(-1), rh_mid=rh_mid.reshape(-1), table_crc=crc)
+                        vmax=vmax.reshape(-1), chi=chi.reshape(-1), rh_mid=rh_mid.reshape(-1), table_crc=crc,
+                        table_p=tp, table_s=ts, table_T=tT)
     print("wrote", out, os.path.getsize(out), "bytes; PI>0 in %d of %d columns, max %.1f m/s" %
           ((vmax > 0).sum(), N, np.nanmax(vmax)))
 

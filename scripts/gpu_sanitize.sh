@@ -35,8 +35,7 @@ for shape in ((19, 64), (7, 33)):
     ua[3, 0, 2, 5] = np.nan
     eng2.wind_stats(ua, va, 0, 1, np.arange(25, dtype=np.int32))
     eng2.wind_stats(ua, va, 0, 1, np.arange(0, 25, 4, dtype=np.int32))
-with np.load("tests/golden/entropy_table.npz") as t:
-    eng2.set_entropy_table(t["p"], t["s"], t["T"])
+eng2.set_entropy_table(*synth_thermo.fixture_table())
 p, ta, hus, sst, psl = synth_thermo.soundings(700, seed=2)
 print("thermo", float(np.nanmean(eng2.thermo_month(p, ta, hus, sst, psl, 1.0, 13)[0])))
 eng.close(); eng2.close()

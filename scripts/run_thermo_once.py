@@ -14,8 +14,7 @@ from tropical_cyclone_risk_b200.params import params_from_namelist
 
 dev = torch.device("cuda:0")
 eng = Engine(params_from_namelist(nl, "NA"), device=0)
-with np.load(os.path.join(ROOT, "tests", "golden", "entropy_table.npz")) as t:
-    eng.set_entropy_table(t["p"], t["s"], t["T"])
+eng.set_entropy_table(*synth_thermo.fixture_table())
 n_pts, base = 721 * 1440, 8192
 p, ta, hus, sst, psl = synth_thermo.soundings(base, seed=21)
 reps = (n_pts + base - 1) // base

@@ -185,8 +185,8 @@ def test_gpu_wind_stats_rejects_bad_groups(engine):
 # ================================================================================================
 def _thermo_golden():
     from conftest import golden
-    g, t = golden("ref_thermo.npz"), golden("entropy_table.npz")
-    return g, (t["p"], t["s"], t["T"])
+    g = golden("ref_thermo.npz")
+    return g, (g["table_p"], g["table_s"], g["table_T"])
 
 
 def _assert_close_to_reference(got, want, rtol, atol, what):

@@ -1,6 +1,8 @@
 """Synthetic ERA5-shaped soundings for the thermodynamic pre-processing kernel:
 the 28 pressure levels scripts/download_era5.py:80-84 requests, lowest level first as
 calc_thermo.py:50-55 arranges them, float32 temperature / specific humidity like the ERA5 files."""
+import os
+
 import numpy as np
 
 ERA5_LEVELS_HPA = np.array([1000, 975, 950, 925, 900, 875, 850, 825, 800, 775, 750, 700, 650, 600, 550, 500, 450, 400,
@@ -42,3 +44,13 @@ def soundings(n, seed=0, edge_cases=True):
     sst = sst.astype(np.float32).astype(np.float64)
     psl = psl.astype(np.float32).astype(np.float64)
     return p, ta, hus, sst, psl
+
+
+def fixture_table():
+    """(p_look, s_look, T_lookup): the entropy inversion table the thermodynamic fixtures were generated with
+    (tests/golden/ref_thermo.npz, generated in the build container from the reference's
+    thermo/entropy_table.npz) -- for benches, smoke runs and tests on machines without a reference checkout.
+    Production callers pass their own table (preproc.load_entropy_table)."""
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ref_thermo.npz")
+    with np.load(path) as g:
+        return np.array(g["table_p"]), np.array(g["table_s"]), np.array(g["table_T"])
