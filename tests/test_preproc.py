@@ -200,6 +200,8 @@ def test_thermo_oracle_matches_reference_golden():
     NaN-level columns: identical NaN pattern, PI within 1e-11 relative of the live reference."""
     g, table = _thermo_golden()
     assert int(np.frombuffer(table[2].tobytes(), dtype=np.uint32).sum() & 0xffffffff) == int(g["table_crc"])
+    from tropical_cyclone_risk_b200 import synth_thermo
+    assert all(np.array_equal(a, b) for a, b in zip(synth_thermo.fixture_table(), table))        # what bench / smoke load
     v, c, r = po.thermo(g["p"], g["ta"], g["hus"], g["sst"], g["psl"], table, float(g["cecd"]), int(g["k_mid"]))
     _assert_close_to_reference(v, g["vmax"], 1e-11, 1e-11, "vmax")
     _assert_close_to_reference(c, g["chi"], 1e-10, 1e-12, "chi")
