@@ -14,8 +14,9 @@ What differs from the reference, by design:
   * random numbers are an indexed Philox stream keyed by (run_seed, year) instead of the
     wall-clock-seeded global MT19937 (track/bam_track.py:37-42), so results are reproducible
     and independent of the number of GPUs;
-  * the monthly environment tables come from an *input provider* (`set_inputs`): this image has
-    no NetCDF/HDF5 reader, so the default provider is the synthetic ERA5-shaped generator.
+  * the monthly environment tables come from an *input provider* (`configure(inputs=...)`): the default is
+    the synthetic ERA5-shaped generator; `refdata.ReferenceInputs` reads the reference's own static files and
+    its env_wnd / thermo caches (NetCDF-4 through the built-in HDF5 reader `h5lite`, NetCDF-3 through SciPy).
 
 There is no CPU fallback: without a CUDA device `run_tracks` raises.
 """

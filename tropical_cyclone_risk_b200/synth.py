@@ -156,11 +156,19 @@ def synth_static(full_res=True):
     bathy[land_b] = 300
     land = land_fraction(lon_l, lat_l).astype(np.int8)
 
-    # basin masks, boxes of scripts/generate_land_masks.py:43-110 on the 0.25 deg grid
+    lon_m, lat_m, masks, gl = basin_masks(lambda lon, lat: ~land_fraction(lon, lat))
+    return dict(lon_b=lon_b, lat_b=lat_b, bathy=bathy, lon_l=lon_l, lat_l=lat_l, land=land,
+                lon_m=lon_m, lat_m=lat_m, masks=masks, mask_GL=gl)
+
+
+def basin_masks(ocean_fn):
+    """The basin masks of scripts/generate_land_masks.py:43-110 on its 0.25-degree grid (721 x 1440, 0..360 E):
+    boxes AND ocean.  ocean_fn(lon_m, lat_m) -> bool [721][1440].  Returns (lon_m, lat_m, masks uint8 [7][721][1440]
+    in layout.BASIN_IDS order, mask_GL uint8)."""
     lat_m = np.linspace(-90.0, 90.0, 721)
     lon_m = np.linspace(0.0, 360.0, 1441)[:-1]
     LON, LAT = np.meshgrid(lon_m, lat_m)
-    ocean = ~land_fraction(lon_m, lat_m)
+    ocean = np.asarray(ocean_fn(lon_m, lat_m), dtype=bool)
     na_box = np.zeros(LON.shape, dtype=bool)
     for la, lo in zip((0, 9, 10, 14, 18), (285, 278, 276, 271, 262)):
         na_box |= (LAT >= la) & (LON >= lo) & ocean
@@ -179,8 +187,7 @@ def synth_static(full_res=True):
     }
     gl = ocean & (np.abs(LAT) <= 50)
     masks = np.stack([m[b] for b in layout.BASIN_IDS]).astype(np.uint8)
-    return dict(lon_b=lon_b, lat_b=lat_b, bathy=bathy, lon_l=lon_l, lat_l=lat_l, land=land,
-                lon_m=lon_m, lat_m=lat_m, masks=masks, mask_GL=gl.astype(np.uint8))
+    return lon_m, lat_m, masks, gl.astype(np.uint8)
 
 
 def ocean_axes():

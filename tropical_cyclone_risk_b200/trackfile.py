@@ -49,9 +49,15 @@ def write_tracks(path, out):
 
 
 def read_tracks(path):
-    """Round-trip reader (tests; analysis without xarray)."""
-    with netcdf_file(path, "r", mmap=False) as f:
-        out = {k: np.array(v[:]) for k, v in f.variables.items()}
+    """Reader for both flavours: the NetCDF-3 files written above and the NetCDF-4 / HDF5 files the reference writes
+    through xarray (util/compute.py:263; the samples under notebooks/data) -- the latter through h5lite.py, strings
+    arriving as variable-length strings.  Returns {variable: ndarray} with `tc_basins` / `basin` as 'U2' arrays."""
+    from . import refdata
+    out = {k: v for k, (v, _) in refdata.open_variables(path).items()}
     for k in ("tc_basins", "basin"):
-        out[k] = np.array([b"".join(row).decode().strip() for row in out[k]], dtype="U2")
+        a = out[k]
+        if a.dtype.kind == "S" and a.ndim == 2:                       # char array [n][strlen]
+            out[k] = np.array([b"".join(row).decode().strip() for row in a], dtype="U2")
+        else:
+            out[k] = np.array([str(x).strip() for x in a.reshape(-1)], dtype="U2")
     return out
