@@ -1,0 +1,144 @@
+"""run.py / compute_downscaling_inputs mirror (driver.py): file discovery, CF decoding, month stamps, cache files.
+No GPU here: an engine stand-in with the oracle's arithmetic takes the place of the CUDA engine (the kernels themselves
+are checked bit for bit in tests/test_preproc.py)."""
+import datetime
+import types
+
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+from oracle import preproc_oracle as po
+
+
+class OracleEngine:
+    def __init__(self, table):
+        self.table = table
+
+    def wind_stats(self, ua, va, iu, il, gs):
+        n = ua.shape[0]
+        return po.wind_stats([a[:, k].reshape(n, -1) for k in (iu, il) for a in (ua, va)], gs)
+
+    def thermo_month(self, p_env, ta, hus, sst, psl, cecd, k_mid):
+        out = po.thermo(p_env, ta, hus, sst, psl, self.table, cecd, k_mid)
+        return tuple(o.reshape(np.shape(sst)) for o in out)
+
+
+def _namelist(tmp_path):
+    from tropical_cyclone_risk_b200 import namelist as nl
+    cfg = types.SimpleNamespace(**{k: getattr(nl, k) for k in dir(nl) if not k.startswith("__")})
+    cfg.base_directory = str(tmp_path / "in")
+    cfg.output_directory = str(tmp_path / "out")
+    cfg.exp_prefix, cfg.dataset_type = "era5", "ERA5"
+    cfg.var_keys = {'ERA5': {'sst': 'sst', 'mslp': 'sp', 'temp': 't', 'sp_hum': 'q', 'u': 'u', 'v': 'v',
+                             'lvl': 'level', 'lon': 'longitude', 'lat': 'latitude'}}
+    cfg.start_year, cfg.start_month, cfg.end_year, cfg.end_month = 2001, 1, 2001, 4
+    return cfg
+
+
+LAT = np.linspace(40, -40, 9)                    # ERA5 files run north to south
+LON = np.arange(0.0, 360.0, 30.0)
+HOURS0 = (datetime.datetime(2001, 1, 1) - datetime.datetime(1900, 1, 1)).total_seconds() / 3600.0
+
+
+def _write(path, name, times_h, data, levels=None, packed=False, units="m s**-1"):
+    with netcdf_file(str(path), "w", version=2) as f:
+        f.createDimension("time", len(times_h)); f.createDimension("latitude", LAT.size); f.createDimension("longitude", LON.size)
+        t = f.createVariable("time", "i4", ("time",)); t.units = "hours since 1900-01-01 00:00:00.0"; t.calendar = "gregorian"
+        t[:] = np.asarray(times_h, dtype=np.int32)
+        f.createVariable("latitude", "f4", ("latitude",))[:] = LAT
+        f.createVariable("longitude", "f4", ("longitude",))[:] = LON
+        dims = ("time", "latitude", "longitude")
+        if levels is not None:
+            f.createDimension("level", len(levels))
+            lv = f.createVariable("level", "i4", ("level",)); lv.units = "millibars"; lv[:] = levels
+            dims = ("time", "level", "latitude", "longitude")
+        if packed:                                                        # ERA5 style: int16 + scale_factor / add_offset / _FillValue
+            sf, ao = 0.002, 3.0
+            v = f.createVariable(name, "i2", dims); v.scale_factor = sf; v.add_offset = ao; v._FillValue = np.int16(-32767); v.units = units
+            v[:] = np.clip(np.rint((data - ao) / sf), -32766, 32767).astype(np.int16)
+        else:
+            v = f.createVariable(name, "f4", dims); v.units = units
+            v[:] = data.astype(np.float32)
+
+
+@pytest.fixture()
+def era5_tree(tmp_path):
+    from tropical_cyclone_risk_b200 import synth_thermo
+    cfg = _namelist(tmp_path)
+    (tmp_path / "in" / "winds").mkdir(parents=True)
+    rng = np.random.default_rng(4)
+    n_days = 31 + 28 + 31 + 30 + 10                                       # Jan 1 .. May 10, 2 x daily
+    th = HOURS0 + 12 * np.arange(2 * n_days)
+    levels = [250, 850]
+    u = rng.normal(3, 8, (th.size, 2, LAT.size, LON.size))
+    v = 0.3 * u + rng.normal(0, 5, u.shape)
+    _write(tmp_path / "in" / "winds" / "era5_u_daily_2001.nc", "u", th, u, levels, packed=True)
+    _write(tmp_path / "in" / "winds" / "era5_v_daily_2001.nc", "v", th, v, levels, packed=True)
+    # monthly thermodynamic inputs: Jan .. May, 28 levels 70 .. 1000 hPa (ascending pressure, like the ERA5 files)
+    tm = [HOURS0 + 24 * d for d in (0, 31, 59, 90, 120)]
+    n = LAT.size * LON.size
+    p, ta, hus, sst, psl = synth_thermo.soundings(5 * n, seed=9, edge_cases=False)
+    ta = ta.reshape(28, 5, LAT.size, LON.size).transpose(1, 0, 2, 3)[:, ::-1]
+    hus = hus.reshape(28, 5, LAT.size, LON.size).transpose(1, 0, 2, 3)[:, ::-1]
+    lv = (p / 100.0)[::-1].astype(int)
+    _write(tmp_path / "in" / "era5_t_monthly.nc", "t", tm, ta, lv, units="K")
+    _write(tmp_path / "in" / "era5_q_monthly.nc", "q", tm, hus, lv, units="kg kg**-1")
+    _write(tmp_path / "in" / "era5_sst_monthly.nc", "sst", tm, sst.reshape(5, LAT.size, LON.size), units="K")
+    _write(tmp_path / "in" / "era5_sp_monthly.nc", "sp", tm, psl.reshape(5, LAT.size, LON.size), units="Pa")
+    return cfg, dict(th=th, p=p, ta=ta, hus=hus, sst=sst.reshape(5, LAT.size, LON.size), psl=psl.reshape(5, LAT.size, LON.size))
+
+
+def test_glob_prefix_and_names(era5_tree):
+    from tropical_cyclone_risk_b200 import driver
+    cfg, _ = era5_tree
+    assert [p.split("/")[-1] for p in driver.glob_prefix(cfg, "u")] == ["era5_u_daily_2001.nc"]
+    assert [p.split("/")[-1] for p in driver.glob_prefix(cfg, "sst")] == ["era5_sst_monthly.nc"]
+    assert driver.get_env_wnd_fn(cfg).endswith("out/env_wnd_era5_200101_200104.nc")
+    assert driver.get_fn_thermo(cfg).endswith("out/thermo_era5_200101_200104.nc")
+    assert driver.get_bounding_times(cfg) == (datetime.datetime(2001, 1, 1), datetime.datetime(2001, 4, 30))
+
+
+def test_compute_downscaling_inputs_writes_the_reference_caches(era5_tree, capsys):
+    from conftest import golden
+    from tropical_cyclone_risk_b200 import driver, layout, refdata
+    cfg, src = era5_tree
+    g = golden("ref_thermo.npz")
+    table = (g["table_p"], g["table_s"], g["table_T"])
+    eng = OracleEngine(table)
+    driver.compute_downscaling_inputs(eng, cfg)
+    assert "Saved" in capsys.readouterr().out
+    # ---- wind statistics: month stamps of wnd_stat_wrapper (first = the start date itself, then the 15th) ----
+    w = refdata._Cache(driver.get_env_wnd_fn(cfg), layout.FIELD_NAMES[:14])
+    assert w.times == [datetime.datetime(2001, 1, 1), datetime.datetime(2001, 2, 15), datetime.datetime(2001, 3, 15),
+                       datetime.datetime(2001, 4, 15)]
+    assert np.array_equal(w.lat, LAT.astype(np.float32).astype(np.float64))
+    su = driver._Source(cfg, driver.glob_prefix(cfg, "u")[0], "u", True)
+    sv = driver._Source(cfg, driver.glob_prefix(cfg, "v")[0], "v", True)
+    assert su.data.dtype == np.float32 and su.level_units == "millibars"
+    feb = [i for i, t in enumerate(su.times) if t.month == 2]
+    want = po.wind_stats([a[feb][:, k].reshape(len(feb), -1) for k in (0, 1) for a in (su.data, sv.data)], np.arange(len(feb) + 1))
+    for i, name in enumerate(layout.FIELD_NAMES[:14]):
+        assert np.array_equal(np.asarray(w.vars[name][1]).reshape(-1), want[i]), name
+    # ---- thermodynamics: every sample inside the namelist's period, stamped the 15th, levels re-ordered ----
+    t = refdata._Cache(driver.get_fn_thermo(cfg), ("vmax", "chi", "rh_mid"))
+    assert t.times == [datetime.datetime(2001, m, 15) for m in (1, 2, 3, 4)]
+    k = 2
+    ta_k = src["ta"][k, ::-1].astype(np.float32)                         # as the kernel sees it: lowest level first
+    hus_k = src["hus"][k, ::-1].astype(np.float32)
+    wv, wc, wr = po.thermo(src["p"], ta_k, hus_k, src["sst"][k].astype(np.float32).astype(np.float64),
+                           src["psl"][k].astype(np.float32).astype(np.float64), table, cfg.Ck / cfg.Cd, 13)
+    assert np.array_equal(np.asarray(t.vars["vmax"][k]).reshape(-1), wv)
+    assert np.array_equal(np.asarray(t.vars["chi"][k]).reshape(-1), wc, equal_nan=True)
+    assert np.array_equal(np.asarray(t.vars["rh_mid"][k]).reshape(-1), wr)
+    # ---- a second call finds the caches and does nothing (env_wind.py:85-87, calc_thermo.py:80-81) ----
+    driver.compute_downscaling_inputs(eng, cfg)
+    assert "Saved" not in capsys.readouterr().out
+
+
+def test_decode_cf_masks_and_scales():
+    from tropical_cyclone_risk_b200 import driver
+    raw = np.array([-32767, 0, 100], dtype=np.int16)
+    out = driver.decode_cf(raw, {"scale_factor": 0.5, "add_offset": 10.0, "_FillValue": np.int16(-32767)})
+    assert np.isnan(out[0]) and out[1] == 10.0 and out[2] == 60.0 and out.dtype == np.float32
+    assert np.array_equal(driver.decode_cf(np.array([1.5, 2.5], np.float32), {}), [1.5, 2.5])
