@@ -170,3 +170,34 @@ def test_h5lite_refuses_what_it_does_not_understand(tmp_path):
     p.write_bytes(b"not a netcdf file at all")
     with pytest.raises(ValueError):
         refdata.open_variables(str(p))
+
+
+@needs_ref
+def test_oracle_year_on_the_reference_static_data():
+    """The reference's real bathymetry, land mask, basin masks (from land.nc) and Levitus climatologies, under a
+    synthetic atmosphere: a North Atlantic year forms its storms over open water in the tropical Atlantic."""
+    from oracle import tcr_oracle as orc
+    from tropical_cyclone_risk_b200 import fields, params, refdata, synth
+    from tropical_cyclone_risk_b200 import namelist as nl
+    ri = refdata.ReferenceInputs(REF)
+    st = ri.static()
+    bounds = params.basin_bounds(nl, "NA")
+    stat = fields.prepare_static(bounds, st)
+    mlon, mlat, m = fields.crop_to_basin(st["lon_m"], st["lat_m"], fields.mask_planes(st, "NA"), bounds)
+    olon, olat, mld, strat = ri.ocean()
+    lon, lat = synth.era5_axes()
+    planes = []
+    for month in range(1, 13):
+        raw = synth.synth_month_raw(2001, month, lon, lat)
+        lon_b, lat_b, pl = fields.prepare_month(nl, bounds, lon, lat, raw, olon, olat, mld[month - 1], strat[month - 1])
+        planes.append(pl)
+    env = orc.OracleEnv(lon_b, lat_b, np.stack(planes), stat)
+    masks = orc.Masks(mlon, mlat, np.ascontiguousarray(m, dtype=np.uint8))
+    r = orc.run_year(params.params_from_namelist(nl, "NA"), env, 0, masks, 20260101, 2001, 12, chunk=4096, n_threads=4)
+    lon0, lat0 = r["lon"][:, 0], r["lat"][:, 0]
+    assert not np.isnan(lon0).any() and np.nanmax(r["vmax"]) >= 18.0
+    assert (lon0 > 262).all() and (lon0 < 358).all() and (lat0 > 3).all() and (lat0 < 45).all()
+    # genesis points are over water according to the reference's own land mask
+    ix = np.rint((lon0 - st["lon_l"][0]) / (st["lon_l"][1] - st["lon_l"][0])).astype(int)
+    iy = np.rint((lat0 - st["lat_l"][0]) / (st["lat_l"][1] - st["lat_l"][0])).astype(int)
+    assert (st["land"][iy, ix] == 0).all()
