@@ -142,3 +142,51 @@ def test_decode_cf_masks_and_scales():
     out = driver.decode_cf(raw, {"scale_factor": 0.5, "add_offset": 10.0, "_FillValue": np.int16(-32767)})
     assert np.isnan(out[0]) and out[1] == 10.0 and out[2] == 60.0 and out.dtype == np.float32
     assert np.array_equal(driver.decode_cf(np.array([1.5, 2.5], np.float32), {}), [1.5, 2.5])
+
+
+def _rank_worker(rank, world, port, base, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pathlib
+        from conftest import golden
+        from tropical_cyclone_risk_b200 import driver
+        cfg = _namelist(pathlib.Path(base))
+        cfg.output_directory = os.path.join(base, "out_w2")
+        g = golden("ref_thermo.npz")
+        driver.compute_downscaling_inputs(OracleEngine((g["table_p"], g["table_s"], g["table_T"])), cfg)
+        dist.barrier()
+        q.put(rank)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_compute_downscaling_inputs_gloo_world2_matches_single_rank(era5_tree, tmp_path):
+    """Months / time samples sharded over two ranks (gloo), rank 0 writes: the same cache files as one rank."""
+    import socket
+    import torch.multiprocessing as mp
+    from conftest import golden
+    from tropical_cyclone_risk_b200 import driver, layout, refdata
+    cfg, _ = era5_tree
+    g = golden("ref_thermo.npz")
+    driver.compute_downscaling_inputs(OracleEngine((g["table_p"], g["table_s"], g["table_T"])), cfg)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    assert sorted(q.get(timeout=180) for _ in range(2)) == [0, 1]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    cfg2 = _namelist(tmp_path)
+    cfg2.output_directory = str(tmp_path / "out_w2")
+    for fn, names in ((driver.get_env_wnd_fn, layout.FIELD_NAMES[:14]), (driver.get_fn_thermo, ("vmax", "chi", "rh_mid"))):
+        a, b = refdata._Cache(fn(cfg), names), refdata._Cache(fn(cfg2), names)
+        assert a.times == b.times
+        for n in names:
+            assert np.array_equal(a.vars[n], b.vars[n], equal_nan=True), n
