@@ -12,8 +12,8 @@ and writes, in an image that has no netCDF4 / h5py / libhdf5:
 Implemented from the published HDF5 File Format Specification (version 3.0); nothing here is derived from the
 reference.  Supported: fixed-point and IEEE floating-point datasets of any rank (little / big endian), fixed-length
 strings, variable-length strings through the global heap; data layouts compact / contiguous / chunked (version-1
-chunk B-tree) with the deflate, shuffle and fletcher32 filters; attributes of those types.  Anything else raises
-NotImplementedError rather than guessing.
+chunk B-tree) with the deflate, shuffle and fletcher32 filters; attributes of those types stored compactly (up to
+eight per object).  Anything else raises NotImplementedError rather than guessing.
 """
 import struct
 import zlib
@@ -57,6 +57,8 @@ class Dataset:
             elif mtype == 0x0C:
                 k, v = f._attribute(body)
                 self.attrs[k] = v
+            elif mtype == 0x15:
+                f._refuse_dense_attributes(body, self.name)
 
     @property
     def is_dataset(self):
@@ -276,7 +278,17 @@ class File:
             elif mtype == 0x0C:
                 k, v = self._attribute(body)
                 attrs[k] = v
+            elif mtype == 0x15:
+                self._refuse_dense_attributes(body, "group")
         return links, attrs
+
+    def _refuse_dense_attributes(self, body, what):
+        """Attribute-info message: more than eight attributes are kept in a fractal heap, which this reader does not
+        walk -- silently dropping them could lose a scale_factor, so refuse."""
+        flags = body[1]
+        heap = _u(body, 2 + (2 if flags & 1 else 0), 8)
+        if heap != UNDEF:
+            raise NotImplementedError("%s keeps its attributes in dense storage (more than 8 attributes)" % what)
 
     def _symtab(self, btree, heap, links):
         b = self.buf
