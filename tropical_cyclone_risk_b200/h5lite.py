@@ -52,6 +52,8 @@ class Dataset:
                 self.dtype, self._vlen_str = f._datatype(body)
             elif mtype == 0x08:
                 self._layout = body
+            elif mtype == 0x05:
+                self._fill = self._fill_value(body)
             elif mtype == 0x0B:
                 self._filters = f._filters(body)
             elif mtype == 0x0C:
@@ -105,8 +107,28 @@ class Dataset:
             raise NotImplementedError("version-%d layout class %d" % (ver, cls))
         raise NotImplementedError("data layout message version %d (HDF5 1.10 chunk indexes)" % ver)
 
+    @staticmethod
+    def _fill_value(body):
+        """Raw bytes of the dataset's fill value (fill value message, versions 1-3), or None."""
+        ver = body[0]
+        if ver in (1, 2):
+            if ver == 2 and not body[3]:
+                return None
+            size = _u(body, 4, 4)
+            return bytes(body[8:8 + size]) if size else None
+        if ver == 3:
+            if not (body[1] & 0x20):
+                return None
+            size = _u(body, 2, 4)
+            return bytes(body[6:6 + size]) if size else None
+        return None
+
     def _filled(self, n):
-        return np.zeros(n, dtype=self.dtype)
+        """What unwritten storage reads as: the fill value if the dataset defines one, else zeros."""
+        out = np.zeros(n, dtype=self.dtype)
+        if self._fill is not None and len(self._fill) == self.dtype.itemsize and not self._vlen_str:
+            out[:] = np.frombuffer(self._fill, dtype=self.dtype, count=1)[0]
+        return out
 
     def _finish(self, flat):
         a = np.array(flat).reshape(self.shape if self.shape else ())
@@ -122,7 +144,7 @@ class Dataset:
         rank = len(shape)
         if len(cdims) != rank:
             raise H5Error("chunk rank mismatch in %s" % self.name)
-        out = np.zeros(shape, dtype=self.dtype)
+        out = self._filled(int(np.prod(shape, dtype=np.int64))).reshape(shape)
         if btree == UNDEF:
             return out.reshape(-1)
         csize = int(np.prod(cdims)) * self.dtype.itemsize
