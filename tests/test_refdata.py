@@ -201,3 +201,25 @@ def test_oracle_year_on_the_reference_static_data():
     ix = np.rint((lon0 - st["lon_l"][0]) / (st["lon_l"][1] - st["lon_l"][0])).astype(int)
     iy = np.rint((lat0 - st["lat_l"][0]) / (st["lat_l"][1] - st["lat_l"][0])).astype(int)
     assert (st["land"][iy, ix] == 0).all()
+
+
+@needs_ref
+def test_h5lite_attribute_span_matches_real_attribute_messages():
+    """Dense attribute storage (objects with more than eight attributes) is walked with the same fractal-heap code as
+    the dense links of the sample track files plus a per-message length computed from the message's own header; that
+    length is checked here against every compact attribute message of two real files (both header generations)."""
+    from tropical_cyclone_risk_b200 import h5lite
+    n = 0
+    for path in (os.path.join(REF, "intensity", "data", "mld_climatology.nc"),
+                 os.path.join(REF, "notebooks", "data", "tracks_NA_era5_197901_202312.nc")):
+        f = h5lite.File(path)
+        for name in f.keys():
+            for mtype, body in f._object_header(f._links[name]):
+                if mtype != 0x0C:
+                    continue
+                probe = h5lite.File.__new__(h5lite.File)
+                probe.buf, probe.osz, probe.lsz = bytes(body) + b"\0" * 16, 8, 8
+                used = probe._attribute_span(0)[0]                      # DIMENSION_LIST (vlen of references) included
+                assert 0 <= len(body) - used < 8, (path, name, len(body), used)
+                n += 1
+    assert n > 60

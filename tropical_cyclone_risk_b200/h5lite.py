@@ -12,8 +12,7 @@ and writes, in an image that has no netCDF4 / h5py / libhdf5:
 Implemented from the published HDF5 File Format Specification (version 3.0); nothing here is derived from the
 reference.  Supported: fixed-point and IEEE floating-point datasets of any rank (little / big endian), fixed-length
 strings, variable-length strings through the global heap; data layouts compact / contiguous / chunked (version-1
-chunk B-tree) with the deflate, shuffle and fletcher32 filters; attributes of those types stored compactly (up to
-eight per object).  Anything else raises NotImplementedError rather than guessing.
+chunk B-tree) with the deflate, shuffle and fletcher32 filters; attributes of those types, compact or dense (fractal heap).  Anything else raises NotImplementedError rather than guessing.
 """
 import struct
 import zlib
@@ -60,7 +59,7 @@ class Dataset:
                 k, v = f._attribute(body)
                 self.attrs[k] = v
             elif mtype == 0x15:
-                f._refuse_dense_attributes(body, self.name)
+                self.attrs.update(f._dense_attributes(body, self.name))
 
     @property
     def is_dataset(self):
@@ -301,16 +300,24 @@ class File:
                 k, v = self._attribute(body)
                 attrs[k] = v
             elif mtype == 0x15:
-                self._refuse_dense_attributes(body, "group")
+                attrs.update(self._dense_attributes(body, "group"))
         return links, attrs
 
-    def _refuse_dense_attributes(self, body, what):
-        """Attribute-info message: more than eight attributes are kept in a fractal heap, which this reader does not
-        walk -- silently dropping them could lose a scale_factor, so refuse."""
+    def _dense_attributes(self, body, what):
+        """Attribute-info message: more than eight attributes live in a fractal heap.  Returns {name: value}; if the
+        heap cannot be walked the object is refused (dropping attributes silently could lose a scale_factor)."""
         flags = body[1]
         heap = _u(body, 2 + (2 if flags & 1 else 0), 8)
-        if heap != UNDEF:
-            raise NotImplementedError("%s keeps its attributes in dense storage (more than 8 attributes)" % what)
+        out = {}
+        if heap == UNDEF:
+            return out
+        try:
+            for obj in self._fractal_heap_objects(heap, "attr"):
+                k, v = self._attribute(obj)
+                out[k] = v
+        except (H5Error, NotImplementedError, IndexError, ValueError, UnicodeDecodeError) as e:
+            raise NotImplementedError("%s keeps its attributes in dense storage that this reader cannot walk (%s)" % (what, e))
+        return out
 
     def _symtab(self, btree, heap, links):
         b = self.buf
@@ -361,8 +368,11 @@ class File:
         return name, _u(body, off, 8)
 
     # -- fractal heap (dense link / attribute storage) ------------------------------------------------
-    def _fractal_heap_objects(self, addr):
-        """Every managed object of a fractal heap, in storage order (what dense groups keep their link messages in)."""
+    def _fractal_heap_objects(self, addr, kind="link"):
+        """Every managed object of a fractal heap, in storage order: the link messages of a dense group (kind "link")
+        or the attribute messages of an object with more than eight attributes (kind "attr")."""
+        span = self._link_span if kind == "link" else self._attribute_span
+        starts = (1,) if kind == "link" else (1, 2, 3)                 # message version bytes; free space is zero-filled
         b = self.buf
         if b[addr:addr + 4] != b"FRHP":
             raise H5Error("bad fractal heap header")
@@ -393,9 +403,11 @@ class File:
                 raise H5Error("bad fractal heap direct block")
             q = baddr + 5 + 8 + off_bytes + (4 if checksummed else 0)
             end = baddr + bsize
-            # managed objects are link messages packed back to back; free space is zero-filled
-            while q < end and b[q] == 1:                              # link message version 1
-                _, naddr, used = self._link_span(q)
+            # managed objects are packed back to back from the start of the block; free space is zero-filled
+            while q < end and b[q] in starts:
+                used = span(q)[-1]
+                if used <= 0 or q + used > end:
+                    raise H5Error("fractal heap object overruns its block")
                 objs.append(b[q:q + used])
                 q += used
 
@@ -450,6 +462,22 @@ class File:
         else:
             off += 2 + _u(b, off, 2)
         return name, addr, off - q
+
+    def _attribute_span(self, q):
+        """(bytes used,) of the attribute message starting at buffer offset q (dense attribute storage)."""
+        b = self.buf
+        ver = b[q]
+        nsz, tsz, ssz = _u(b, q + 2, 2), _u(b, q + 4, 2), _u(b, q + 6, 2)
+        off = q + 8 + (1 if ver == 3 else 0)
+        pad = (lambda x: (x + 7) // 8 * 8) if ver == 1 else (lambda x: x)
+        if nsz == 0 or nsz > 1024 or tsz == 0 or tsz > 4096 or ssz > 4096:
+            raise H5Error("implausible attribute message in a fractal heap")
+        t0 = off + pad(nsz)
+        esize = _u(b, t0 + 4, 4)                                        # element size: every datatype class keeps it here
+        shape = self._dataspace(b[t0 + pad(tsz):t0 + pad(tsz) + ssz]) if ssz else ()
+        n = int(np.prod(shape, dtype=np.int64)) if shape else (0 if shape is None else 1)
+        end = t0 + pad(tsz) + pad(ssz) + n * esize
+        return (end - q,)
 
     # -- message decoders -----------------------------------------------------------------------------
     def _dataspace(self, body):
