@@ -190,3 +190,19 @@ def test_compute_downscaling_inputs_gloo_world2_matches_single_rank(era5_tree, t
         assert a.times == b.times
         for n in names:
             assert np.array_equal(a.vars[n], b.vars[n], equal_nan=True), n
+
+
+def test_the_reference_namelist_is_accepted_unchanged():
+    """namelist.py of a reference checkout drives everything here as it is (build container only)."""
+    import os
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not present")
+    from tropical_cyclone_risk_b200 import driver, params
+    nl = driver.load_namelist(os.path.join(rh.REF_ROOT, "namelist.py"))
+    p = params.params_from_namelist(nl, "NA")
+    assert p.n_steps == 361 and p.dt_track == 3600.0
+    assert params.basin_bounds(nl, "NA") == (260.0, 0.0, 360.0, 60.0)
+    assert driver.get_env_wnd_fn(nl).endswith("env_wnd_era5_201601_202112.nc")
+    assert driver.get_fn_thermo(nl).endswith("thermo_era5_201601_202112.nc")
+    assert nl.var_keys[nl.dataset_type]["mslp"] == "sp" and nl.select_thermo == 1 and nl.select_interp == 2
