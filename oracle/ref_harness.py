@@ -114,9 +114,10 @@ def injected_phases(phases):
         np.random.rand = orig
 
 
-def gen_track(ref, f, lon0, lat0, v0, m0, phases, h_bl):
+def gen_track(ref, f, lon0, lat0, v0, m0, phases, h_bl, post=True):
     """Reference gen_track + the per-candidate post-processing of run_tracks
-    (util/compute.py:178-206), computed for every storm that returned a result."""
+    (util/compute.py:178-206), computed for every storm that returned a result
+    (post=False: the integration only)."""
     nl = ref.namelist
     f.h_bl = h_bl
     with injected_phases(phases):
@@ -125,6 +126,8 @@ def gen_track(ref, f, lon0, lat0, v0, m0, phases, h_bl):
         return dict(status=2, nfev=0, n_time=0)
     out = dict(status=int(res.status), nfev=int(res.nfev), n_time=int(res.t.size),
                t=res.t.copy(), y=res.y.copy())
+    if not post:
+        return out
     lon_t, lat_t, v_t = res.y[0], res.y[1], res.y[2]
     v_2d = np.interp(2 * 24 * 60 * 60, res.t, v_t.flatten())
     is_tc = bool(np.logical_and(np.any(v_t >= nl.seed_v_threshold_ms), v_2d >= nl.seed_v_2d_threshold_ms))

@@ -183,7 +183,7 @@ def test_oracle_year_on_the_reference_static_data():
     st = ri.static()
     bounds = params.basin_bounds(nl, "NA")
     stat = fields.prepare_static(bounds, st)
-    mlon, mlat, m = fields.crop_to_basin(st["lon_m"], st["lat_m"], fields.mask_planes(st, "NA"), bounds)
+    mlon, mlat, m = fields.crop_masks(st, "NA", bounds)
     olon, olat, mld, strat = ri.ocean()
     lon, lat = synth.era5_axes()
     planes = []

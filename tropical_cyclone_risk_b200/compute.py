@@ -89,7 +89,7 @@ class _Session:
             eng = Engine(p, device=device)
             st = self.inputs.static()
             eng.upload_static(fields.prepare_static(bounds, st))
-            mlon, mlat, m = fields.crop_to_basin(st["lon_m"], st["lat_m"], fields.mask_planes(st, basin_id), bounds)
+            mlon, mlat, m = fields.crop_masks(st, basin_id, bounds, p)
             eng.upload_masks(mlon, mlat, m)
             self.engines[key] = (eng, bounds)
         return self.engines[key]

@@ -10,24 +10,48 @@
 /* ======================================================================================== */
 /* table builders: planes -> cell records                                                    */
 /* ======================================================================================== */
-/* one month: planes [19][nlat][nlon] float32 -> rec [ncy][ncx][20] float4 (corner quads)      */
-/* blockIdx.y = month of a batch: planes [n][19][nlat][nlon] -> rec [n][ncy][ncx][20] */
-__global__ void k_build_month(const float* __restrict__ planes, float4* __restrict__ rec, int nlat, int nlon)
+/* one month: planes [19][nlat][nlon] float32 -> rec [ncy][ncx][20] float4 (corner quads) and the
+ * integrator's widened twin recb [ncy][ncx][20] uint4 (tcr_device.cuh "integrator records")      */
+/* blockIdx.y = month of a batch: planes [n][19][nlat][nlon] -> rec / recb [n][ncy][ncx][20] */
+__device__ __forceinline__ float4 tcr_plane_quad(const float* __restrict__ planes, int ch, int nlat, int nlon, int iy, int ix)
+{
+    const float* p = planes + (size_t)ch * nlat * nlon + (size_t)iy * nlon + ix;
+    return make_float4(p[0], p[nlon], p[1], p[nlon + 1]);
+}
+
+__global__ void k_build_month(const float* __restrict__ planes, float4* __restrict__ rec, uint4* __restrict__ recb, int nlat, int nlon)
 {
     const int ncx = nlon - 1, ncy = nlat - 1;
     const size_t total = (size_t)ncx * ncy * TCR_REC_F4;
     planes += (size_t)blockIdx.y * TCR_N_FIELDS * nlat * nlon;
     rec += (size_t)blockIdx.y * total;
+    recb += (size_t)blockIdx.y * total;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int ch = (int)(idx % TCR_REC_F4);
         size_t cell = idx / TCR_REC_F4;
         int ix = (int)(cell % ncx), iy = (int)(cell / ncx);
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ch < TCR_N_FIELDS) {
-            const float* p = planes + (size_t)ch * nlat * nlon + (size_t)iy * nlon + ix;
-            r = make_float4(p[0], p[nlon], p[1], p[nlon + 1]);
-        }
+        if (ch < TCR_N_FIELDS) r = tcr_plane_quad(planes, ch, nlat, nlon, iy, ix);
         rec[idx] = r;
+        uint4 b;
+        if (ch < TCR_RECB_CH) {
+            /* high words of the exactly widened corners */
+            b = make_uint4((uint32_t)__double2hiint((double)r.x), (uint32_t)__double2hiint((double)r.y),
+                           (uint32_t)__double2hiint((double)r.z), (uint32_t)__double2hiint((double)r.w));
+        } else {
+            /* slots 18, 19: the three mantissa bits of every corner that do not fit the high word; value
+             * v = 4 * channel + corner sits in word v / 10 at bits 3 * (v % 10) .. + 2 */
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            const int w0 = (ch - TCR_RECB_CH) * 4;
+            for (int v = w0 * 10; v < (w0 + 4) * 10 && v < 4 * TCR_RECB_CH; ++v) {
+                const float4 q = tcr_plane_quad(planes, v >> 2, nlat, nlon, iy, ix);
+                const float f = (v & 3) == 0 ? q.x : (v & 3) == 1 ? q.y : (v & 3) == 2 ? q.z : q.w;
+                const uint32_t low3 = (uint32_t)__double2loint((double)f) >> 29;
+                w[v / 10 - w0] |= low3 << (3 * (v % 10));
+            }
+            b = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        recb[idx] = b;
     }
 }
 
@@ -748,15 +772,19 @@ enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
  * table is read from HBM/L2 (64 B per evaluation); only emitted samples go to HBM.
  * THREADS x MINB fixes the register budget (launch bounds): <256,1> 255 registers, <128,3> 168,
  * <128,4> 128 -- chosen at run time by tcr_set_tuning, default by measurement.   */
-template <int THREADS, int MINB, int KSMEM, int CTA_LOCKSTEP>
+template <int THREADS, int MINB, int KSMEM, int CTA_LOCKSTEP, int REC>
 __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
 {
+    static_assert(REC != 2 || KSMEM == 2, "record staging lives behind the eight stage vectors");
     /* Stage storage, "stage" j = 0..7: K0 (FSAL derivative), K1..K5, K6, and the step's end state y_new.
      * KSMEM = 1: K1..K5 (dead during an RHS evaluation) live in shared memory, [stage][component][thread],
      * which frees 40 registers; KSMEM = 2: all eight (64 registers); KSMEM = 0: registers only. */
     extern __shared__ __align__(16) double k_smem[];
     double Kr[8][4] = {};
     double* const ks = k_smem + (KSMEM ? threadIdx.x : 0);
+    /* REC == 2: this thread's column of the record staging area [20][THREADS] uint4, which shares its first
+     * 17 x THREADS doubles with the drain-phase packing (used only between macro steps, behind CTA barriers) */
+    uint4* const rs = reinterpret_cast<uint4*>(k_smem + 32 * THREADS) + threadIdx.x;
     auto in_smem = [](int j) { return KSMEM == 2 || (KSMEM == 1 && j >= 1 && j <= 5); };
     auto k_off = [](int j, int i) { return ((KSMEM == 2 ? j : j - 1) * 4 + i) * THREADS; };
     auto Kg = [&](int j, int i) -> double { return in_smem(j) ? ks[k_off(j, i)] : Kr[j][i]; };
@@ -977,7 +1005,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
 
             double dy[4] = {0, 0, 0, 0};
             TcrRhsAux aux = {0, 0, 0};
-            if (ev) { tcr_rhs(cx, ym, ftab, hbl, te, ye, dy, aux); ++nfev; }
+            if (ev) { tcr_rhs<REC>(cx, ym, ftab, hbl, te, ye, dy, aux, rs, THREADS); ++nfev; }
 
             /* ---- consume ---- */
             if (mode == M_RK) {

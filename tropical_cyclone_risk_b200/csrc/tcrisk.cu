@@ -115,7 +115,7 @@ struct tcr_handle {
     size_t smem_optin = 0;
     int64_t launches = 0;
     /* tables */
-    DevBuf rec, stage, prep;
+    DevBuf rec, recb, stage, prep;     /* rec: float32 cell records; recb: the integrator's widened twin */
     AxisBuf ax_lon, ax_lat;
     int nlat = 0, nlon = 0, n_ym = 0;
     size_t month_f4 = 0;
@@ -280,7 +280,7 @@ int tcr_destroy(tcr_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     h->ws.release_all();
-    DevBuf* bufs[] = {&h->rec, &h->stage, &h->prep, &h->bathy, &h->land, &h->masks, &h->sincos};
+    DevBuf* bufs[] = {&h->rec, &h->recb, &h->stage, &h->prep, &h->bathy, &h->land, &h->masks, &h->sincos};
     for (DevBuf* b : bufs) b->release();
     AxisBuf* axs[] = {&h->ax_lon, &h->ax_lat, &h->ax_lon_b, &h->ax_lat_b, &h->ax_lon_l, &h->ax_lat_l, &h->ax_lon_m, &h->ax_lat_m};
     for (AxisBuf* a : axs) a->buf.release();
@@ -310,7 +310,7 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 {
     if (!h) return set_err("null handle");
     if (integ_variant > 0) {
-        if (integ_variant > 21) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
+        if (integ_variant > 24) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
         h->integ_variant = integ_variant - 1;
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
@@ -430,9 +430,11 @@ int tcr_alloc_tables(tcr_handle* h, int n_ym, int nlat, int nlon, const double* 
     if (make_axis(h, lon, nlon, h->ax_lon, tb.lon) || make_axis(h, lat, nlat, h->ax_lat, tb.lat)) return -1;
     h->month_f4 = (size_t)(nlat - 1) * (nlon - 1) * TCR_REC_F4;
     if (h->rec.ensure(h->month_f4 * sizeof(float4) * (size_t)n_ym)) return -1;
+    if (h->recb.ensure(h->month_f4 * sizeof(uint4) * (size_t)n_ym)) return -1;
     if (h->stage.ensure((size_t)TCR_N_FIELDS * nlat * nlon * sizeof(float))) return -1;
     h->nlat = nlat; h->nlon = nlon; h->n_ym = n_ym;
     tb.rec = h->rec.as<float4>();
+    tb.recb = h->recb.as<uint4>();
     tb.ncx = nlon - 1; tb.ncy = nlat - 1; tb.n_ym = n_ym;
     return 0;
 }
@@ -446,7 +448,7 @@ int tcr_upload_month_dev(tcr_handle* h, int ym, const float* d_planes)
     {
         LaunchTimer lt_(h, TCR_K_BUILD);
         k_build_month<<<grid_for(h->month_f4, 256, h->num_sms), 256, 0, h->stream>>>(
-            d_planes, h->rec.as<float4>() + h->month_f4 * (size_t)ym, h->nlat, h->nlon);
+            d_planes, h->rec.as<float4>() + h->month_f4 * (size_t)ym, h->recb.as<uint4>() + h->month_f4 * (size_t)ym, h->nlat, h->nlon);
     }
     CKK(h);
     return 0;
@@ -465,7 +467,8 @@ int tcr_upload_months(tcr_handle* h, int ym0, int n_months, const float* planes)
     {
         LaunchTimer lt_(h, TCR_K_BUILD);
         dim3 grid((unsigned)grid_for(h->month_f4, 256, h->num_sms), (unsigned)n_months);
-        k_build_month<<<grid, 256, 0, h->stream>>>(h->stage.as<float>(), h->rec.as<float4>() + h->month_f4 * (size_t)ym0, h->nlat, h->nlon);
+        k_build_month<<<grid, 256, 0, h->stream>>>(h->stage.as<float>(), h->rec.as<float4>() + h->month_f4 * (size_t)ym0,
+                                               h->recb.as<uint4>() + h->month_f4 * (size_t)ym0, h->nlat, h->nlon);
     }
     CKK(h);
     return 0;
@@ -618,7 +621,7 @@ static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned i
 
 }  // extern "C"
 
-template <int THREADS, int MINB, int KSMEM, int LOCKSTEP = 0>
+template <int THREADS, int MINB, int KSMEM, int LOCKSTEP = 0, int REC = 1>
 static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_upper)
 {
     const int warps_per_cta = THREADS / 32;
@@ -628,11 +631,13 @@ static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_uppe
     int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
     a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
     { static const int pack_on = getenv("TCR_NO_PACK") ? 0 : 1; a.pack = pack_on; }
-    /* KSMEM 2: eight stage vectors + the 17-word staging area of the drain-phase packing */
-    const size_t smem = KSMEM == 2 ? (size_t)(32 + 17) * THREADS * sizeof(double) : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
-    cudaFuncSetAttribute(k_integrate<THREADS, MINB, KSMEM, LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    /* KSMEM 2: eight stage vectors + the 17-word staging area of the drain-phase packing, which the record
+     * staging of REC 2 (20 x 16 B per thread) overlays */
+    const size_t smem = KSMEM == 2 ? (size_t)(32 + (REC == 2 ? 40 : 17)) * THREADS * sizeof(double)
+                                   : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
+    cudaFuncSetAttribute(k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     LaunchTimer lt_(h, TCR_K_INTEGRATE);
-    k_integrate<THREADS, MINB, KSMEM, LOCKSTEP><<<grid, THREADS, smem, h->stream>>>(h->ctx, a);
+    k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC><<<grid, THREADS, smem, h->stream>>>(h->ctx, a);
 }
 
 static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
@@ -659,6 +664,9 @@ static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
     case 18: launch_integrate_variant<192, 3, 2, 63>(h, a, n_upper); break;      /* 96 registers, 18 warps/SM */
     case 19: launch_integrate_variant<224, 2, 2, 63>(h, a, n_upper); break;      /* 144 registers, 14 warps/SM */
     case 20: launch_integrate_variant<384, 1, 2, 63>(h, a, n_upper); break;      /* one 12-warp CTA per SM */
+    case 21: launch_integrate_variant<192, 2, 2, 63, 0>(h, a, n_upper); break;   /* round-1 record path (float32 records, F2F) */
+    case 22: launch_integrate_variant<192, 2, 2, 63, 2>(h, a, n_upper); break;   /* records staged in shared memory by cp.async */
+    case 23: launch_integrate_variant<384, 1, 2, 63, 2>(h, a, n_upper); break;
     default: return set_err("unknown integrate variant %d", h->integ_variant);
     }
     CKK(h);

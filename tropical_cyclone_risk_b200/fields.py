@@ -117,6 +117,24 @@ def prepare_static(bounds, static):
                 lon_l=lon_l, lat_l=lat_l, land=np.ascontiguousarray(land, dtype=np.int8))
 
 
+def crop_masks(static, run_basin_id, bounds, p=None):
+    """The 8 genesis mask planes on the part of their global grid a seed attempt can query.
+
+    The reference samples the GLOBAL 0.25-degree masks (util/compute.py:87-97, 146, 156-157).  The first
+    draw of an attempt is latitude-weighted over [lat_min, lat_max] of :140-141 -- which, through np.sign(-0.0)
+    >= 0, reaches 45 N for the southern basins whose box ends at '0S' -- so the crop must cover that range as
+    well as the basin box: a query outside a narrower crop would be clamped to its edge row and read ocean
+    where the global mask reads 0.  Returns (lon_m, lat_m, planes uint8 [8][nlat][nlon])."""
+    lat_lo, lat_hi = bounds[1], bounds[3]
+    if p is not None:
+        lat_lo, lat_hi = min(lat_lo, float(p.gen_lat_min)), max(lat_hi, float(p.gen_lat_max))
+    else:
+        lat_lo, lat_hi = min(lat_lo, -45.0), max(lat_hi, 45.0)
+    wide = (bounds[0], lat_lo, bounds[2], lat_hi)
+    mlon, mlat, m = crop_to_basin(static["lon_m"], static["lat_m"], mask_planes(static, run_basin_id), wide)
+    return mlon, mlat, np.ascontiguousarray(m, dtype=np.uint8)
+
+
 def mask_planes(static, run_basin_id):
     """uint8 [8][nlat_m][nlon_m]: layout.BASIN_IDS order then the run basin's mask."""
     if run_basin_id == "GL":

@@ -92,7 +92,7 @@ def _check_minit(namelist):
     return amp, center, slope, offset
 
 
-def params_from_namelist(namelist, basin_id, max_redraws=16):
+def params_from_namelist(namelist, basin_id, max_redraws=64):
     """Build the POD parameter block for one run basin from a reference-style namelist module."""
     if list(namelist.steering_levels) != [250, 850]:
         raise NotImplementedError("only the two-level (250/850 hPa) steering configuration is built")

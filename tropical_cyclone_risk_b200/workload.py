@@ -43,8 +43,7 @@ class Workload:
         st = synth.synth_static(full_res=full_res)
         self.static_global = st
         self.static = fields.prepare_static(self.bounds, st)
-        mlon, mlat, m = fields.crop_to_basin(st["lon_m"], st["lat_m"], fields.mask_planes(st, basin), self.bounds)
-        self.mask_lon, self.mask_lat, self.mask_planes = mlon, mlat, np.ascontiguousarray(m, dtype=np.uint8)
+        self.mask_lon, self.mask_lat, self.mask_planes = fields.crop_masks(st, basin, self.bounds, self.p)
 
     @property
     def n_ym(self):
