@@ -7,9 +7,13 @@
 
 One *step* = one pass of the hot path over one batch: `tcr_run_years` for the workload's years
 (seeding -> adaptive-RK45 integration -> post-processing -> ordered selection -> 9-tuple).
-Workload at every N: BASELINE.json configs[1] per GPU -- NA basin, 10 years, 1000 tracks/year,
-361 output steps, ERA5-shaped synthetic monthly tables (weak scaling: rank r owns its own 10
-years; the only collective is the all-gather of finished tracks at write-out).
+Workload (defaults; --basin / --years / --tracks / --interval override, and the label in `config.workload` is derived
+from what actually ran):
+  N = 1   BASELINE.json configs[2], the largest single-GPU configuration: GL all-basin, 40 years, 5000 tracks/year,
+          361 output steps, all 480 ERA5-shaped synthetic month tables resident in HBM (9.9 GB of cell records)
+  N > 1   BASELINE.json configs[3] sharded by whole years, weak scaling: every rank owns 5 GL years x 20000
+          tracks/year (at N = 8 that is configs[3] itself: 40 years x 20000); the only collective is the all-gather
+          of finished tracks at write-out, inside the timed region of every step.
 
 A *storm-step* is one emitted output sample of one integrated seed:
 stats.storm_steps counts the samples of every gen_track call the sequential reference loop
@@ -45,8 +49,13 @@ B_PER_STEP_TRACK = 32      # lon, lat, v, m float64 written by the integrator pe
 B_PER_STORM_PICKUP = 1004  # 60 double2 Fourier coefficients + 5 doubles + 1 int per integrated seed
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
 # workload (profiles/r01_prof_integrate_summary.txt, profiles/r01_prof_interp_summary.txt); None for other workloads
-NCU_TRAFFIC = {"k_integrate": 2.061e9 + 1.818e9, "k_env_interp": 10.154e9 + 5.608e9,
-               "k_wind_stats": 1.030e9 + 0.113e9, "k_thermo": 0.2494e9 + 0.0074e9}
+NCU_TRAFFIC = {"k_env_interp": 10.154e9 + 5.608e9, "k_wind_stats": 1.030e9 + 0.113e9, "k_thermo": 0.2494e9 + 0.0074e9}
+# k_integrate, keyed by workload (basin_years_tracks_steps): the committed ncu capture of one launch of THAT workload
+NCU_INTEGRATE = {
+    "NA_10_1000_361": {"source": "profiles/r01_prof_integrate_summary.txt", "traffic": 2.061e9 + 1.818e9,
+                       "fp64_pipe_pct_of_peak": 25.1, "issue_slots_busy_pct": 31.4, "lanes_per_instruction": 23.1,
+                       "l2_hit_pct": 83.4, "dram_pct_of_peak": 4.9, "registers": 168, "warps_per_sm": 12},
+}
 
 
 def load_peaks():
@@ -208,10 +217,42 @@ def bench_namelist(args):
     return cfg
 
 
+def resolve_workload(args):
+    """Fill the workload defaults that depend on N (see the module docstring)."""
+    if args.basin is None:
+        args.basin = "GL"
+    if args.years is None:
+        args.years = 40 if args.gpus == 1 else 5
+    if args.tracks is None:
+        args.tracks = 5000 if args.gpus == 1 else 20000
+    return args
+
+
+def workload_label(args, n_steps):
+    """Name the BASELINE.json config this run corresponds to -- from the arguments, never hard-coded."""
+    b, y, t, n = args.basin, args.years, args.tracks, args.gpus
+    shape = "%s basin, %d years x %d tracks/year per GPU, %d output steps" % (b, y, t, n_steps)
+    if (b, y, t, n_steps) == ("GL", 40, 5000, 361) and n == 1:
+        name = "BASELINE configs[2] (GL all-basin, 40 years, tracks_per_year=5000, 1xB200)"
+    elif (b, t, n_steps) == ("GL", 20000, 361) and y * n == 40:
+        name = "BASELINE configs[3] (GL all-basin, 40 years, tracks_per_year=20000, years sharded over %d GPUs)" % n
+    elif (b, t, n_steps) == ("GL", 20000, 361):
+        name = "BASELINE configs[3] per-rank shard (5 of its 40 GL years x 20000 tracks/year on each of %d GPUs; weak scaling, " \
+               "N = 8 is configs[3] itself)" % n if y == 5 else "GL x 20000 tracks/year (configs[3] shape), %d years per GPU" % y
+    elif (b, y, t, n_steps) == ("NA", 10, 1000, 361):
+        name = "BASELINE configs[1] per GPU (NA, 10 years, tracks_per_year=1000)"
+    elif (b, t, n_steps) == ("WP", 50000, 1441):
+        name = "BASELINE configs[4] shape (WP, tracks_per_year=50000, output_interval_s=900), %d years per GPU" % y
+    elif (b, y, t, n_steps) == ("GL", 1, 100, 361):
+        name = "BASELINE configs[0] (GL, 1 year, tracks_per_year=100)"
+    else:
+        name = "custom"
+    return "%s: %s, ERA5-shaped (1 deg) synthetic env fields, 1 m/s roughness" % (name, shape)
+
+
 def workload_config(args, n_steps):
     return {
-        "workload": "BASELINE configs[1] per GPU: %s basin, %d years, tracks_per_year=%d, %d output steps, "
-                    "ERA5-shaped (1 deg) synthetic env fields, 1 m/s roughness" % (args.basin, args.years, args.tracks, n_steps),
+        "workload": workload_label(args, n_steps),
         "basin": args.basin, "years_per_gpu": args.years, "tracks_per_year": args.tracks, "n_steps": int(n_steps),
         "run_seed": RUN_SEED, "parallelism": "years sharded over ranks; NCCL all-gather of finished tracks at write-out (every step, inside the timed region)",
         "l2": "inputs larger than L2: cell-record tables %d months + result block, see l2_bytes" % (12 * args.years),
@@ -428,42 +469,39 @@ def run_gpu_arm(args):
         storms_all = acc["integrated"] + acc["wasted_integrated"]
         ki_bytes = B_PER_RHS * rhs_all + B_PER_STEP_TRACK * steps_all + B_PER_STORM_PICKUP * storms_all
         ki_ach = ki_bytes / max(ki_n, 1) / (ki_ms / max(ki_n, 1) * 1e-3) / 1e9 if ki_ms > 0 else 0.0
-        std_cfg = args.basin == "NA" and args.years == 10 and args.tracks == 1000
+        cfg_key = "%s_%d_%d_%d" % (args.basin, args.years, args.tracks, ns)
+        ncu = NCU_INTEGRATE.get(cfg_key)
         roof = {"kernel": "k_integrate", "bound": "hbm", "achieved": ki_ach, "peak": peak, "unit": "GB/s",
-                "frac": ki_ach / peak, "traffic": NCU_TRAFFIC["k_integrate"] if std_cfg else None,
-                "traffic_source": "profiles/r01_prof_integrate_summary.txt (ncu --set full, one launch of this workload)",
+                "frac": ki_ach / peak, "traffic": ncu["traffic"] if ncu else None,
                 "algorithmic_bytes_per_launch": ki_bytes / max(ki_n, 1), "peak_source": peak_src,
                 "launches": ki_n, "avg_launch_ms": ki_ms / max(ki_n, 1),
-                "share_of_step": ki_ms / ms, "rhs_per_s": rhs_all / (ki_ms * 1e-3) if ki_ms > 0 else 0.0,
-                "note": "latency / fp64-issue bound kernel (SURVEY 8d): HBM fraction reported for honesty, "
-                        "the HBM-roofline kernel is roofline_interp",
-                "ncu": {"source": "profiles/r01_prof_integrate_summary.txt (ncu --set full of one launch of this workload)",
-                        "fp64_pipe_pct_of_peak": 25.1, "issue_slots_busy_pct": 31.4, "lanes_per_instruction": 23.1,
-                        "l2_hit_pct": 83.4, "dram_pct_of_peak": 4.9, "registers": 168, "warps_per_sm": 12,
-                        "stalls": "fixed-latency fp64 chains 28 %, L2/L1 loads 24 %, CTA barriers (lockstep + drain packing) 18 %, instruction fetch 3 %"}}
-        kernel_share = {k: v[0] / ms for k, v in ktimes.items() if v[1]}
+                "share_of_step": ki_ms / ms, "rhs_per_s": rhs_all / (ki_ms * 1e-3) if ki_ms > 0 else 0.0}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, ns),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e_max / K, "host_check_vmax0": e2e_state["check"],
-                    "pipeline": "download of step i and upload of step i+2's planes overlap the compute of step i+1 "
-                                "(2 result blocks, 2 sets of table slots; every step's H2D and D2H are inside the timed region)"},
+                    "ms_per_step": ms_e_max / K},
             "gpu_launches": launches_all,
             "roofline": roof,
-            "work_per_step": {k: tot[k] / K for k in keys},
-            "waves_per_step": acc["waves"],
-            "kernel_share_of_step": kernel_share,
-            "clocks": clocks,
         }
         line["config"]["l2_bytes"] = {"tables": int(wl.n_ym * (wl.lat.size - 1) * (wl.lon.size - 1) * 320),
                                       "result_block": int(total * 8)}
+        details = {
+            "e2e": {"host_check_vmax0": e2e_state["check"],
+                    "pipeline": "download of step i and upload of step i+2's planes overlap the compute of step i+1 "
+                                "(2 result blocks, 2 sets of table slots; every step's H2D and D2H are inside the timed region)"},
+            "roofline": {"note": "latency / fp64-issue bound kernel (SURVEY 8d): HBM fraction reported because the contract asks for it; "
+                                 "the HBM-roofline kernel is roofline_interp",
+                         "ncu": ncu},
+            "work_per_step": {k: tot[k] / K for k in keys},
+            "waves_per_step": acc["waves"],
+            "kernel_share_of_step": {k: v[0] / ms for k, v in ktimes.items() if v[1]},
+        }
         if not args.no_interp:
-            line["roofline_interp"] = bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args)
-            line["roofline_poi"] = bench_poi(eng, torch, dev, peak, peak_src, ns)
-            line["roofline_windstats"] = bench_windstats(eng, torch, dev, peak, peak_src)
-            line["roofline_thermo"] = bench_thermo(eng, torch, dev, peak, peak_src, cpu=(world == 1 and not args.no_cpu))
+            ri = bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args)
+            details["roofline_interp"] = ri.pop("details")
+            line["roofline_interp"] = ri                                  # compact, ahead of every bulky key
         if world == 1 and not args.no_cpu:
             threads = cpu_threads()
             n_att = args.cpu_attempts or 60000 * threads
@@ -473,8 +511,14 @@ def run_gpu_arm(args):
                 "value": st["storm_steps"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
                 "sample": "oracle port (oracle/tcr_oracle.c), %s year %d, run_seed %d: seed attempts [0, %d) -- seeding + "
                           "gen_track + post-processing of every attempt (%.1f s, %d threads)" % (
-                              args.basin, BASE_YEAR, RUN_SEED, n_att, dt, threads),
+                              args.basin, years[0], RUN_SEED, n_att, dt, threads),
                 "rhs_per_s": st["rhs_evals"] / dt}
+        line["clocks"] = clocks
+        if not args.no_interp:
+            line["roofline_poi"] = bench_poi(eng, torch, dev, peak, peak_src, ns)
+            line["roofline_windstats"] = bench_windstats(eng, torch, dev, peak, peak_src)
+            line["roofline_thermo"] = bench_thermo(eng, torch, dev, peak, peak_src, cpu=(world == 1 and not args.no_cpu))
+        line["details"] = details
         emit(line)
     eng.close()
     if world > 1:
@@ -482,39 +526,55 @@ def run_gpu_arm(args):
 
 
 def bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args):
-    """The stand-alone bilinear sampler on random queries over every resident table (>> L2)."""
+    """The stand-alone bilinear sampler on random queries (>> L2).  Headline: the default kernel over a window of month
+    tables of about 1 GB (8 x L2; every resident table when they are fewer) -- the footprint one year-batch of the
+    integrator touches; the same launch over ALL resident tables (9.9 GB at configs[2], where random 320-byte gathers
+    also run out of TLB reach) is reported next to it in `details`."""
     n = int(args.interp_queries)
+    month_bytes = int((wl.lat.size - 1) * (wl.lon.size - 1) * 320)
+    window = int(min(wl.n_ym, max(12, (1 << 30) // month_bytes)))
     g = torch.Generator(device=dev); g.manual_seed(7)
     b = wl.bounds
     lon = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * (b[2] - b[0]) + b[0]).contiguous()
     lat = (torch.rand(n, generator=g, device=dev, dtype=torch.float64) * (b[3] - b[1]) + b[1]).contiguous()
-    ym = torch.randint(0, wl.n_ym, (n,), generator=g, device=dev, dtype=torch.int32)
     out = torch.empty((n, 21), dtype=torch.float64, device=dev)
-    res = {}
-    for variant, name in ((0, "k_env_interp"), (1, "k_env_interp_tma"), (2, "k_env_interp<4>"), (3, "k_env_interp<5>"),
-                          (4, "k_env_interp_pipe"), (5, "k_env_interp_async<256>"), (6, "k_env_interp_async<128>")):
-        eng.set_interp_variant(variant)
-        for _ in range(3):
-            eng.env_interp_dev(n, ym.data_ptr(), lon.data_ptr(), lat.data_ptr(), out.data_ptr())
-        torch.cuda.synchronize()
-        eng.set_timing(True)
-        reps = 10
-        for _ in range(reps):
-            eng.env_interp_dev(n, ym.data_ptr(), lon.data_ptr(), lat.data_ptr(), out.data_ptr())
-        ms, cnt = eng.kernel_times()["env_interp"]
-        eng.set_timing(False)
-        ach = B_PER_QUERY * n / (ms / cnt * 1e-3) / 1e9
-        res[name] = {"achieved": ach, "frac": ach / peak, "avg_launch_ms": ms / cnt, "launches": cnt}
-    eng.set_interp_variant(0)
-    best = max(res, key=lambda k: res[k]["achieved"])
-    std_cfg = args.basin == "NA" and args.years == 10 and n == (1 << 25)
-    return {"kernel": best, "bound": "hbm", "achieved": res[best]["achieved"], "peak": peak, "unit": "GB/s",
-            "frac": res[best]["frac"], "traffic": NCU_TRAFFIC["k_env_interp"] if std_cfg else None,
-            "traffic_source": "profiles/r01_prof_interp_summary.txt (ncu --set full, one launch of this workload)",
-            "peak_source": peak_src, "queries_per_launch": n,
-            "algorithmic_bytes_per_query": B_PER_QUERY, "moved_bytes_per_query": 320 + 12 + 20 + 168,
-            "table_bytes": int(wl.n_ym * (wl.lat.size - 1) * (wl.lon.size - 1) * 320), "variants": res,
-            "l2": "random queries over all %d month tables (>> 126 MB L2) + %d MB streamed output" % (wl.n_ym, n * 168 >> 20)}
+
+    def run(ym, variants):
+        res = {}
+        for variant, name in variants:
+            eng.set_interp_variant(variant)
+            for _ in range(3):
+                eng.env_interp_dev(n, ym.data_ptr(), lon.data_ptr(), lat.data_ptr(), out.data_ptr())
+            torch.cuda.synchronize()
+            eng.set_timing(True)
+            for _ in range(10):
+                eng.env_interp_dev(n, ym.data_ptr(), lon.data_ptr(), lat.data_ptr(), out.data_ptr())
+            ms, cnt = eng.kernel_times()["env_interp"]
+            eng.set_timing(False)
+            ach = B_PER_QUERY * n / (ms / cnt * 1e-3) / 1e9
+            res[name] = {"achieved": ach, "frac": ach / peak, "avg_launch_ms": ms / cnt, "launches": cnt}
+        eng.set_interp_variant(0)
+        return res
+
+    all_variants = ((0, "k_env_interp"), (1, "k_env_interp_tma"), (2, "k_env_interp<4>"), (3, "k_env_interp<5>"),
+                    (4, "k_env_interp_pipe"), (5, "k_env_interp_async<256>"), (6, "k_env_interp_async<128>"))
+    ym_w = torch.randint(0, window, (n,), generator=g, device=dev, dtype=torch.int32)
+    res = run(ym_w, all_variants)
+    head = res["k_env_interp"]
+    details = {"variants": res, "window_months": window, "window_table_bytes": window * month_bytes,
+               "moved_bytes_per_query": 320 + 12 + 20 + 168,
+               "traffic_source": "profiles/r01_prof_interp_summary.txt (ncu --set full, one launch over 228 MB of tables)"}
+    if window < wl.n_ym:
+        ym_all = torch.randint(0, wl.n_ym, (n,), generator=g, device=dev, dtype=torch.int32)
+        details["all_resident_tables"] = dict(run(ym_all, all_variants[:1])["k_env_interp"], months=wl.n_ym,
+                                              table_bytes=wl.n_ym * month_bytes)
+    return {"kernel": "k_env_interp", "bound": "hbm", "achieved": head["achieved"], "peak": peak, "unit": "GB/s",
+            "frac": head["frac"], "traffic": NCU_TRAFFIC["k_env_interp"] if n == (1 << 25) else None,
+            "avg_launch_ms": head["avg_launch_ms"], "peak_source": peak_src, "queries_per_launch": n,
+            "algorithmic_bytes_per_query": B_PER_QUERY, "table_bytes": window * month_bytes,
+            "l2": "random queries over %d month tables (%d MB >> 126 MB L2) + %d MB streamed output" % (
+                window, window * month_bytes >> 20, n * 168 >> 20),
+            "details": details}
 
 
 def bench_poi(eng, torch, dev, peak, peak_src, ns, n_rows=400000):
@@ -661,16 +721,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--basin", default="NA")
-    ap.add_argument("--years", type=int, default=10, help="years per GPU")
-    ap.add_argument("--tracks", type=int, default=1000, help="tracks per year")
+    ap.add_argument("--basin", default=None, help="run basin (default GL)")
+    ap.add_argument("--years", type=int, default=None, help="years per GPU (default 40 at N = 1, 5 at N > 1)")
+    ap.add_argument("--tracks", type=int, default=None, help="tracks per year (default 5000 at N = 1, 20000 at N > 1)")
     ap.add_argument("--interval", type=int, default=0, help="output_interval_s (0 = namelist default 3600; 900 gives the 1441-step tracks of configs[4])")
     ap.add_argument("--interp-queries", type=float, default=float(1 << 25))
     ap.add_argument("--cpu-attempts", type=int, default=0, help="seed attempts per CPU sample (default scales with threads)")
     ap.add_argument("--integ-variant", type=int, default=0, help="integrate-kernel register variant (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-interp", action="store_true")
-    args = ap.parse_args()
+    args = resolve_workload(ap.parse_args())
     if args.warmup < 3 and args.impl == "b200":
         print("bench.py: note: fewer than 3 warm-up steps", file=sys.stderr)
     if args.impl == "reference":

@@ -752,7 +752,13 @@ struct IntegArgs {
     const int32_t* ym;                 /* [n] table index                                     */
     const double* lon0; const double* lat0; const double* v0; const double* m0; const double* h_bl;
     const double* ftab;                /* [n][n_steps][4] Fourier tables (k_fourier_table)    */
-    double* track;                     /* [n][n_steps][4] lon,lat,v,m                         */
+    double* track;                     /* [n][n_steps][4] lon,lat,v,m -- or, with track_row, a POOL of rows  */
+    /* track pool (tcr_run_years): a storm writes its samples into the row its lane holds; a TC candidate
+     * keeps the row (track_row[slot] = row) and the lane draws a fresh one, every other storm's row is
+     * reused by the lane's next storm -- so rows exist for the lanes in flight plus the candidates (2-3 %
+     * of the storms) instead of for every integrated seed.  pool_ctl[0] = fresh rows handed out so far (row = pool_first + that: rows
+     * below pool_first = the launch's lane count belong to the lanes), pool_ctl[1] = overflow flag (the host re-runs the wave with fewer slots).  */
+    int32_t* track_row; unsigned int* pool_ctl; unsigned int pool_rows; unsigned int pool_first;
     int32_t* n_time; int32_t* status; int32_t* nfev; uint32_t* flags;
     unsigned long long* queue;         /* work counter, zeroed by the host                    */
     int32_t* cand_list; unsigned int* cand_count;   /* TC candidates (NULL: not collected)    */
@@ -772,10 +778,11 @@ enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
  * table is read from HBM/L2 (64 B per evaluation); only emitted samples go to HBM.
  * THREADS x MINB fixes the register budget (launch bounds): <256,1> 255 registers, <128,3> 168,
  * <128,4> 128 -- chosen at run time by tcr_set_tuning, default by measurement.   */
-template <int THREADS, int MINB, int KSMEM, int CTA_LOCKSTEP, int REC>
+template <int THREADS, int MINB, int KSMEM, int CTA_LOCKSTEP, int REC, int PARK>
 __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
 {
     static_assert(REC != 2 || KSMEM == 2, "record staging lives behind the eight stage vectors");
+    static_assert((PARK == 0 || KSMEM == 2) && (PARK == 0 || REC != 2), "state parking shares the staging area behind the stage vectors");
     /* Stage storage, "stage" j = 0..7: K0 (FSAL derivative), K1..K5, K6, and the step's end state y_new.
      * KSMEM = 1: K1..K5 (dead during an RHS evaluation) live in shared memory, [stage][component][thread],
      * which frees 40 registers; KSMEM = 2: all eight (64 registers); KSMEM = 0: registers only. */
@@ -809,6 +816,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
 #pragma unroll
         for (int i = 0; i < 4; ++i) Ks(j, i, 0.0);
     double* trk = nullptr;
+    /* track pool: the row this lane writes (its storm's while active, its spare while idle) */
+    unsigned int row = (unsigned int)(blockIdx.x * THREADS + threadIdx.x);
+    const size_t row_doubles = (size_t)ns * 4;
 
     /* storm end: n_time / status / nfev / TC criteria (util/compute.py:185-189) */
     auto finalize = [&](int st) {
@@ -833,6 +843,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
         }
         A.flags[sid] = fl;
         if (fl && A.cand_list) A.cand_list[atomicAdd(A.cand_count, 1u)] = (int32_t)sid;
+        if (A.track_row) {
+            A.track_row[sid] = fl ? (int32_t)row : -1;
+            if (fl) {                                            /* the candidate keeps its row: take a fresh one */
+                const unsigned int fresh = A.pool_first + atomicAdd(A.pool_ctl, 1u);
+                if (fresh < A.pool_rows) row = fresh; else A.pool_ctl[1] = 1u;
+            }
+        }
         mode = M_IDLE;
     };
 
@@ -860,7 +877,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                     total += c; warps_used += (c > 0); if (w < wid) before += c;
                 }
                 if (total > 0 && total <= 32 * (warps_used - 1)) {
-                    double* stg = k_smem + 32 * THREADS;                 /* [17][THREADS] staging behind the stage vectors */
+                    double* stg = k_smem + 32 * THREADS;                 /* [18][THREADS] staging behind the stage vectors */
                     if (mode != M_IDLE) {
                         const int r = before + __popc(act_b & ((1u << lane) - 1u));
                         double* d = stg + r;
@@ -872,6 +889,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                         d[14 * THREADS] = __hiloint2double(ym, nfev);
                         d[15 * THREADS] = __hiloint2double(n_out, n_attempts);
                         d[16 * THREADS] = __hiloint2double(mode, (rejected ? 1 : 0) | (new_step ? 2 : 0) | (any_v ? 4 : 0));
+                        d[17 * THREADS] = __hiloint2double(0, (int)row);
                     }
                     __syncthreads();
                     if ((int)threadIdx.x < total) {
@@ -887,10 +905,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                         const int fl = __double2loint(d[16 * THREADS]);
                         rejected = fl & 1; new_step = (fl & 2) != 0; any_v = (fl & 4) != 0;
                         status = 100;
+                        row = (unsigned int)__double2loint(d[17 * THREADS]);
                         ftab = A.ftab + (size_t)sid * ns * 4;
-                        trk = A.track + (size_t)sid * ns * 4;
+                        trk = A.track + (A.track_row ? (size_t)row : (size_t)sid) * row_doubles;
                     } else {
-                        mode = M_IDLE;
+                        mode = M_IDLE;             /* the queue is drained: this lane never needs a row again */
                     }
                     __syncthreads();                                     /* staging reusable by the next packing */
                 }
@@ -932,7 +951,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                             y[0] = A.lon0[sid]; y[1] = A.lat0[sid]; y[2] = A.v0[sid]; y[3] = A.m0[sid];
                             hbl = 0.5 * p.Ck / A.h_bl[sid];          /* storm-constant prefactor of dv/dt, dm/dt */
                             ftab = A.ftab + (size_t)sid * ns * 4;
-                            trk = A.track + (size_t)sid * ns * 4;
+                            trk = A.track + (A.track_row ? (size_t)row : (size_t)sid) * row_doubles;
                             nfev = 0; n_out = 0; n_attempts = 0; any_v = false; t = 0.0; status = 100;
                             mode = M_INIT0;
                         }
@@ -1005,7 +1024,38 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
 
             double dy[4] = {0, 0, 0, 0};
             TcrRhsAux aux = {0, 0, 0};
-            if (ev) { tcr_rhs<REC>(cx, ym, ftab, hbl, te, ye, dy, aux, rs, THREADS); ++nfev; }
+            if constexpr (PARK != 0) {
+                /* PARK: the RHS needs ~120 registers of its own and only (te, ye, ym, ftab, hbl) of the storm: the
+                 * rest of the storm's state (12 doubles, 6 words) waits in shared memory while it runs -- the area
+                 * the drain-phase packing uses between macro steps -- which brings the kernel under 128 / 144
+                 * registers without local-memory spills, i.e. 16 / 14 warps per SM instead of 12.  The empty asm
+                 * statements keep the compiler from forwarding the stores to the loads. */
+                double* pk = k_smem + 32 * THREADS + threadIdx.x;
+                pk[0 * THREADS] = y[0]; pk[1 * THREADS] = y[1]; pk[2 * THREADS] = y[2]; pk[3 * THREADS] = y[3];
+                pk[4 * THREADS] = t; pk[5 * THREADS] = h; pk[6 * THREADS] = h_abs; pk[7 * THREADS] = t_new;
+                pk[8 * THREADS] = g; pk[9 * THREADS] = min_step; pk[10 * THREADS] = h0; pk[11 * THREADS] = d1;
+                pk[12 * THREADS] = __longlong_as_double((long long)sid);
+                pk[13 * THREADS] = __hiloint2double(n_out, n_attempts);
+                pk[14 * THREADS] = __hiloint2double(status, (int)row);
+                pk[15 * THREADS] = __hiloint2double(nfev, (rejected ? 1 : 0) | (new_step ? 2 : 0) | (any_v ? 4 : 0) | (drained ? 8 : 0));
+                asm volatile("" ::: "memory");
+            }
+            if (ev) { tcr_rhs<REC>(cx, ym, ftab, hbl, te, ye, dy, aux, rs, THREADS); }
+            if constexpr (PARK != 0) {
+                asm volatile("" ::: "memory");
+                const double* pk = k_smem + 32 * THREADS + threadIdx.x;
+                y[0] = pk[0 * THREADS]; y[1] = pk[1 * THREADS]; y[2] = pk[2 * THREADS]; y[3] = pk[3 * THREADS];
+                t = pk[4 * THREADS]; h = pk[5 * THREADS]; h_abs = pk[6 * THREADS]; t_new = pk[7 * THREADS];
+                g = pk[8 * THREADS]; min_step = pk[9 * THREADS]; h0 = pk[10 * THREADS]; d1 = pk[11 * THREADS];
+                sid = (int64_t)__double_as_longlong(pk[12 * THREADS]);
+                n_out = __double2hiint(pk[13 * THREADS]); n_attempts = __double2loint(pk[13 * THREADS]);
+                status = __double2hiint(pk[14 * THREADS]); row = (unsigned int)__double2loint(pk[14 * THREADS]);
+                nfev = __double2hiint(pk[15 * THREADS]);
+                const int fl = __double2loint(pk[15 * THREADS]);
+                rejected = fl & 1; new_step = (fl & 2) != 0; any_v = (fl & 4) != 0; drained = (fl & 8) != 0;
+                trk = A.track + (A.track_row ? (size_t)row : (size_t)sid) * row_doubles;
+            }
+            if (ev) ++nfev;
 
             /* ---- consume ---- */
             if (mode == M_RK) {
@@ -1153,13 +1203,76 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
 /* speed (util/sphere.py:58-83), axi_to_max_wind (wind/tc_wind.py:6-21), nanmax(vmax) >= 18   */
 /* (util/compute.py:205).  One CTA per storm; lanes stride over the output samples.           */
 /* ======================================================================================== */
+/* one output sample of a storm: env winds at the track point (util/compute.py:201-202), translation speed from the
+ * neighbouring samples (util/sphere.py:58-83) and axi_to_max_wind (wind/tc_wind.py:6-21)                       */
+__device__ __forceinline__ double tcr_post_sample(const TcrCtx& cx, int ym, const double* __restrict__ ftab,
+                                                  const double* __restrict__ trk, int nt, int k, double w[4])
+{
+    const tcr_params& p = cx.p;
+    const double2 a = *reinterpret_cast<const double2*>(trk + (size_t)k * 4);
+    const double lon = a.x, lat = a.y;
+    const double v = trk[(size_t)k * 4 + 2];
+    const double tk = tcr_node_time(cx, k);
+    w[0] = w[1] = w[2] = w[3] = 0.0;
+    if (!(tcr_isnan(lon) || tcr_isnan(tk))) {
+        TcrFsNodes fsn;
+        tcr_fs_begin(cx, ftab, tk, fsn);
+        TcrCell c;
+        tcr_cell_at(cx.tab.lon, cx.tab.lat, lon, lat, c);
+        tcr_env_winds_cell(cx, tcr_record(cx.tab, ym, c), c, fsn, tk, w);
+    }
+    double ut, vt;
+    if (nt <= 1) {
+        ut = vt = NAN;
+    } else {
+        double lon_m, lat_m, lon_p, lat_p;
+        if (k == 0) {
+            const double2 b = *reinterpret_cast<const double2*>(trk + 4);
+            lon_m = 2 * lon - b.x; lat_m = 2 * lat - b.y;
+        } else {
+            const double2 b = *reinterpret_cast<const double2*>(trk + (size_t)(k - 1) * 4);
+            lon_m = b.x; lat_m = b.y;
+        }
+        if (k == nt - 1) {
+            const double2 b = *reinterpret_cast<const double2*>(trk + (size_t)(nt - 2) * 4);
+            lon_p = 2 * lon - b.x; lat_p = 2 * lat - b.y;
+        } else {
+            const double2 b = *reinterpret_cast<const double2*>(trk + (size_t)(k + 1) * 4);
+            lon_p = b.x; lat_p = b.y;
+        }
+        double dlon = 0.5 * (tcr_sign(lon_p - lon_m) * tcr_haversine_km(p, lon_p, lat, lon_m, lat));
+        double dlat = 0.5 * (tcr_sign(lat_p - lat_m) * tcr_haversine_km(p, lon, lat_p, lon, lat_m));
+        ut = dlon * 1000.0 / p.dt_track;
+        vt = dlat * 1000.0 / p.dt_track;
+    }
+    double G = 0.8 + 0.35 * (1.0 + tcr_tanh((lat - 35.0) / 10.0));
+    if (1.0 < G) G = 1.0;
+    double u_shr = w[0] - w[2], v_shr = w[1] - w[3];
+    double U = G * ut + 0.1 * u_shr * v / 15.0;
+    double V = G * vt + 0.1 * v_shr * v / 15.0;
+    double mag_inc = sqrt(U * U + V * V);
+    double vm;
+    if (mag_inc == 0.0) {
+        vm = fabs(v);
+    } else {
+        double mag_fac = (v * 0.50) / mag_inc;
+        if (!tcr_isnan(mag_fac) && 1.0 < mag_fac) mag_fac = 1.0;
+        double ug = v * (U / mag_inc) + U * mag_fac;
+        double vg = v * (V / mag_inc) + V * mag_fac;
+        vm = sqrt(ug * ug + vg * vg);
+    }
+    return vm;
+}
+
 struct PostArgs {
     int64_t n;                          /* storms if list == NULL */
     const int32_t* list; const unsigned int* list_count;
     const int32_t* ym; const double* ftab; const double* track;
+    const int32_t* track_row;           /* pool row of a candidate's track (NULL: track is indexed by storm) */
+    const unsigned int* pool_ctl;       /* [1] != 0: the track pool overflowed, the wave is void             */
     const int32_t* n_time; const int32_t* status;
-    double* env;                        /* [n][n_steps][4] */
-    double* vmax;                       /* [n][n_steps]    */
+    double* env;                        /* [n][n_steps][4]; NULL: only the kept flag is formed (tcr_run_years) */
+    double* vmax;                       /* [n][n_steps]                                                        */
     uint32_t* flags;
 };
 
@@ -1169,6 +1282,7 @@ __global__ void __launch_bounds__(128) k_postprocess(const __grid_constant__ Tcr
     __shared__ int have;
     const tcr_params& p = cx.p;
     const int ns = p.n_steps;
+    if (A.pool_ctl && A.pool_ctl[1]) return;
     const int64_t count = A.list ? (int64_t)*A.list_count : A.n;
     for (int64_t item = blockIdx.x; item < count; item += gridDim.x) {
         const int64_t sid = A.list ? (int64_t)A.list[item] : item;
@@ -1178,67 +1292,17 @@ __global__ void __launch_bounds__(128) k_postprocess(const __grid_constant__ Tcr
         if (threadIdx.x == 0) { best_bits = 0ull; have = 0; }
         __syncthreads();
         const int ym = A.ym[sid];
-        const double* trk = A.track + (size_t)sid * ns * 4;
+        const double* trk = A.track + (size_t)(A.track_row ? (int64_t)A.track_row[sid] : sid) * ns * 4;
         const double* ftab = A.ftab + (size_t)sid * ns * 4;
-        double* env = A.env + (size_t)sid * ns * 4;
-        double* vmx = A.vmax + (size_t)sid * ns;
         for (int k = threadIdx.x; k < nt; k += blockDim.x) {
-            const double2 a = *reinterpret_cast<const double2*>(trk + (size_t)k * 4);
-            const double lon = a.x, lat = a.y;
-            const double v = trk[(size_t)k * 4 + 2];
-            const double tk = tcr_node_time(cx, k);
-            double w[4] = {0.0, 0.0, 0.0, 0.0};
-            if (!(tcr_isnan(lon) || tcr_isnan(tk))) {
-                TcrFsNodes fsn;
-                tcr_fs_begin(cx, ftab, tk, fsn);
-                TcrCell c;
-                tcr_cell_at(cx.tab.lon, cx.tab.lat, lon, lat, c);
-                tcr_env_winds_cell(cx, tcr_record(cx.tab, ym, c), c, fsn, tk, w);
+            double w[4];
+            const double vm = tcr_post_sample(cx, ym, ftab, trk, nt, k, w);
+            if (A.env) {
+                double2* ed = reinterpret_cast<double2*>(A.env + ((size_t)sid * ns + k) * 4);
+                ed[0] = make_double2(w[0], w[1]);
+                ed[1] = make_double2(w[2], w[3]);
+                A.vmax[(size_t)sid * ns + k] = vm;
             }
-            double2* ed = reinterpret_cast<double2*>(env + (size_t)k * 4);
-            ed[0] = make_double2(w[0], w[1]);
-            ed[1] = make_double2(w[2], w[3]);
-            double ut, vt;
-            if (nt <= 1) {
-                ut = vt = NAN;
-            } else {
-                double lon_m, lat_m, lon_p, lat_p;
-                if (k == 0) {
-                    const double2 b = *reinterpret_cast<const double2*>(trk + 4);
-                    lon_m = 2 * lon - b.x; lat_m = 2 * lat - b.y;
-                } else {
-                    const double2 b = *reinterpret_cast<const double2*>(trk + (size_t)(k - 1) * 4);
-                    lon_m = b.x; lat_m = b.y;
-                }
-                if (k == nt - 1) {
-                    const double2 b = *reinterpret_cast<const double2*>(trk + (size_t)(nt - 2) * 4);
-                    lon_p = 2 * lon - b.x; lat_p = 2 * lat - b.y;
-                } else {
-                    const double2 b = *reinterpret_cast<const double2*>(trk + (size_t)(k + 1) * 4);
-                    lon_p = b.x; lat_p = b.y;
-                }
-                double dlon = 0.5 * (tcr_sign(lon_p - lon_m) * tcr_haversine_km(p, lon_p, lat, lon_m, lat));
-                double dlat = 0.5 * (tcr_sign(lat_p - lat_m) * tcr_haversine_km(p, lon, lat_p, lon, lat_m));
-                ut = dlon * 1000.0 / p.dt_track;
-                vt = dlat * 1000.0 / p.dt_track;
-            }
-            double G = 0.8 + 0.35 * (1.0 + tcr_tanh((lat - 35.0) / 10.0));
-            if (1.0 < G) G = 1.0;
-            double u_shr = w[0] - w[2], v_shr = w[1] - w[3];
-            double U = G * ut + 0.1 * u_shr * v / 15.0;
-            double V = G * vt + 0.1 * v_shr * v / 15.0;
-            double mag_inc = sqrt(U * U + V * V);
-            double vm;
-            if (mag_inc == 0.0) {
-                vm = fabs(v);
-            } else {
-                double mag_fac = (v * 0.50) / mag_inc;
-                if (!tcr_isnan(mag_fac) && 1.0 < mag_fac) mag_fac = 1.0;
-                double ug = v * (U / mag_inc) + U * mag_fac;
-                double vg = v * (V / mag_inc) + V * mag_fac;
-                vm = sqrt(ug * ug + vg * vg);
-            }
-            vmx[k] = vm;
             if (!tcr_isnan(vm)) {
                 /* vm >= 0: the bit pattern orders like the value */
                 atomicMax(&best_bits, (unsigned long long)tcr_d2bits(fabs(vm)));
@@ -1530,6 +1594,7 @@ struct SelectArgs {
     int32_t* row_slot;          /* [n_years][n_tracks] slot of a row assigned in THIS wave, else -1 */
     double* tc_month; int32_t* tc_basin; double* n_seeds;    /* outputs (device)               */
     tcr_year_stats* stats;      /* [n_years] device accumulators                               */
+    const unsigned int* pool_ctl;   /* [1] != 0: the track pool overflowed -- the wave is void, nothing is committed */
 };
 
 #define SEL_ITEMS 8
@@ -1541,6 +1606,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
     __shared__ unsigned long long s_acc[5];
     __shared__ unsigned int s_hist[TCR_N_BASINS * 12];
     const int yr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (A.pool_ctl[1]) return;
     const int64_t off = A.wave_off[yr];
     const int64_t W = A.consumed[yr];
     for (int r = tid; r < A.n_tracks; r += blockDim.x) A.row_slot[(size_t)yr * A.n_tracks + r] = -1;
@@ -1641,27 +1707,30 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
     }
 }
 
-/* copy the rows assigned in this wave into the caller's 9-tuple layout (compute.py:126-133,
- * 193-207), NaN-padded past n_time.  One warp per (year, row).                               */
+/* write the rows assigned in this wave into the caller's 9-tuple layout (compute.py:126-133, 193-207), NaN-padded
+ * past n_time.  One warp per (year, row).  env winds and vmax of a kept storm are formed HERE, from its track and
+ * Fourier table (the arithmetic of k_postprocess, so the same bits): the wave keeps no env / vmax rows at all.   */
 struct GatherArgs {
     int n_years, n_tracks;
     const int32_t* row_slot; const int32_t* n_time;
-    const double* track; const double* env; const double* vmax;
+    const int32_t* ym; const double* ftab; const double* track; const int32_t* track_row;
+    const unsigned int* pool_ctl;
     double* o_lon; double* o_lat; double* o_v; double* o_m; double* o_vmax; double* o_env;
 };
 
 __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ TcrCtx cx, const GatherArgs A)
 {
     const int ns = cx.p.n_steps;
+    if (A.pool_ctl[1]) return;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= (int64_t)A.n_years * A.n_tracks) return;
     const int slot = A.row_slot[row];
     if (slot < 0) return;
     const int lane = threadIdx.x & 31;
     const int nt = A.n_time[slot];
-    const double* trk = A.track + (size_t)slot * ns * 4;
-    const double* env = A.env + (size_t)slot * ns * 4;
-    const double* vmx = A.vmax + (size_t)slot * ns;
+    const int ym = A.ym[slot];
+    const double* trk = A.track + (size_t)A.track_row[slot] * ns * 4;
+    const double* ftab = A.ftab + (size_t)slot * ns * 4;
     const size_t o = (size_t)row * ns;
     for (int k = lane; k < ns; k += 32) {
         double2 a = make_double2(NAN, NAN), b = a, e0 = a, e1 = a;
@@ -1669,9 +1738,10 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ TcrCtx c
         if (k < nt) {
             a = *reinterpret_cast<const double2*>(trk + (size_t)k * 4);
             b = *reinterpret_cast<const double2*>(trk + (size_t)k * 4 + 2);
-            e0 = *reinterpret_cast<const double2*>(env + (size_t)k * 4);
-            e1 = *reinterpret_cast<const double2*>(env + (size_t)k * 4 + 2);
-            vm = vmx[k];
+            double w[4];
+            vm = tcr_post_sample(cx, ym, ftab, trk, nt, k, w);
+            e0 = make_double2(w[0], w[1]);
+            e1 = make_double2(w[2], w[3]);
         }
         A.o_lon[o + k] = a.x; A.o_lat[o + k] = a.y; A.o_v[o + k] = b.x; A.o_m[o + k] = b.y;
         A.o_vmax[o + k] = vm;

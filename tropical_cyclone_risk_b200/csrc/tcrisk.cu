@@ -82,14 +82,16 @@ struct TimedSpan { int which; cudaEvent_t a, b; };
  * (slot_bytes(n_steps) each: Fourier table, track, env winds, vmax).                          */
 struct Workspace {
     int64_t att_cap = 0, slot_cap = 0;
+    int64_t full_cap = 0;          /* slots that also own track / env / vmax rows (tcr_integrate)           */
+    int64_t pool_rows = 0;         /* rows of the track pool (tcr_run_years): lanes in flight + candidates   */
     int ns = 0;
     DevBuf code, basin, month, att_slot, a_lon, a_lat, a_v0, a_m0;   /* per attempt */
     DevBuf blk_count, blk_off;                                       /* per 256-attempt seed block */
     DevBuf att_kept, wave_tot;                                       /* k_wave_stats: byte per attempt; per-year totals + histogram */
     DevBuf s_ym, s_lon, s_lat, s_v0, s_m0, s_hbl, s_att, s_key;       /* per slot */
-    DevBuf n_time, status, nfev, flags, cand;
+    DevBuf n_time, status, nfev, flags, cand, track_row;
     DevBuf coef, ftab, track, env, vmax;
-    DevBuf counters;       /* [0] queue (u64), u32 @+8 n_slots, @+12 cand_count, @+16 n_pass */
+    DevBuf counters;       /* [0] queue (u64), u32 @+8 n_slots, @+12 cand_count, @+16 n_pass, @+20 pool next, @+24 pool overflow */
     DevBuf year_i64;       /* wave_off [ny+1], k0 [ny], consumed [ny], used [ny] */
     DevBuf year_i32;       /* ym_base [ny], year_key [ny], nt [ny] */
     DevBuf row_slot, stats;
@@ -98,10 +100,10 @@ struct Workspace {
     {
         DevBuf* all[] = {&code, &basin, &month, &att_slot, &a_lon, &a_lat, &a_v0, &a_m0, &blk_count, &blk_off, &att_kept, &wave_tot,
                          &s_ym, &s_lon, &s_lat, &s_v0, &s_m0, &s_hbl, &s_att, &s_key,
-                         &n_time, &status, &nfev, &flags, &cand, &coef, &ftab, &track, &env, &vmax, &counters, &year_i64,
+                         &n_time, &status, &nfev, &flags, &cand, &track_row, &coef, &ftab, &track, &env, &vmax, &counters, &year_i64,
                          &year_i32, &row_slot, &stats, &out};
         for (DevBuf* b : all) b->release();
-        att_cap = slot_cap = 0;
+        att_cap = slot_cap = full_cap = pool_rows = 0;
     }
 };
 
@@ -310,7 +312,7 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 {
     if (!h) return set_err("null handle");
     if (integ_variant > 0) {
-        if (integ_variant > 24) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
+        if (integ_variant > 28) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
         h->integ_variant = integ_variant - 1;
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
@@ -563,10 +565,16 @@ int tcr_env_interp(tcr_handle* h, int64_t n, const int32_t* ym, const double* lo
 }
 
 /* ---- workspace ----------------------------------------------------------------------------- */
-static size_t slot_bytes(int ns) { return 960 + (size_t)ns * 104 + 96; }
+/* per integrated slot: 60 coefficient pairs, the Fourier table (32 B per node), ~100 B of scalars, and its share
+ * of the track pool (one row per kPoolDiv slots: candidates are 2-3 % of the storms)                       */
+static const int kPoolDiv = 8;
+static size_t slot_bytes(int ns) { return 960 + (size_t)ns * 32 + 104 + (size_t)ns * 32 / kPoolDiv; }
 static const size_t kAttemptBytes = 56;
+static int64_t max_lanes(const tcr_handle* h) { return (int64_t)h->num_sms * 576; }   /* most threads per SM of any variant */
 
-static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_years)
+/* full: every slot owns a track / env / vmax row (tcr_integrate returns them for every storm); otherwise tracks
+ * live in the pool and env winds / vmax are never stored per slot (k_gather forms them for the rows it emits) */
+static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_years, bool full)
 {
     Workspace& w = h->ws;
     const int ns = h->ctx.p.n_steps;
@@ -584,10 +592,25 @@ static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_yea
         if (w.s_ym.ensure(c * 4) || w.s_lon.ensure(c * 8) || w.s_lat.ensure(c * 8) || w.s_v0.ensure(c * 8) ||
             w.s_m0.ensure(c * 8) || w.s_hbl.ensure(c * 8) || w.s_att.ensure(c * 8) || w.s_key.ensure(c * 4) ||
             w.n_time.ensure(c * 4) || w.status.ensure(c * 4) || w.nfev.ensure(c * 4) || w.flags.ensure(c * 4) ||
-            w.cand.ensure(c * 4) || w.coef.ensure(c * TCR_N_PHASES * sizeof(double2)) ||
-            w.ftab.ensure(c * ns * 32) || w.track.ensure(c * ns * 32) || w.env.ensure(c * ns * 32) || w.vmax.ensure(c * ns * 8))
+            w.cand.ensure(c * 4) || w.track_row.ensure(c * 4) || w.coef.ensure(c * TCR_N_PHASES * sizeof(double2)) ||
+            w.ftab.ensure(c * ns * 32))
             return -1;
         w.slot_cap = slot_cap;
+    }
+    if (full) {
+        if (slot_cap > w.full_cap) {
+            const size_t c = (size_t)slot_cap;
+            if (w.track.ensure(c * ns * 32) || w.env.ensure(c * ns * 32) || w.vmax.ensure(c * ns * 8)) return -1;
+            w.full_cap = slot_cap;
+        }
+    } else {
+        const int64_t rows = max_lanes(h) + std::max<int64_t>(4096, w.slot_cap / kPoolDiv);
+        if (rows > w.pool_rows || w.track.bytes < (size_t)rows * ns * 32) {
+            if (w.track.ensure((size_t)rows * ns * 32)) return -1;
+            w.pool_rows = rows;
+            w.full_cap = std::min<int64_t>(w.full_cap, (int64_t)(w.track.bytes / ((size_t)ns * 32)));
+        }
+        w.pool_rows = std::min<int64_t>((int64_t)(w.track.bytes / ((size_t)ns * 32)), 0x7fffffff);
     }
     if (w.counters.ensure(64)) return -1;
     const size_t ny = (size_t)std::max(n_years, 1);
@@ -621,7 +644,7 @@ static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned i
 
 }  // extern "C"
 
-template <int THREADS, int MINB, int KSMEM, int LOCKSTEP = 0, int REC = 1>
+template <int THREADS, int MINB, int KSMEM, int LOCKSTEP = 0, int REC = 1, int PARK = 0>
 static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_upper)
 {
     const int warps_per_cta = THREADS / 32;
@@ -631,13 +654,14 @@ static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_uppe
     int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
     a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
     { static const int pack_on = getenv("TCR_NO_PACK") ? 0 : 1; a.pack = pack_on; }
+    a.pool_first = (unsigned int)grid * THREADS;                      /* lanes own rows [0, grid x THREADS) */
     /* KSMEM 2: eight stage vectors + the 17-word staging area of the drain-phase packing, which the record
      * staging of REC 2 (20 x 16 B per thread) overlays */
-    const size_t smem = KSMEM == 2 ? (size_t)(32 + (REC == 2 ? 40 : 17)) * THREADS * sizeof(double)
+    const size_t smem = KSMEM == 2 ? (size_t)(32 + (REC == 2 ? 40 : 18)) * THREADS * sizeof(double)
                                    : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
-    cudaFuncSetAttribute(k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC, PARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     LaunchTimer lt_(h, TCR_K_INTEGRATE);
-    k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC><<<grid, THREADS, smem, h->stream>>>(h->ctx, a);
+    k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC, PARK><<<grid, THREADS, smem, h->stream>>>(h->ctx, a);
 }
 
 static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
@@ -667,6 +691,10 @@ static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
     case 21: launch_integrate_variant<192, 2, 2, 63, 0>(h, a, n_upper); break;   /* round-1 record path (float32 records, F2F) */
     case 22: launch_integrate_variant<192, 2, 2, 63, 2>(h, a, n_upper); break;   /* records staged in shared memory by cp.async */
     case 23: launch_integrate_variant<384, 1, 2, 63, 2>(h, a, n_upper); break;
+    case 24: launch_integrate_variant<192, 2, 2, 63, 1, 1>(h, a, n_upper); break;   /* PARK: storm state parked in smem during the RHS */
+    case 25: launch_integrate_variant<224, 2, 2, 63, 1, 1>(h, a, n_upper); break;   /* 144 registers, 14 warps/SM */
+    case 26: launch_integrate_variant<256, 2, 2, 63, 1, 1>(h, a, n_upper); break;   /* 128 registers, 16 warps/SM */
+    case 27: launch_integrate_variant<288, 2, 2, 63, 1, 1>(h, a, n_upper); break;   /* 112 registers, 18 warps/SM */
     default: return set_err("unknown integrate variant %d", h->integ_variant);
     }
     CKK(h);
@@ -688,7 +716,7 @@ int tcr_integrate(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon
     if (!h->rec.p || !h->have_static) return set_err("tcr_integrate: tables / static fields not uploaded");
     if (n > 0x7fffffff) return set_err("tcr_integrate: n too large");
     CK(cudaSetDevice(h->device));
-    if (ws_ensure(h, 0, n, 1)) return -1;
+    if (ws_ensure(h, 0, n, 1, true)) return -1;
     Workspace& w = h->ws;
     const int ns = h->ctx.p.n_steps;
     cudaStream_t s = h->stream;
@@ -730,6 +758,7 @@ int tcr_integrate(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon
     memset(&pa, 0, sizeof pa);
     pa.n = n; pa.list = nullptr; pa.list_count = nullptr;
     pa.ym = a.ym; pa.ftab = a.ftab; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
+    pa.track_row = nullptr; pa.pool_ctl = nullptr;
     pa.env = w.env.as<double>(); pa.vmax = w.vmax.as<double>(); pa.flags = a.flags;
     {
         LaunchTimer lt_(h, TCR_K_POSTPROCESS);
@@ -835,14 +864,16 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
             size_t held = w0.ftab.bytes + w0.track.bytes + w0.env.bytes + w0.vmax.bytes + w0.coef.bytes + w0.out.bytes;
-            size_t budget = std::min<size_t>((size_t)64 << 30, (size_t)((free_b + held) * 0.6));
+            size_t budget = std::min<size_t>((size_t)96 << 30, (size_t)((free_b + held) * 0.6));
             if (budget > out_bytes) budget -= out_bytes;
             const int64_t cap_mem = (int64_t)((double)budget / ((double)kAttemptBytes + pass_est * (double)slot_bytes(ns)));
             /* 25 % headroom so that the next call's slightly different estimate still fits */
             int64_t att_cap = std::max<int64_t>(4096, std::min(cap_mem, want_att + want_att / 4));
             int64_t slot_cap = std::min(att_cap, std::max<int64_t>(4096, (int64_t)((double)att_cap * pass_est) + 1024));
-            if (ws_ensure(h, std::max(att_cap, w0.att_cap), std::max(slot_cap, w0.slot_cap), n_years)) return -1;
-        } else if (ws_ensure(h, w0.att_cap, w0.slot_cap, n_years)) {
+            w0.env.release(); w0.vmax.release();                       /* only tcr_integrate keeps per-slot env / vmax rows */
+            if (w0.full_cap > 0) { w0.track.release(); w0.full_cap = 0; w0.pool_rows = 0; }
+            if (ws_ensure(h, std::max(att_cap, w0.att_cap), std::max(slot_cap, w0.slot_cap), n_years, false)) return -1;
+        } else if (ws_ensure(h, w0.att_cap, w0.slot_cap, n_years, false)) {
             return -1;
         }
     }
@@ -891,6 +922,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
     unsigned int* d_nslots = reinterpret_cast<unsigned int*>(d_queue + 1);
     unsigned int* d_ncand = d_nslots + 1;
     unsigned int* d_npass = d_nslots + 2;
+    unsigned int* d_pool = d_nslots + 3;                       /* [0] fresh rows handed out, [1] overflow */
 
     std::vector<tcr_year_stats> hstats(n_years);
     bool final_done = false;
@@ -996,13 +1028,15 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         a.n_time = w.n_time.as<int32_t>(); a.status = w.status.as<int32_t>(); a.nfev = w.nfev.as<int32_t>();
         a.flags = w.flags.as<uint32_t>();
         a.queue = d_queue; a.cand_list = w.cand.as<int32_t>(); a.cand_count = d_ncand;
+        a.track_row = w.track_row.as<int32_t>(); a.pool_ctl = d_pool; a.pool_rows = (unsigned int)w.pool_rows;
         if (launch_fourier_table(h, slots_upper, d_nslots) || launch_integrate(h, a, slots_upper)) return -1;
 
         PostArgs pa;
         memset(&pa, 0, sizeof pa);
         pa.n = 0; pa.list = w.cand.as<int32_t>(); pa.list_count = d_ncand;
         pa.ym = a.ym; pa.ftab = a.ftab; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
-        pa.env = w.env.as<double>(); pa.vmax = w.vmax.as<double>(); pa.flags = a.flags;
+        pa.track_row = a.track_row; pa.pool_ctl = d_pool;
+        pa.env = nullptr; pa.vmax = nullptr; pa.flags = a.flags;
         {
             LaunchTimer lt_(h, TCR_K_POSTPROCESS);
             k_postprocess<<<h->num_sms * 8, 128, 0, s>>>(h->ctx, pa);
@@ -1028,6 +1062,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         se.nt = d_nt; se.used = d_used; se.row_slot = w.row_slot.as<int32_t>();
         se.tc_month = d_month; se.tc_basin = d_basin; se.n_seeds = d_seeds;
         se.stats = w.stats.as<tcr_year_stats>();
+        se.pool_ctl = d_pool;
         {
             LaunchTimer lt_(h, TCR_K_SELECT);
             k_wave_stats<<<seed_blocks, 256, 0, s>>>(wa);
@@ -1039,7 +1074,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         GatherArgs ga;
         memset(&ga, 0, sizeof ga);
         ga.n_years = n_years; ga.n_tracks = n_tracks; ga.row_slot = se.row_slot; ga.n_time = a.n_time;
-        ga.track = a.track; ga.env = pa.env; ga.vmax = pa.vmax;
+        ga.ym = a.ym; ga.ftab = a.ftab; ga.track = a.track; ga.track_row = a.track_row; ga.pool_ctl = d_pool;
         ga.o_lon = d_lon; ga.o_lat = d_lat; ga.o_v = d_v; ga.o_m = d_m; ga.o_vmax = d_vmax; ga.o_env = d_env;
         {
             LaunchTimer lt_(h, TCR_K_GATHER);
@@ -1049,12 +1084,19 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
 
         CK(cudaMemcpyAsync(pin_nt, d_nt, n_years * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(pin_used, d_consumed, n_years * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(pin_used + n_years, d_npass, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(pin_used + n_years, d_npass, 12, cudaMemcpyDeviceToHost, s));       /* n_pass, pool next, pool overflow */
         /* a wave sized from survival hints almost always completes every year: queue the final
          * read-back behind it so that the call costs ONE host synchronisation, not two */
         const bool speculative = h->hint_kept_rate > 0.0 && scale == 1.0;
         if (speculative) { if (final_copies()) return -1; }
         CK(cudaStreamSynchronize(s));
+        if (reinterpret_cast<unsigned int*>(pin_used + n_years)[2] != 0u) {
+            /* more TC candidates than the track pool has rows: nothing of this wave was committed (k_select and
+             * k_gather stood down); repeat it with half the slots -- results do not depend on wave size */
+            slot_cap = std::max<int64_t>(1024, std::min<int64_t>(slot_cap, total) / 2);
+            final_done = false;
+            continue;
+        }
         final_done = speculative;
         sum_pass += (int64_t)(*reinterpret_cast<unsigned int*>(pin_used + n_years));
         sum_att_launched += total;
