@@ -140,8 +140,13 @@ def test_decode_cf_masks_and_scales():
     from tropical_cyclone_risk_b200 import driver
     raw = np.array([-32767, 0, 100], dtype=np.int16)
     out = driver.decode_cf(raw, {"scale_factor": 0.5, "add_offset": 10.0, "_FillValue": np.int16(-32767)})
-    assert np.isnan(out[0]) and out[1] == 10.0 and out[2] == 60.0 and out.dtype == np.float32
-    assert np.array_equal(driver.decode_cf(np.array([1.5, 2.5], np.float32), {}), [1.5, 2.5])
+    # xarray's _choose_float_dtype: int16 WITH an add_offset decodes to float64 (classic packed ERA5) ...
+    assert np.isnan(out[0]) and out[1] == 10.0 and out[2] == 60.0 and out.dtype == np.float64
+    # ... int16 with a scale factor only to float32, float32 data stay float32, wider integers go to float64
+    assert driver.decode_cf(raw, {"scale_factor": 0.5}).dtype == np.float32
+    assert driver.decode_cf(np.array([1, 2], np.int32), {"scale_factor": 0.5}).dtype == np.float64
+    f = driver.decode_cf(np.array([1.5, 2.5], np.float32), {})
+    assert np.array_equal(f, [1.5, 2.5]) and f.dtype == np.float32
 
 
 def _rank_worker(rank, world, port, base, q):
@@ -190,6 +195,56 @@ def test_compute_downscaling_inputs_gloo_world2_matches_single_rank(era5_tree, t
         assert a.times == b.times
         for n in names:
             assert np.array_equal(a.vars[n], b.vars[n], equal_nan=True), n
+
+
+def _run_worker(rank, world, port, base, q):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import pathlib
+        from conftest import golden
+        from oracle import ref_harness as rh
+        from test_host_logic import _fake_run_years
+        from tropical_cyclone_risk_b200 import driver
+        cfg = _namelist(pathlib.Path(base))
+        cfg.output_directory = os.path.join(base, "out_run2")
+        cfg.exp_name, cfg.tracks_per_year = "w2", 3
+        g = golden("ref_thermo.npz")
+        out = driver.run("NA", cfg, rh.REF_ROOT, engine=OracleEngine((g["table_p"], g["table_s"], g["table_T"])),
+                         run_years_fn=_fake_run_years)
+        q.put((rank, out["tc_lon"].shape, out.get("fn_trk_out")))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_driver_run_gloo_world2(era5_tree, tmp_path):
+    """driver.run under two ranks (gloo): rank 0 writes the caches atomically, every rank waits for them behind a
+    barrier before run_downscaling opens them, the years are sharded and gathered, rank 0 alone writes the track
+    file.  (Build container only: the static inputs come from the reference tree.)"""
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not present")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_run_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1] == (3, 361)                          # 2001 only (start/end year of the test namelist) x 3 tracks
+    assert got[0][2] is not None and got[1][2] is None                 # rank 0 wrote the track file, rank 1 did not
+    assert os.path.exists(got[0][2])
+    out = str(tmp_path / "out_run2")
+    assert not [f for f in os.listdir(out) if ".tmp." in f]            # no half-written cache left behind
 
 
 def test_the_reference_namelist_is_accepted_unchanged():

@@ -59,11 +59,25 @@ def get_fn_thermo(nl):
                                               nl.end_year, nl.end_month)
 
 
-def decode_cf(a, attrs, dtype=np.float32):
-    """xarray's mask_and_scale: fill / missing values -> NaN, then raw * scale_factor + add_offset."""
+def cf_float_dtype(a, attrs):
+    """The float type xarray's mask_and_scale decodes a packed variable to (xarray/coding/variables.py
+    _choose_float_dtype): float32 only for float32 data and for integers of at most 16 bits WITHOUT an add_offset;
+    an add_offset (classic packed ERA5) or a wider integer gives float64."""
+    a = np.asarray(a)
+    if a.dtype.kind == "f":
+        return np.float32 if a.dtype.itemsize <= 4 else np.float64
+    if a.dtype.itemsize <= 2 and attrs.get("add_offset") is None:
+        return np.float32
+    return np.float64
+
+
+def decode_cf(a, attrs, dtype=None):
+    """xarray's mask_and_scale: fill / missing values -> NaN, then raw * scale_factor + add_offset, in the float
+    type xarray would pick (cf_float_dtype) unless `dtype` forces one."""
     a = np.asarray(a)
     if a.dtype.kind not in "iuf":
         return a
+    dtype = np.dtype(dtype or cf_float_dtype(a, attrs)).type
     out = a.astype(dtype)
     for k in ("_FillValue", "missing_value"):
         if k in attrs and attrs[k] is not None:
@@ -91,7 +105,10 @@ class _Source:
         self.times = refdata.decode_cf_time(t, tattrs.get('units'), tattrs.get('calendar', 'standard'))
         data, attrs = v[var_key]
         self.units = str(attrs.get('units', ''))
-        self.data = decode_cf(data, attrs)
+        # decoded the way xarray decodes (float64 for packed int16 + add_offset), then handed to the float32
+        # kernels: the reference carries the float64 values into its statistics, so for packed inputs the planes
+        # here differ from its own by the float32 rounding of each sample (~6e-8 relative); documented deviation
+        self.data = np.asarray(decode_cf(data, attrs), dtype=np.float32)
         if with_levels:
             lv, lattrs = v[keys['lvl']]
             self.levels = np.asarray(lv, dtype=np.float64)
@@ -99,11 +116,13 @@ class _Source:
 
 
 def _write_cache(path, times, lon, lat, variables):
-    """(time, lat, lon) float64 variables + coordinates, time as days since 1900-01-01 (what xarray would decode)."""
+    """(time, lat, lon) float64 variables + coordinates, time as days since 1900-01-01 (what xarray would decode).
+    Written under a temporary name and moved into place: a reader never sees a half-written cache."""
     from scipy.io import netcdf_file
     os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
     t0 = datetime.datetime(1900, 1, 1)
-    with netcdf_file(path, "w", version=2) as f:
+    tmp = "%s.tmp.%d" % (path, os.getpid())
+    with netcdf_file(tmp, "w", version=2) as f:
         f.createDimension("time", len(times)); f.createDimension("lat", lat.size); f.createDimension("lon", lon.size)
         v = f.createVariable("time", "f8", ("time",))
         v.units = "days since 1900-01-01 00:00:00"
@@ -115,6 +134,17 @@ def _write_cache(path, times, lon, lat, variables):
             w = f.createVariable(name, "f8", ("time", "lat", "lon"))
             w._FillValue = np.nan
             w[:] = data
+    os.replace(tmp, path)
+
+
+def _barrier():
+    """Every rank waits until rank 0 has written a cache file the next stage opens."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+    except ImportError:
+        pass
 
 
 def _rank():
@@ -138,9 +168,25 @@ def month_stamps(nl, file_times):
     return t_months[0:-1]
 
 
+def _cache_exists(path):
+    """os.path.exists as rank 0 sees it, agreed by every rank (a cache that appears between two ranks' checks
+    must not split them into a computing and a skipping group: the gathers below are collectives)."""
+    have = os.path.exists(path)
+    try:
+        import torch
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            flag = [have]
+            dist.broadcast_object_list(flag, src=0)
+            have = bool(flag[0])
+    except ImportError:
+        pass
+    return have
+
+
 def gen_wind_mean_cov(engine, nl, group_sub_daily=False):
     fn_out = get_env_wnd_fn(nl)
-    if os.path.exists(fn_out):
+    if _cache_exists(fn_out):
         return fn_out
     keys = nl.var_keys[nl.dataset_type]
     fns_ua, fns_va = glob_prefix(nl, keys['u']), glob_prefix(nl, keys['v'])
@@ -166,6 +212,7 @@ def gen_wind_mean_cov(engine, nl, group_sub_daily=False):
         names = preproc.wind_mean_vector_names() + preproc.wind_cov_matrix_names()
         _write_cache(fn_out, stamps, lon, lat, {n: allst[:, i] for i, n in enumerate(names)})
         print('Saved %s' % fn_out)
+    _barrier()
     return fn_out
 
 
@@ -179,7 +226,7 @@ def _concat(sources):
 
 def gen_thermo(engine, nl):
     fn_out = get_fn_thermo(nl)
-    if os.path.exists(fn_out):
+    if _cache_exists(fn_out):
         return fn_out
     keys = nl.var_keys[nl.dataset_type]
     dt_start, dt_end = get_bounding_times(nl)
@@ -221,6 +268,7 @@ def gen_thermo(engine, nl):
         stamps = [datetime.datetime(t_psl[i].year, t_psl[i].month, 15) for i in sel]   # calc_thermo.py:98-101
         _write_cache(fn_out, stamps, psl_s[0].lon, psl_s[0].lat, dict(vmax=g[:, 0], chi=g[:, 1], rh_mid=g[:, 2]))
         print('Saved %s' % fn_out)
+    _barrier()
     return fn_out
 
 
@@ -255,22 +303,48 @@ def make_engine(nl, reference_root, device=0):
     return eng
 
 
-def run(basin_id, nl, reference_root, namelist_path=None):
-    """run.py:8-19."""
+def local_device():
+    """This rank's GPU: LOCAL_RANK under torchrun (one process per GPU), else torch's current device."""
+    import torch
+    if "LOCAL_RANK" in os.environ:
+        dev = int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(dev)
+        return dev
+    return torch.cuda.current_device()
+
+
+def init_distributed():
+    """Under torchrun: one process per GPU, NCCL over NVLink (the write-out all-gather of compute.run_downscaling)."""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return False
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dev = local_device()
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    return True
+
+
+def run(basin_id, nl, reference_root, namelist_path=None, engine=None, run_years_fn=None):
+    """run.py:8-19.  `engine` / `run_years_fn` replace the CUDA engine in host-logic tests."""
     from . import compute
     f_base = '%s/%s/' % (nl.output_directory, nl.exp_name)
-    os.makedirs(f_base, exist_ok=True)
-    print('Saving model output to %s' % f_base)
-    if namelist_path:
-        shutil.copyfile(namelist_path, '%s/namelist.py' % f_base)
-    eng = make_engine(nl, reference_root)
+    rank, _, _ = _rank()
+    if rank == 0:
+        os.makedirs(f_base, exist_ok=True)
+        print('Saving model output to %s' % f_base)
+        if namelist_path:
+            shutil.copyfile(namelist_path, '%s/namelist.py' % f_base)
+    eng = engine if engine is not None else make_engine(nl, reference_root, device=local_device())
     try:
         compute_downscaling_inputs(eng, nl)
     finally:
-        eng.close()
+        if engine is None:
+            eng.close()
     compute.configure(namelist=nl, inputs=refdata.ReferenceInputs(reference_root, get_env_wnd_fn(nl), get_fn_thermo(nl)))
     print('Running tracks for basin %s...' % basin_id)
-    return compute.run_downscaling(basin_id)
+    return compute.run_downscaling(basin_id, run_years_fn=run_years_fn)
 
 
 def main(argv=None):
@@ -281,6 +355,7 @@ def main(argv=None):
     ap.add_argument("--reference-root", default=None, help="reference checkout (static data, entropy table); default: the namelist's directory")
     a = ap.parse_args(argv)
     nl = load_namelist(a.namelist)
+    init_distributed()
     run(a.basin, nl, a.reference_root or os.path.dirname(os.path.abspath(a.namelist)), a.namelist)
 
 
