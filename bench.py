@@ -254,7 +254,7 @@ def workload_config(args, n_steps):
     return {
         "workload": workload_label(args, n_steps),
         "basin": args.basin, "years_per_gpu": args.years, "tracks_per_year": args.tracks, "n_steps": int(n_steps),
-        "run_seed": RUN_SEED, "parallelism": "years sharded over ranks; NCCL all-gather of finished tracks at write-out (every step, inside the timed region)",
+        "run_seed": RUN_SEED, "parallelism": "years sharded over ranks; all-gather of finished tracks at write-out (every step, inside the timed region)",
         "l2": "inputs larger than L2: cell-record tables %d months + result block, see l2_bytes" % (12 * args.years),
     }
 
@@ -275,6 +275,8 @@ def run_gpu_arm(args):
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from tropical_cyclone_risk_b200 import gather as tgather
+    numa = tgather.bind_to_gpu_numa(local)                      # before any pinned allocation (first touch)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
@@ -307,48 +309,45 @@ def run_gpu_arm(args):
     sizes = [("lon", rows * ns), ("lat", rows * ns), ("v", rows * ns), ("m", rows * ns), ("vmax", rows * ns),
              ("env", rows * ns * 4), ("tc_month", rows), ("n_seeds", ny * 84), ("tc_basin", (rows + 1) // 2)]
     total = sum(n for _, n in sizes)
-    # two result blocks: the write-out all-gather of step i (NCCL's stream) overlaps the seeding /
-    # table / integration kernels of step i+1, which write the other block
+    # two result blocks: the write-out gather of step i leaves block i % 2 while step i+1 fills the other one
     n_blocks = 2 if world > 1 else 1
-    res_blocks, dptrs, gathered, pending = [], [], [], []
+    res_blocks, dptrs = [], []
     for _ in range(n_blocks):
         res = torch.empty(total, dtype=torch.float64, device=dev)
         dptr, off = {}, 0
         for name, n in sizes:
             dptr[name] = res.data_ptr() + off * 8
             off += n
-        res_blocks.append(res); dptrs.append(dptr); pending.append(None)
-        gathered.append(torch.empty((world, total), dtype=torch.float64, device=dev) if world > 1 else None)
+        res_blocks.append(res); dptrs.append(dptr)
     step_no = [0]
 
     diag = os.environ.get("TCR_BENCH_DIAG") == "1"
-    # Write-out all-gather: by default the next step's kernels wait for it on the stream (0.6-0.8 ms at N = 2 over
-    # NVLink).  Letting it overlap the next step (TCR_BENCH_GATHER=overlap, two result blocks) was measured to cost
-    # MORE: the persistent integrator owns every SM's register file, NCCL's CTAs cannot become resident beside it,
-    # the gather ends up behind that integrator and the step after it waits for the block: 15.5-16.9 ms per step
-    # against 13.1 + 0.7 ms (profiles/r01_n2_gather_modes.txt).
-    gather_overlap = os.environ.get("TCR_BENCH_GATHER", "") == "overlap"
+    # Write-out gather of the finished tracks (every step, inside the timed region).  Default: gather.PeerGather --
+    # each rank writes its block into every peer's buffer with copy-engine device-to-device copies over NVLink (CUDA IPC):
+    # no SM involved, so it overlaps the next step's persistent integrator.  TCR_BENCH_GATHER=nccl: the plain
+    # all_gather_into_tensor, waited for on the stream (round 1: its CTAs cannot run beside the integrator, 0.79
+    # efficiency at N = 8, profiles/r01_n2_gather_modes.txt).
+    gather_mode = os.environ.get("TCR_BENCH_GATHER", "peer") if world > 1 else "none"
+    peer = tgather.PeerGather(total, torch.float64, dev, depth=n_blocks, dst="all", dst_depth=1) if gather_mode == "peer" else None
+    gathered = torch.empty((world, total), dtype=torch.float64, device=dev) if gather_mode == "nccl" else None
 
     def step_device(i):
         t0 = time.perf_counter()
         b = step_no[0] % n_blocks
         step_no[0] += 1
-        if pending[b] is not None:
-            pending[b].wait()                                  # stream-ordered: block b's previous gather has read it
-            pending[b] = None
+        if peer is not None:
+            peer.wait_local(b)                                     # stream-ordered: block b's previous copies have read it
         st = eng.run_years_dev(ym_base, year_key, RUN_SEED + i, nt, dptrs[b])
         t1 = time.perf_counter()
-        if world > 1:
-            work = dist.all_gather_into_tensor(gathered[b], res_blocks[b], async_op=True)
-            if gather_overlap:
-                pending[b] = work                              # waited for two steps later, when block b is reused
-            else:
-                work.wait()                                    # stream-ordered: the next step's kernels start after the gather
+        if peer is not None:
+            peer.push(res_blocks[b], b)
+        elif gathered is not None:
+            dist.all_gather_into_tensor(gathered, res_blocks[b])   # stream-ordered: the next step starts after the gather
         if diag:
             t2 = time.perf_counter()
             torch.cuda.synchronize()
             t3 = time.perf_counter()
-            print("rank %d step %d: run_years %.2f ms, all_gather enqueue %.2f ms, drain %.2f ms" % (
+            print("rank %d step %d: run_years %.2f ms, gather enqueue %.2f ms, drain %.2f ms" % (
                 rank, i, 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)), file=sys.stderr, flush=True)
         return st
 
@@ -392,10 +391,8 @@ def run_gpu_arm(args):
         e2e_state["primed"] = False                             # the look-ahead upload of a step that never ran is discarded
 
     def finish_gathers():
-        for b in range(n_blocks):
-            if pending[b] is not None:
-                pending[b].wait()
-                pending[b] = None
+        if peer is not None:
+            peer.finish()                                          # every rank's copies have landed everywhere
 
     def sum_stats(acc, st):
         for s in st:
@@ -497,6 +494,8 @@ def run_gpu_arm(args):
             "work_per_step": {k: tot[k] / K for k in keys},
             "waves_per_step": acc["waves"],
             "kernel_share_of_step": {k: v[0] / ms for k, v in ktimes.items() if v[1]},
+            "numa": numa,
+            "gather": {"mode": gather_mode, "bytes_per_rank_per_step": int(total * 8) * (world - 1) if world > 1 else 0},
         }
         if not args.no_interp:
             ri = bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args)

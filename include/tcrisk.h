@@ -178,6 +178,14 @@ int tcr_integrate(tcr_handle* h, int64_t n,
                   int32_t* n_time, int32_t* status, int32_t* nfev, uint32_t* flags,
                   int on_device);
 
+/* ---- single evaluations of the right-hand side (inner tier of the seam) ------------------ */
+/* replaces: Coupled_FAST.dydt(t, y) (intensity/coupled_fast.py:196-207) and BetaAdvectionTrack._env_winds(lon, lat,
+ * t) (track/bam_track.py:116-128; called per output point by util/compute.py:201-202) for n independent states:
+ * y [n][4] = lon, lat, v, m; phases [n][4][15] the storm's gen_f phases (self.Fs); dydt [n][4]; env_winds [n][4] =
+ * _env_winds(y[0], y[1], t) (zeros on a NaN argument or a non-positive-definite covariance).  Host pointers.      */
+int tcr_rhs_eval(tcr_handle* h, int64_t n, const int32_t* ym, const double* t, const double* y, const double* h_bl,
+                 const double* phases, double* dydt, double* env_winds);
+
 /* ---- whole years: seeding + integration + ordered selection ---------------------------- */
 /* replaces: run_tracks(year, n_tracks, b) for n_years years at once (util/compute.py:64-210).
  * Year y uses tables ym = ym_base[y] .. ym_base[y]+11 and Philox key (run_seed, year_key[y]).

@@ -91,3 +91,89 @@ def test_cuda_field_preparation_vs_reference_lines():
             assert ulp.max() <= 1 and (ulp == 0).mean() > 0.99
     finally:
         eng.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the inner tier of the seam: the Coupled_FAST-compatible object (tropical_cyclone_risk_b200/coupled_fast.py)
+# ---------------------------------------------------------------------------------------------
+def _shim(monkeypatch):
+    from oracle import ref_harness as rh                      # injected_phases only: nothing of the reference tree is read
+    from tropical_cyclone_risk_b200 import compute, coupled_fast, fields, layout, synth
+    from tropical_cyclone_risk_b200 import namelist as nl
+    lon, lat = synth.era5_axes()
+    olon, olat = synth.ocean_axes()
+    raw = synth.synth_month_raw(2000, 9, lon, lat)
+    mld, strat = synth.synth_ocean(olon, olat, 9)
+    _, _, pg = fields.prepare_month(nl, (0.0, -90.0, 360.0, 90.0), lon, lat, raw, olon, olat, mld, strat)
+    wnd = dict(lon=lon, lat=lat, **{name: pg[i] for i, name in enumerate(layout.FIELD_NAMES[:14])})
+    monkeypatch.setattr(coupled_fast, "random_seed", lambda: None)
+    import datetime
+    fast = coupled_fast.Coupled_FAST(wnd, compute.TC_Basin("NA"), datetime.datetime(2000, 9, 15), nl.output_interval_s,
+                                     nl.total_track_time_days * 86400, static=synth.synth_static(full_res=False), device=0)
+    fast.init_fields(lon, lat, pg[layout.CH_CHI], pg[layout.CH_VPOT], pg[layout.CH_MLD], pg[layout.CH_STRAT])
+    return fast, rh
+
+
+def test_coupled_fast_shim_gen_track_vs_reference_fixture(monkeypatch, na_case):
+    """fast.gen_track(clon, clat, v, m) -> .t / .y / .status / .nfev as the reference's run_tracks loop reads them
+    (util/compute.py:176-203), against the outputs of the reference's own gen_track (tests/golden/ref_tracks.npz)."""
+    fast, rh = _shim(monkeypatch)
+    g = golden("ref_tracks.npz")
+    try:
+        assert fast.total_steps == 361 and fast.nWLvl == 4 and fast.t_s[-1] == 15 * 86400.0
+        o = orc.integrate_batch(na_case.p, na_case.env, np.zeros(g["lon0"].size, np.int32), g["lon0"], g["lat0"], g["v0"], g["m0"],
+                                g["h_bl"], g["phases"], post_all=False)
+        n_none = n_res = 0
+        for i in range(g["lon0"].size):
+            fast.h_bl = float(g["h_bl"][i])
+            with rh.injected_phases(g["phases"][i]):
+                res = fast.gen_track(g["lon0"][i], g["lat0"][i], g["v0"][i], g["m0"][i])
+            if g["status"][i] == 2:
+                assert res is None                                        # ventilation pre-check -> None (coupled_fast.py:241-244)
+                n_none += 1
+                continue
+            n_res += 1
+            assert res.status == g["status"][i] and res.y.shape[0] == 4
+            k = res.t.size
+            # bit-identical to the batched C-ABI path (and so to the oracle), whose comparison with the reference's
+            # numbers is test_cuda_vs_wide_reference / test_tracks_vs_reference_fixtures
+            assert k == o["n_time"][i] and res.nfev == o["nfev"][i]
+            assert np.array_equal(res.y.T, o["track"][i, :k]) and np.array_equal(res.t, fast.t_s[:k])
+            kk = min(k, int(g["n_time"][i]), 24)                          # first day: before any storm turns chaotic
+            err = np.abs(res.y.T[:kk] - g["track"][i, :kk]) / np.maximum(np.abs(g["track"][i, :kk]), 1e-3)
+            assert err.max() < 1e-4
+        assert n_none >= 1 and n_res >= 30
+        # batched form: same results
+        with rh.injected_phases(g["phases"][0]):
+            one = fast.gen_track(g["lon0"][0], g["lat0"][0], g["v0"][0], g["m0"][0])
+        many = fast.gen_tracks(g["lon0"][:5], g["lat0"][:5], g["v0"][:5], g["m0"][:5], h_bl=g["h_bl"][:5], phases=g["phases"][:5])
+        fast.h_bl = float(g["h_bl"][0])
+        assert (one is None) == (many[0] is None)
+    finally:
+        fast.close()
+
+
+def test_coupled_fast_shim_dydt_env_winds_vpot_vs_reference_fixtures(monkeypatch):
+    """fast.dydt, fast._env_winds (util/compute.py:201-202) and fast.f_vpot.ev (:162) against the reference's values."""
+    fast, rh = _shim(monkeypatch)
+    try:
+        g = golden("ref_rhs.npz")
+        worst = worst_w = 0.0
+        for i in range(g["lon"].size):
+            fast.h_bl = float(g["h_bl"][i])
+            fast.Fs_phases = g["phases"][i].reshape(60)
+            y = np.array([g["lon"][i], g["lat"][i], g["v"][i], g["m"][i]])
+            dy = fast.dydt(g["t"][i], y)
+            ref = g["dydt"][i]
+            worst = max(worst, float((np.abs(dy - ref) / np.maximum(np.abs(ref), 1e-12 + 1e-6 * np.abs(ref).max())).max()))
+            w = fast._env_winds(g["lon"][i], g["lat"][i], g["t"][i])
+            rw = g["env_winds"][i]
+            worst_w = max(worst_w, float((np.abs(w - rw) / np.maximum(np.abs(rw), 1e-6 + 1e-6 * np.abs(rw).max())).max()))
+        assert worst < 1e-9 and worst_w < 1e-9, (worst, worst_w)
+        b = golden("ref_bilinear.npz")
+        v = fast.f_vpot.ev(b["lon"], b["lat"])
+        ref = b["vals"][:, 15]
+        assert np.max(np.abs(v - ref) / np.maximum(np.abs(ref), 1e-3 * np.abs(ref).max())) < 1e-12
+        assert np.isscalar(fast.f_vpot.ev(300.0, 20.0)) or np.ndim(fast.f_vpot.ev(300.0, 20.0)) == 0
+    finally:
+        fast.close()

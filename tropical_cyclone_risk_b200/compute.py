@@ -221,6 +221,54 @@ def gather_years(local, years, n_tracks, n_steps, rank, world, device=None):
     return {k: np.stack([p[k] for p in per_year]) for k in _FIELDS}
 
 
+def run_downscaling_device(years, n_tracks, b, rank, world, device):
+    """The CUDA write-out path of run_downscaling: this rank's years are integrated into ONE device-resident block
+    (equal-sized year slots, unused ones NaN), the blocks of all ranks are copied into rank 0's gather buffer by the
+    copy engines over NVLink (gather.PeerGather, CUDA IPC; `world` device-to-device copies, no collective kernel), and
+    rank 0 alone brings the gathered block to the host -- one device->host copy for the whole job.  Returns the
+    year-ordered dict of arrays on rank 0 and None on the other ranks."""
+    import torch
+    from . import gather as tgather
+    from .pipeline import _Block
+    mine = shard_years(years, rank, world)
+    n_slots = (len(years) + world - 1) // world
+    engine, bounds = _session.engine(b.basin_id, device.index)
+    stream = torch.cuda.current_stream(device)
+    engine.set_stream(stream.cuda_stream)
+    blk = _Block(torch, device, n_slots, n_tracks, engine.n_steps, pinned=False)
+    blk.dev.fill_(float("nan"))
+    stats = []
+    if mine:
+        lon = lat = None
+        planes = []
+        for y in mine:
+            lon, lat, pl = _session.inputs.year_planes(_session.namelist, bounds, y)
+            planes.append(pl)
+        engine.alloc_tables(12 * len(mine), lon, lat)
+        for i, pl in enumerate(planes):
+            engine.upload_months(12 * i, pl)
+        # the rank's years fill the first len(mine) year slots of the block (a prefix of every section)
+        sub = _Block(torch, device, len(mine), n_tracks, engine.n_steps, pinned=False) if len(mine) != n_slots else blk
+        stats = engine.run_years_dev(np.arange(len(mine), dtype=np.int32) * 12, np.asarray(mine, dtype=np.int32),
+                                     _session.run_seed, n_tracks, sub.dptr)
+        if sub is not blk:
+            blk.copy_prefix_from(sub)
+    if world > 1:
+        pg = tgather.PeerGather(blk.dev.numel(), torch.float64, device, depth=1, dst="root")
+        pg.push(blk.dev, 0)
+        pg.finish()
+        if rank != 0:
+            return None
+        host = pg.buffer(0).cpu().numpy()                       # the single device->host copy of the job
+    else:
+        host = blk.dev.cpu().numpy()[None]
+    per_rank = [blk.views_of(host[r]) for r in range(world)]
+    per_year = [{k: per_rank[i % world][k][i // world] for k in _FIELDS} for i in range(len(years))]
+    out = {k: np.stack([p[k] for p in per_year]) for k in _FIELDS}
+    out["stats"] = stats
+    return out
+
+
 def get_fn_tracks(b, namelist=None):
     """util/compute.py:40-47"""
     nl = namelist or _session.namelist
@@ -242,9 +290,10 @@ def run_downscaling(basin_id, write=True, run_years_fn=None):
     """Runs the downscaling model in basin `basin_id` according to the namelist
     (util/compute.py:216-270): every year start_year..end_year, tracks_per_year tracks each.
 
-    Under torch.distributed (one process per GPU) the years are sharded over the ranks and
-    all-gathered; every rank returns the full result, rank 0 writes the track file.
-    `run_years_fn(years, n_tracks, b)` replaces the GPU call in host-logic tests."""
+    Under torch.distributed (one process per GPU) the years are sharded over the ranks; the finished tracks meet in
+    rank 0's memory through run_downscaling_device (device-resident, one device->host copy), rank 0 writes the track
+    file and returns the result, the other ranks return None.  `run_years_fn(years, n_tracks, b)` replaces the GPU call
+    in host-logic tests (NumPy blocks, gloo all-gather, every rank returns the full result)."""
     nl = _session.namelist
     n_tracks = nl.tracks_per_year
     b = TC_Basin(basin_id, nl)
@@ -259,11 +308,18 @@ def run_downscaling(basin_id, write=True, run_years_fn=None):
                 device = torch.device("cuda", torch.cuda.current_device())
     except ImportError:
         pass
-    mine = shard_years(years, rank, world)
-    fn = run_years_fn or run_years
-    local = fn(mine, n_tracks, b) if mine else None
     n_steps = int(nl.total_track_time_days * 24 * 60 * 60 / nl.output_interval_s) + 1
-    g = gather_years(local, years, n_tracks, n_steps, rank, world, device)
+    if run_years_fn is None:
+        import torch
+        if device is None:
+            device = torch.device("cuda", _current_device())
+        g = run_downscaling_device(years, n_tracks, b, rank, world, device)
+        if g is None:                                              # not the writing rank: nothing to hold on the host
+            return None
+    else:                                                          # host-logic tests: stand-in for the GPU call, gloo
+        mine = shard_years(years, rank, world)
+        local = run_years_fn(mine, n_tracks, b) if mine else None
+        g = gather_years(local, years, n_tracks, n_steps, rank, world, device)
     ny = len(years)
     out = dict(
         tc_lon=g["lon"].reshape(ny * n_tracks, n_steps), tc_lat=g["lat"].reshape(ny * n_tracks, n_steps),

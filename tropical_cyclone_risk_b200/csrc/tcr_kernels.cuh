@@ -25,7 +25,7 @@ __global__ void k_build_month(const float* __restrict__ planes, float4* __restri
     const size_t total = (size_t)ncx * ncy * TCR_REC_F4;
     planes += (size_t)blockIdx.y * TCR_N_FIELDS * nlat * nlon;
     rec += (size_t)blockIdx.y * total;
-    recb += (size_t)blockIdx.y * total;
+    if (recb) recb += (size_t)blockIdx.y * total;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int ch = (int)(idx % TCR_REC_F4);
         size_t cell = idx / TCR_REC_F4;
@@ -33,6 +33,7 @@ __global__ void k_build_month(const float* __restrict__ planes, float4* __restri
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ch < TCR_N_FIELDS) r = tcr_plane_quad(planes, ch, nlat, nlon, iy, ix);
         rec[idx] = r;
+        if (!recb) continue;
         uint4 b;
         if (ch < TCR_RECB_CH) {
             /* high words of the exactly widened corners */
@@ -48,6 +49,31 @@ __global__ void k_build_month(const float* __restrict__ planes, float4* __restri
                 const float f = (v & 3) == 0 ? q.x : (v & 3) == 1 ? q.y : (v & 3) == 2 ? q.z : q.w;
                 const uint32_t low3 = (uint32_t)__double2loint((double)f) >> 29;
                 w[v / 10 - w0] |= low3 << (3 * (v % 10));
+            }
+            b = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        recb[idx] = b;
+    }
+}
+
+/* integrator records of tables that already exist as float32 records (a REC = 1 kernel variant selected later) */
+__global__ void k_recb_from_rec(const float4* __restrict__ rec, uint4* __restrict__ recb, size_t total)
+{
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(idx % TCR_REC_F4);
+        const float4* cell = rec + (idx - ch);
+        uint4 b;
+        if (ch < TCR_RECB_CH) {
+            const float4 r = cell[ch];
+            b = make_uint4((uint32_t)__double2hiint((double)r.x), (uint32_t)__double2hiint((double)r.y),
+                           (uint32_t)__double2hiint((double)r.z), (uint32_t)__double2hiint((double)r.w));
+        } else {
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            const int w0 = (ch - TCR_RECB_CH) * 4;
+            for (int v = w0 * 10; v < (w0 + 4) * 10 && v < 4 * TCR_RECB_CH; ++v) {
+                const float4 q = cell[v >> 2];
+                const float f = (v & 3) == 0 ? q.x : (v & 3) == 1 ? q.y : (v & 3) == 2 ? q.z : q.w;
+                w[v / 10 - w0] |= ((uint32_t)__double2loint((double)f) >> 29) << (3 * (v % 10));
             }
             b = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -781,17 +807,15 @@ enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
 template <int THREADS, int MINB, int KSMEM, int CTA_LOCKSTEP, int REC, int PARK>
 __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
 {
-    static_assert(REC != 2 || KSMEM == 2, "record staging lives behind the eight stage vectors");
-    static_assert((PARK == 0 || KSMEM == 2) && (PARK == 0 || REC != 2), "state parking shares the staging area behind the stage vectors");
+    static_assert(REC == 0 || REC == 1, "record path: 0 float32 records, 1 integrator records");
+    static_assert(PARK == 0 || KSMEM == 2, "state parking shares the staging area behind the stage vectors");
     /* Stage storage, "stage" j = 0..7: K0 (FSAL derivative), K1..K5, K6, and the step's end state y_new.
      * KSMEM = 1: K1..K5 (dead during an RHS evaluation) live in shared memory, [stage][component][thread],
      * which frees 40 registers; KSMEM = 2: all eight (64 registers); KSMEM = 0: registers only. */
     extern __shared__ __align__(16) double k_smem[];
     double Kr[8][4] = {};
     double* const ks = k_smem + (KSMEM ? threadIdx.x : 0);
-    /* REC == 2: this thread's column of the record staging area [20][THREADS] uint4, which shares its first
-     * 17 x THREADS doubles with the drain-phase packing (used only between macro steps, behind CTA barriers) */
-    uint4* const rs = reinterpret_cast<uint4*>(k_smem + 32 * THREADS) + threadIdx.x;
+    bool cta_drained = false;          /* some thread of the CTA has seen the queue empty (refreshed at the slot-1 barrier) */
     auto in_smem = [](int j) { return KSMEM == 2 || (KSMEM == 1 && j >= 1 && j <= 5); };
     auto k_off = [](int j, int i) { return ((KSMEM == 2 ? j : j - 1) * 4 + i) * THREADS; };
     auto Kg = [&](int j, int i) -> double { return in_smem(j) ? ks[k_off(j, i)] : Kr[j][i]; };
@@ -864,7 +888,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
              * the live storms (17 words each: y, K0, t, h, g, ...) move through shared memory to the
              * lowest threads of the CTA; emptied warps then only meet the slot barriers. */
             const unsigned idle_b = __ballot_sync(TCR_FULL, mode == M_IDLE);
-            if (A.pack && __syncthreads_and(drained || idle_b == 0u)) {
+            /* nothing to pack before the queue runs dry: the CTA-wide vote (a barrier per macro step) only starts then */
+            const bool may_pack = A.pack && (((CTA_LOCKSTEP & 2) == 0) || cta_drained);
+            if (may_pack && __syncthreads_and(drained || idle_b == 0u)) {
                 __shared__ int w_act[THREADS / 32];
                 const int wid = threadIdx.x >> 5;
                 const unsigned act_b = ~idle_b;
@@ -965,6 +991,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                  * of once per warp; the CTA retires when its last warp runs dry */
                 /* CTA_LOCKSTEP = bit mask of the slots that re-align the warps (bit 0 always set) */
                 if (slot == 0) { if (__syncthreads_or(mode != M_IDLE) == 0) return; }
+                else if (slot == 1 && (CTA_LOCKSTEP & 2)) cta_drained = __syncthreads_or(drained) != 0;
                 else if ((CTA_LOCKSTEP >> slot) & 1) __syncthreads();
             } else {
                 if (slot == 0 && __ballot_sync(TCR_FULL, mode != M_IDLE) == 0u) return;   /* warp-uniform */
@@ -1023,7 +1050,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
             }
 
             double dy[4] = {0, 0, 0, 0};
-            TcrRhsAux aux = {0, 0, 0};
+            TcrRhsAux aux = {0, 0, 0, {0, 0, 0, 0}};
             if constexpr (PARK != 0) {
                 /* PARK: the RHS needs ~120 registers of its own and only (te, ye, ym, ftab, hbl) of the storm: the
                  * rest of the storm's state (12 doubles, 6 words) waits in shared memory while it runs -- the area
@@ -1040,7 +1067,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 pk[15 * THREADS] = __hiloint2double(nfev, (rejected ? 1 : 0) | (new_step ? 2 : 0) | (any_v ? 4 : 0) | (drained ? 8 : 0));
                 asm volatile("" ::: "memory");
             }
-            if (ev) { tcr_rhs<REC>(cx, ym, ftab, hbl, te, ye, dy, aux, rs, THREADS); }
+            if (ev) { tcr_rhs<REC>(cx, ym, ftab, hbl, te, ye, dy, aux); }
             if constexpr (PARK != 0) {
                 asm volatile("" ::: "memory");
                 const double* pk = k_smem + 32 * THREADS + threadIdx.x;
@@ -1196,6 +1223,26 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
             }
         }
     }
+}
+
+/* ======================================================================================== */
+/* single evaluations of Coupled_FAST.dydt (coupled_fast.py:196-207) and BetaAdvectionTrack._env_winds              */
+/* (bam_track.py:116-128) at given (t, y): the inner tier of the reference's seam and the test hook of rows a5-a11.  */
+/* One thread per evaluation, the same tcr_rhs the integrator runs.                                                   */
+/* ======================================================================================== */
+__global__ void __launch_bounds__(128) k_rhs_eval(const __grid_constant__ TcrCtx cx, int64_t n, const int32_t* __restrict__ ym,
+                                                  const double* __restrict__ t, const double* __restrict__ y,
+                                                  const double* __restrict__ h_bl, const double* __restrict__ ftab,
+                                                  double* __restrict__ dydt, double* __restrict__ env)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double yi[4] = {y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]};
+    double dy[4];
+    TcrRhsAux aux = {0, 0, 0, {0, 0, 0, 0}};
+    tcr_rhs<0>(cx, ym[i], ftab + (size_t)i * cx.p.n_steps * 4, 0.5 * cx.p.Ck / h_bl[i], t[i], yi, dy, aux);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { dydt[4 * i + k] = dy[k]; env[4 * i + k] = aux.wf[k]; }
 }
 
 /* ======================================================================================== */

@@ -130,6 +130,7 @@ struct tcr_handle {
     bool have_static = false, have_masks = false;
     /* tuning */
     int integ_variant = 17, oversub_permille = 1020, interp_variant = 0;
+    bool use_recb = false;       /* a REC = 1 variant is selected: tables also exist as integrator records */
     /* survival statistics of earlier tcr_run_years calls on this handle: size the first wave */
     double hint_kept_rate = 0.0, hint_pass_rate = 0.0;
     std::vector<double> hint_year_rate;     /* per year slot of the previous call (same n_years): survival differs by year */
@@ -312,8 +313,21 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 {
     if (!h) return set_err("null handle");
     if (integ_variant > 0) {
-        if (integ_variant > 28) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
+        if (integ_variant > 25) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
         h->integ_variant = integ_variant - 1;
+        const int v = h->integ_variant;
+        const bool need_recb = v == 21;                                   /* the REC = 1 variant */
+        if (need_recb && !h->use_recb) {
+            h->use_recb = true;
+            if (h->rec.p) {                                              /* tables already built: derive their twins */
+                CK(cudaSetDevice(h->device));
+                const size_t total = h->month_f4 * (size_t)h->n_ym;
+                if (h->recb.ensure(total * sizeof(uint4))) return -1;
+                k_recb_from_rec<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(h->rec.as<float4>(), h->recb.as<uint4>(), total);
+                CKK(h);
+                h->ctx.tab.recb = h->recb.as<uint4>();
+            }
+        }
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
     if (max_wave_slots > 0) h->max_slots = max_wave_slots;
@@ -432,11 +446,12 @@ int tcr_alloc_tables(tcr_handle* h, int n_ym, int nlat, int nlon, const double* 
     if (make_axis(h, lon, nlon, h->ax_lon, tb.lon) || make_axis(h, lat, nlat, h->ax_lat, tb.lat)) return -1;
     h->month_f4 = (size_t)(nlat - 1) * (nlon - 1) * TCR_REC_F4;
     if (h->rec.ensure(h->month_f4 * sizeof(float4) * (size_t)n_ym)) return -1;
-    if (h->recb.ensure(h->month_f4 * sizeof(uint4) * (size_t)n_ym)) return -1;
+    if (h->use_recb) { if (h->recb.ensure(h->month_f4 * sizeof(uint4) * (size_t)n_ym)) return -1; }
+    else h->recb.release();
     if (h->stage.ensure((size_t)TCR_N_FIELDS * nlat * nlon * sizeof(float))) return -1;
     h->nlat = nlat; h->nlon = nlon; h->n_ym = n_ym;
     tb.rec = h->rec.as<float4>();
-    tb.recb = h->recb.as<uint4>();
+    tb.recb = h->use_recb ? h->recb.as<uint4>() : nullptr;
     tb.ncx = nlon - 1; tb.ncy = nlat - 1; tb.n_ym = n_ym;
     return 0;
 }
@@ -450,7 +465,8 @@ int tcr_upload_month_dev(tcr_handle* h, int ym, const float* d_planes)
     {
         LaunchTimer lt_(h, TCR_K_BUILD);
         k_build_month<<<grid_for(h->month_f4, 256, h->num_sms), 256, 0, h->stream>>>(
-            d_planes, h->rec.as<float4>() + h->month_f4 * (size_t)ym, h->recb.as<uint4>() + h->month_f4 * (size_t)ym, h->nlat, h->nlon);
+            d_planes, h->rec.as<float4>() + h->month_f4 * (size_t)ym,
+            h->use_recb ? h->recb.as<uint4>() + h->month_f4 * (size_t)ym : nullptr, h->nlat, h->nlon);
     }
     CKK(h);
     return 0;
@@ -470,7 +486,7 @@ int tcr_upload_months(tcr_handle* h, int ym0, int n_months, const float* planes)
         LaunchTimer lt_(h, TCR_K_BUILD);
         dim3 grid((unsigned)grid_for(h->month_f4, 256, h->num_sms), (unsigned)n_months);
         k_build_month<<<grid, 256, 0, h->stream>>>(h->stage.as<float>(), h->rec.as<float4>() + h->month_f4 * (size_t)ym0,
-                                               h->recb.as<uint4>() + h->month_f4 * (size_t)ym0, h->nlat, h->nlon);
+                                               h->use_recb ? h->recb.as<uint4>() + h->month_f4 * (size_t)ym0 : nullptr, h->nlat, h->nlon);
     }
     CKK(h);
     return 0;
@@ -574,8 +590,10 @@ static int64_t max_lanes(const tcr_handle* h) { return (int64_t)h->num_sms * 576
 
 /* full: every slot owns a track / env / vmax row (tcr_integrate returns them for every storm); otherwise tracks
  * live in the pool and env winds / vmax are never stored per slot (k_gather forms them for the rows it emits) */
-static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_years, bool full)
+enum WsMode { WS_SLOTS = 0, WS_FULL = 1, WS_POOL = 2 };     /* slots only (coefficients, Fourier tables) / + per-slot rows / + track pool */
+static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_years, WsMode mode)
 {
+    const bool full = mode == WS_FULL;
     Workspace& w = h->ws;
     const int ns = h->ctx.p.n_steps;
     if (w.ns != ns) { w.release_all(); w.ns = ns; }
@@ -603,7 +621,7 @@ static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_yea
             if (w.track.ensure(c * ns * 32) || w.env.ensure(c * ns * 32) || w.vmax.ensure(c * ns * 8)) return -1;
             w.full_cap = slot_cap;
         }
-    } else {
+    } else if (mode == WS_POOL) {
         const int64_t rows = max_lanes(h) + std::max<int64_t>(4096, w.slot_cap / kPoolDiv);
         if (rows > w.pool_rows || w.track.bytes < (size_t)rows * ns * 32) {
             if (w.track.ensure((size_t)rows * ns * 32)) return -1;
@@ -644,7 +662,7 @@ static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned i
 
 }  // extern "C"
 
-template <int THREADS, int MINB, int KSMEM, int LOCKSTEP = 0, int REC = 1, int PARK = 0>
+template <int THREADS, int MINB, int KSMEM, int LOCKSTEP = 0, int REC = 0, int PARK = 0>
 static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_upper)
 {
     const int warps_per_cta = THREADS / 32;
@@ -655,12 +673,10 @@ static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_uppe
     a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
     { static const int pack_on = getenv("TCR_NO_PACK") ? 0 : 1; a.pack = pack_on; }
     a.pool_first = (unsigned int)grid * THREADS;                      /* lanes own rows [0, grid x THREADS) */
-    /* KSMEM 2: eight stage vectors + the 17-word staging area of the drain-phase packing, which the record
-     * staging of REC 2 (20 x 16 B per thread) overlays */
-    const size_t smem = KSMEM == 2 ? (size_t)(32 + (REC == 2 ? 40 : 18)) * THREADS * sizeof(double)
-                                   : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
-    cudaFuncSetAttribute(k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC, PARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    /* KSMEM 2: eight stage vectors + the 18-word staging area of the drain-phase packing */
+    const size_t smem = KSMEM == 2 ? (size_t)(32 + 18) * THREADS * sizeof(double) : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
     LaunchTimer lt_(h, TCR_K_INTEGRATE);
+    cudaFuncSetAttribute(k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC, PARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC, PARK><<<grid, THREADS, smem, h->stream>>>(h->ctx, a);
 }
 
@@ -688,13 +704,10 @@ static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
     case 18: launch_integrate_variant<192, 3, 2, 63>(h, a, n_upper); break;      /* 96 registers, 18 warps/SM */
     case 19: launch_integrate_variant<224, 2, 2, 63>(h, a, n_upper); break;      /* 144 registers, 14 warps/SM */
     case 20: launch_integrate_variant<384, 1, 2, 63>(h, a, n_upper); break;      /* one 12-warp CTA per SM */
-    case 21: launch_integrate_variant<192, 2, 2, 63, 0>(h, a, n_upper); break;   /* round-1 record path (float32 records, F2F) */
-    case 22: launch_integrate_variant<192, 2, 2, 63, 2>(h, a, n_upper); break;   /* records staged in shared memory by cp.async */
-    case 23: launch_integrate_variant<384, 1, 2, 63, 2>(h, a, n_upper); break;
-    case 24: launch_integrate_variant<192, 2, 2, 63, 1, 1>(h, a, n_upper); break;   /* PARK: storm state parked in smem during the RHS */
-    case 25: launch_integrate_variant<224, 2, 2, 63, 1, 1>(h, a, n_upper); break;   /* 144 registers, 14 warps/SM */
-    case 26: launch_integrate_variant<256, 2, 2, 63, 1, 1>(h, a, n_upper); break;   /* 128 registers, 16 warps/SM */
-    case 27: launch_integrate_variant<288, 2, 2, 63, 1, 1>(h, a, n_upper); break;   /* 112 registers, 18 warps/SM */
+    case 21: launch_integrate_variant<192, 2, 2, 63, 1>(h, a, n_upper); break;   /* integrator records: widened corners, ten 256-bit loads, no F2F */
+    case 22: launch_integrate_variant<192, 2, 2, 63, 0, 1>(h, a, n_upper); break;   /* PARK: storm state parked in smem during the RHS */
+    case 23: launch_integrate_variant<224, 2, 2, 63, 0, 1>(h, a, n_upper); break;   /* 128 registers, 14 warps/SM */
+    case 24: launch_integrate_variant<256, 2, 2, 63, 0, 1>(h, a, n_upper); break;   /* 128 registers, 16 warps/SM */
     default: return set_err("unknown integrate variant %d", h->integ_variant);
     }
     CKK(h);
@@ -716,7 +729,7 @@ int tcr_integrate(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon
     if (!h->rec.p || !h->have_static) return set_err("tcr_integrate: tables / static fields not uploaded");
     if (n > 0x7fffffff) return set_err("tcr_integrate: n too large");
     CK(cudaSetDevice(h->device));
-    if (ws_ensure(h, 0, n, 1, true)) return -1;
+    if (ws_ensure(h, 0, n, 1, WS_FULL)) return -1;
     Workspace& w = h->ws;
     const int ns = h->ctx.p.n_steps;
     cudaStream_t s = h->stream;
@@ -775,6 +788,48 @@ int tcr_integrate(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon
     if (flags) CK(cudaMemcpyAsync(flags, w.flags.p, n * 4, out_kind, s));
     CK(cudaStreamSynchronize(s));
     ph.release();
+    return 0;
+}
+
+/* ---- single RHS evaluations (inner tier of the seam, test hook) --------------------------------- */
+int tcr_rhs_eval(tcr_handle* h, int64_t n, const int32_t* ym, const double* t, const double* y, const double* h_bl,
+                 const double* phases, double* dydt, double* env_winds)
+{
+    if (!h) return set_err("null handle");
+    if (n < 0) return set_err("tcr_rhs_eval: negative n");
+    if (n == 0) return 0;
+    if (!ym || !t || !y || !h_bl || !phases || !dydt || !env_winds) return set_err("tcr_rhs_eval: null argument");
+    if (!h->rec.p || !h->have_static) return set_err("tcr_rhs_eval: tables / static fields not uploaded");
+    if (n > 0x7fffffff) return set_err("tcr_rhs_eval: n too large");
+    for (int64_t i = 0; i < n; ++i)
+        if (ym[i] < 0 || ym[i] >= h->n_ym) return set_err("tcr_rhs_eval: ym[%lld]=%d out of range", (long long)i, ym[i]);
+    CK(cudaSetDevice(h->device));
+    if (ws_ensure(h, 0, n, 1, WS_SLOTS)) return -1;
+    Workspace& w = h->ws;
+    cudaStream_t s = h->stream;
+    DevBuf in, out;
+    if (in.ensure((size_t)n * (TCR_N_PHASES + 6) * 8) || out.ensure((size_t)n * 64)) return -1;
+    double* d_ph = in.as<double>();
+    double* d_t = d_ph + n * TCR_N_PHASES;
+    double* d_y = d_t + n;
+    double* d_hbl = d_y + 4 * n;
+    CK(cudaMemcpyAsync(d_ph, phases, (size_t)n * TCR_N_PHASES * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_t, t, n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_y, y, n * 32, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_hbl, h_bl, n * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(w.s_ym.p, ym, n * 4, cudaMemcpyHostToDevice, s));
+    {
+        LaunchTimer lt_(h, TCR_K_COEF);
+        k_coef_from_phases<<<(unsigned)((n * TCR_N_PHASES + 255) / 256), 256, 0, s>>>(h->ctx, n, d_ph, w.coef.as<double2>());
+        CKK(h);
+    }
+    if (launch_fourier_table(h, n, nullptr)) return -1;
+    k_rhs_eval<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(h->ctx, n, w.s_ym.as<int32_t>(), d_t, d_y, d_hbl, w.ftab.as<double>(),
+                                                           out.as<double>(), out.as<double>() + 4 * n);
+    CKK(h);
+    CK(cudaMemcpyAsync(dydt, out.p, n * 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(env_winds, out.as<double>() + 4 * n, n * 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return 0;
 }
 
@@ -872,8 +927,8 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
             int64_t slot_cap = std::min(att_cap, std::max<int64_t>(4096, (int64_t)((double)att_cap * pass_est) + 1024));
             w0.env.release(); w0.vmax.release();                       /* only tcr_integrate keeps per-slot env / vmax rows */
             if (w0.full_cap > 0) { w0.track.release(); w0.full_cap = 0; w0.pool_rows = 0; }
-            if (ws_ensure(h, std::max(att_cap, w0.att_cap), std::max(slot_cap, w0.slot_cap), n_years, false)) return -1;
-        } else if (ws_ensure(h, w0.att_cap, w0.slot_cap, n_years, false)) {
+            if (ws_ensure(h, std::max(att_cap, w0.att_cap), std::max(slot_cap, w0.slot_cap), n_years, WS_POOL)) return -1;
+        } else if (ws_ensure(h, w0.att_cap, w0.slot_cap, n_years, WS_POOL)) {
             return -1;
         }
     }

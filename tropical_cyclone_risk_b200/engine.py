@@ -207,6 +207,16 @@ class Engine:
             _ptr(out["nfev"]), _ptr(out["flags"]), 0))
         return out
 
+    def rhs_eval(self, ym, t, y, h_bl, phases):
+        """Coupled_FAST.dydt(t, y) and _env_winds(y[0], y[1], t) for n independent states: (dydt [n][4], env [n][4])."""
+        ym, t, h_bl = _arr(ym, np.int32), _arr(t, np.float64), _arr(h_bl, np.float64)
+        n = t.size
+        y = _arr(y, np.float64).reshape(n, 4)
+        phases = _arr(phases, np.float64).reshape(n, 60)
+        dydt, env = np.empty((n, 4)), np.empty((n, 4))
+        _lib.check(self.lib.tcr_rhs_eval(self._h, n, _ptr(ym), _ptr(t), _ptr(y), _ptr(h_bl), _ptr(phases), _ptr(dydt), _ptr(env)))
+        return dydt, env
+
     def seed_attempts(self, ym_base, year_key, run_seed, k0, n):
         out = dict(code=np.zeros(n, np.int32), basin=np.zeros(n, np.int32), month=np.zeros(n, np.int32),
                    lon=np.zeros(n), lat=np.zeros(n), v0=np.zeros(n), m0=np.zeros(n), pi_gen=np.zeros(n))

@@ -17,7 +17,7 @@ class _Block:
     """One result block: flat float64 buffer on the device, pinned twin on the host, and the
     section offsets of the 9-tuple inside it."""
 
-    def __init__(self, torch, dev, n_years, n_tracks, n_steps):
+    def __init__(self, torch, dev, n_years, n_tracks, n_steps, pinned=True):
         rows = n_years * n_tracks
         self.shapes = [("lon", (n_years, n_tracks, n_steps)), ("lat", (n_years, n_tracks, n_steps)),
                        ("v", (n_years, n_tracks, n_steps)), ("m", (n_years, n_tracks, n_steps)),
@@ -27,7 +27,7 @@ class _Block:
         self.offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         total = int(self.offsets[-1])
         self.dev = torch.empty(total, dtype=torch.float64, device=dev)
-        self.host = torch.empty(total, dtype=torch.float64).pin_memory()
+        self.host = torch.empty(total, dtype=torch.float64).pin_memory() if pinned else None
         self.rows = rows
         self.dptr = {name: self.dev.data_ptr() + int(self.offsets[i]) * 8 for i, (name, _) in enumerate(self.shapes)}
         self.dptr["tc_basin"] = self.dev.data_ptr() + int(self.offsets[len(self.shapes)]) * 8
@@ -36,12 +36,24 @@ class _Block:
         self.nbytes = total * 8
 
     def host_views(self):
-        h = self.host.numpy()
+        return self.views_of(self.host.numpy())
+
+    def views_of(self, h):
+        """The sections of a flat float64 host array laid out like this block."""
         out = {name: h[int(self.offsets[i]):int(self.offsets[i + 1])].reshape(shape)
                for i, (name, shape) in enumerate(self.shapes)}
         b0 = int(self.offsets[len(self.shapes)])
         out["tc_basin"] = h[b0:].view(np.int32)[:self.rows].reshape(self.shapes[6][1])
         return out
+
+    def copy_prefix_from(self, sub):
+        """Device copy of a block with fewer year slots into the leading year slots of every section of this one."""
+        for i, (name, shape) in enumerate(self.shapes):
+            n = int(np.prod(sub.shapes[i][1]))
+            self.dev[int(self.offsets[i]):int(self.offsets[i]) + n].copy_(sub.dev[int(sub.offsets[i]):int(sub.offsets[i]) + n])
+        b0, s0 = int(self.offsets[len(self.shapes)]), int(sub.offsets[len(sub.shapes)])
+        n = (sub.rows + 1) // 2
+        self.dev[b0:b0 + n].copy_(sub.dev[s0:s0 + n])
 
 
 class YearPipeline:
