@@ -101,6 +101,8 @@ typedef struct tcr_year_stats {
     int64_t wasted_rhs_evals;  /* their dydt evaluations                                         */
     int32_t n_kept;            /* == n_tracks on success                                         */
     int32_t n_waves;
+    int64_t redraw_exhausted;  /* attempts whose ocean-point redraw chain (compute.py:146-148, unbounded in the reference)
+                                  hit tcr_params.max_redraws and were dropped: expected 0 (max_redraws = 64)          */
 } tcr_year_stats;
 
 typedef struct tcr_handle tcr_handle;
@@ -200,6 +202,21 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
                   double* lon, double* lat, double* v, double* m, double* vmax, double* env,
                   double* tc_month, int32_t* tc_basin, double* n_seeds,
                   tcr_year_stats* stats, int on_device);
+
+/* ---- within-year sharding (partition mode 2) --------------------------------------- */
+/* replaces: nothing in the reference (it gives a year to ONE dask process, util/compute.py:224-230); needed when one
+ * (basin, year) is larger than a GPU should take (BASELINE configs[4]: 50 000 tracks / year).  After tcr_set_shard(h,
+ * rank, world, fn, user) every tcr_run_years call on `h` is COLLECTIVE over `world` handles (one per GPU, all called
+ * with the same arguments): every rank seeds every attempt (cheap), integrates the attempts k with k % world == rank,
+ * and once per wave the ranks exchange, through `fn`, the per-attempt kept flags and the counted-seed histograms -- so
+ * that all of them select the same first n_tracks survivors in attempt order: the result does not depend on world.
+ * Each rank then holds the rows whose storms it integrated; every other row of its lon / lat / v / m / vmax / env
+ * arrays is all-zero bits (merge = integer sum over ranks); tc_month, tc_basin, n_seeds are complete on every rank.
+ * Of tcr_year_stats, attempts / counted_seeds / n_kept / n_waves are global, the other counters this rank's share.
+ * fn(user, d_buf, count, dtype, op, cuda_stream): in-place all-reduce of `count` elements at device pointer d_buf over
+ * the group, stream-ordered on `cuda_stream`; dtype 0 = uint8, 1 = int32, 2 = int64; op 0 = sum, 1 = min; 0 on success. */
+typedef int (*tcr_allreduce_fn)(void* user, void* d_buf, int64_t count, int dtype, int op, void* cuda_stream);
+int tcr_set_shard(tcr_handle* h, int rank, int world, tcr_allreduce_fn fn, void* user);
 
 /* seeding only: evaluate attempts [k0, k0+n) of one year -> per-attempt records (test hook
  * for util/compute.py:136-175).  code: 0 = not a seed, 1 = counted (PI <= 35), 2 = passed,

@@ -144,7 +144,7 @@ def test_integrate_golden_seeds_bit_exact(na_case, na_eng):
     _check_integrate(na_eng, na_case, (np.zeros(n, np.int32), g["lon0"], g["lat0"], g["v0"], g["m0"], g["h_bl"], g["phases"]))
 
 
-@pytest.mark.parametrize("variant", list(range(1, 26)))
+@pytest.mark.parametrize("variant", list(range(1, 22)))
 def test_integrate_random_bit_exact(na_case, na_eng, variant):
     """every register-budget variant of the integrate kernel (tcr_set_tuning)"""
     na_eng.set_tuning(integ_variant=variant)
@@ -522,3 +522,17 @@ def test_prepare_month_on_device(basin, descending):
         assert _same(a, b)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("basin", ["NI", "EP", "SP"])
+def test_redraw_chains_never_exhausted(basin):
+    """The reference redraws the ocean point in an unbounded loop (util/compute.py:146-148); here the chain is bounded
+    by tcr_params.max_redraws (64) and an exhausted attempt would be dropped -- tcr_year_stats counts them: none, even in
+    the land-heavy boxes."""
+    case = Case(basin, [2001])
+    eng = _engine(case)
+    try:
+        r = eng.run_years([0], [2001], 17, 30)
+    finally:
+        eng.close()
+    assert r["stats"][0]["n_kept"] == 30 and r["stats"][0]["redraw_exhausted"] == 0

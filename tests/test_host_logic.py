@@ -31,7 +31,7 @@ def test_params_struct_matches_header():
     # 8-byte members only + 4 int32 -> no padding surprises; the numbers are those of include/tcrisk.h
     n_doubles = 8 + 2 * 5 + 4 + 1 + 4 + 2 + 1 + 7 + 7 + 5 + 4 + 15
     assert ctypes.sizeof(params.TcrParams) == n_doubles * 8 + 16
-    assert ctypes.sizeof(params.TcrYearStats) == 9 * 8 + 8
+    assert ctypes.sizeof(params.TcrYearStats) == 9 * 8 + 8 + 8
 
 
 def test_product_never_imports_oracle():
@@ -168,3 +168,41 @@ def test_trackfile_schema_roundtrip(tmp_path):
     assert list(f["basin"]) == ["AU", "EP", "NA", "NI", "SI", "SP", "WP"]
     assert list(f["tc_basins"]) == list(out["tc_basins"])
     assert f["seeds_per_month"].shape == (2, 7, 12) and f["time"][-1] == 15 * 86400.0
+
+
+def _merge_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tropical_cyclone_risk_b200 import gather
+        rng = np.random.default_rng(3)
+        full = rng.normal(size=(6, 50))
+        full[:, 40:] = np.nan                                       # NaN padding
+        full[1, 3], full[4, 7] = -0.0, 0.0                          # signed zeros survive an integer sum, not a float one
+        block = np.zeros_like(full)
+        block[rank::world] = full[rank::world]                      # rows this rank "integrated"; the others stay zero bits
+        t = torch.from_numpy(block.reshape(-1).copy())
+        gather.merge_sharded_block(t)
+        q.put((rank, t.numpy().reshape(full.shape).view(np.int64).tolist(), full.view(np.int64).tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_merge_sharded_block_is_exact_gloo_world2():
+    """The write-out merge of within-year sharding: integer sum of float64 bit patterns over ranks (gloo, world 2)."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_merge_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, merged, full in got:
+        assert merged == full

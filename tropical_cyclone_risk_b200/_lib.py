@@ -14,7 +14,7 @@ SYMBOLS = (
     "tcr_env_interp", "tcr_integrate", "tcr_run_years", "tcr_seed_attempts", "tcr_set_tuning",
     "tcr_launch_count", "tcr_set_interp_variant", "tcr_host_alloc", "tcr_host_free",
     "tcr_set_timing", "tcr_kernel_time", "tcr_poi_vmax", "tcr_exceedance", "tcr_prepare_month",
-    "tcr_wind_stats", "tcr_set_entropy_table", "tcr_thermo_month", "tcr_rhs_eval",
+    "tcr_wind_stats", "tcr_set_entropy_table", "tcr_thermo_month", "tcr_rhs_eval", "tcr_set_shard",
 )
 
 _lib = None
@@ -23,6 +23,10 @@ c_i32p = C.POINTER(C.c_int32)
 c_u32p = C.POINTER(C.c_uint32)
 c_f64p = C.POINTER(C.c_double)
 c_f32p = C.POINTER(C.c_float)
+
+
+# tcr_allreduce_fn (include/tcrisk.h): int fn(void* user, void* d_buf, int64 count, int dtype, int op, void* stream)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p)
 
 
 class TcrError(RuntimeError):
@@ -67,6 +71,7 @@ def load():
     lib.tcr_set_entropy_table.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     lib.tcr_thermo_month.argtypes = [vp, C.c_int64, C.c_int, vp, vp, vp, vp, vp, C.c_double, C.c_int, vp, vp, vp, C.c_int]
     lib.tcr_rhs_eval.argtypes = [vp, C.c_int64] + [vp] * 7
+    lib.tcr_set_shard.argtypes = [vp, C.c_int, C.c_int, ALLREDUCE_FN, vp]
     lib.tcr_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.tcr_host_free.argtypes = [vp]
     _lib = lib

@@ -230,6 +230,8 @@ def run_downscaling_device(years, n_tracks, b, rank, world, device):
     import torch
     from . import gather as tgather
     from .pipeline import _Block
+    if world > 1 and len(years) < world and os.environ.get("TCR_SHARD", "auto") != "years":
+        return _run_downscaling_within_year(years, n_tracks, b, rank, world, device)
     mine = shard_years(years, rank, world)
     n_slots = (len(years) + world - 1) // world
     engine, bounds = _session.engine(b.basin_id, device.index)
@@ -265,6 +267,43 @@ def run_downscaling_device(years, n_tracks, b, rank, world, device):
     per_rank = [blk.views_of(host[r]) for r in range(world)]
     per_year = [{k: per_rank[i % world][k][i // world] for k in _FIELDS} for i in range(len(years))]
     out = {k: np.stack([p[k] for p in per_year]) for k in _FIELDS}
+    out["stats"] = stats
+    return out
+
+
+def _run_downscaling_within_year(years, n_tracks, b, rank, world, device):
+    """Fewer years than GPUs (BASELINE configs[4]: one WP year of 50 000 tracks on 8 GPUs): every rank runs EVERY year,
+    integrating the seed attempts k with k % world == rank (Engine.set_shard; one exchange of kept flags and counted-seed
+    histograms per wave over NCCL), so each rank holds the rows of the storms it integrated and zero bits elsewhere;
+    the blocks merge on rank 0 by an integer sum of the float64 bit patterns (dist.reduce), then one device->host copy."""
+    import torch
+    import torch.distributed as dist
+    from . import gather as tgather
+    from .pipeline import _Block
+    engine, bounds = _session.engine(b.basin_id, device.index)
+    stream = torch.cuda.current_stream(device)
+    engine.set_stream(stream.cuda_stream)
+    engine.set_shard(rank, world, tgather.dist_allreduce(device))
+    try:
+        lon = lat = None
+        planes = []
+        for y in years:
+            lon, lat, pl = _session.inputs.year_planes(_session.namelist, bounds, y)
+            planes.append(pl)
+        engine.alloc_tables(12 * len(years), lon, lat)
+        for i, pl in enumerate(planes):
+            engine.upload_months(12 * i, pl)
+        blk = _Block(torch, device, len(years), n_tracks, engine.n_steps, pinned=False)
+        stats = engine.run_years_dev(np.arange(len(years), dtype=np.int32) * 12, np.asarray(years, dtype=np.int32),
+                                     _session.run_seed, n_tracks, blk.dptr)
+    finally:
+        engine.set_shard(0, 1)
+    n_track_words = int(blk.offsets[6])                               # lon, lat, v, m, vmax, env: the sharded sections
+    dist.reduce(blk.dev[:n_track_words].view(torch.int64), dst=0, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return None
+    v = blk.views_of(blk.dev.cpu().numpy())
+    out = {k: np.array(v[k]) for k in _FIELDS}
     out["stats"] = stats
     return out
 

@@ -10,74 +10,24 @@
 /* ======================================================================================== */
 /* table builders: planes -> cell records                                                    */
 /* ======================================================================================== */
-/* one month: planes [19][nlat][nlon] float32 -> rec [ncy][ncx][20] float4 (corner quads) and the
- * integrator's widened twin recb [ncy][ncx][20] uint4 (tcr_device.cuh "integrator records")      */
-/* blockIdx.y = month of a batch: planes [n][19][nlat][nlon] -> rec / recb [n][ncy][ncx][20] */
-__device__ __forceinline__ float4 tcr_plane_quad(const float* __restrict__ planes, int ch, int nlat, int nlon, int iy, int ix)
-{
-    const float* p = planes + (size_t)ch * nlat * nlon + (size_t)iy * nlon + ix;
-    return make_float4(p[0], p[nlon], p[1], p[nlon + 1]);
-}
-
-__global__ void k_build_month(const float* __restrict__ planes, float4* __restrict__ rec, uint4* __restrict__ recb, int nlat, int nlon)
+/* one month: planes [19][nlat][nlon] float32 -> rec [ncy][ncx][20] float4 (corner quads)      */
+/* blockIdx.y = month of a batch: planes [n][19][nlat][nlon] -> rec [n][ncy][ncx][20] */
+__global__ void k_build_month(const float* __restrict__ planes, float4* __restrict__ rec, int nlat, int nlon)
 {
     const int ncx = nlon - 1, ncy = nlat - 1;
     const size_t total = (size_t)ncx * ncy * TCR_REC_F4;
     planes += (size_t)blockIdx.y * TCR_N_FIELDS * nlat * nlon;
     rec += (size_t)blockIdx.y * total;
-    if (recb) recb += (size_t)blockIdx.y * total;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         int ch = (int)(idx % TCR_REC_F4);
         size_t cell = idx / TCR_REC_F4;
         int ix = (int)(cell % ncx), iy = (int)(cell / ncx);
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ch < TCR_N_FIELDS) r = tcr_plane_quad(planes, ch, nlat, nlon, iy, ix);
+        if (ch < TCR_N_FIELDS) {
+            const float* p = planes + (size_t)ch * nlat * nlon + (size_t)iy * nlon + ix;
+            r = make_float4(p[0], p[nlon], p[1], p[nlon + 1]);
+        }
         rec[idx] = r;
-        if (!recb) continue;
-        uint4 b;
-        if (ch < TCR_RECB_CH) {
-            /* high words of the exactly widened corners */
-            b = make_uint4((uint32_t)__double2hiint((double)r.x), (uint32_t)__double2hiint((double)r.y),
-                           (uint32_t)__double2hiint((double)r.z), (uint32_t)__double2hiint((double)r.w));
-        } else {
-            /* slots 18, 19: the three mantissa bits of every corner that do not fit the high word; value
-             * v = 4 * channel + corner sits in word v / 10 at bits 3 * (v % 10) .. + 2 */
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
-            const int w0 = (ch - TCR_RECB_CH) * 4;
-            for (int v = w0 * 10; v < (w0 + 4) * 10 && v < 4 * TCR_RECB_CH; ++v) {
-                const float4 q = tcr_plane_quad(planes, v >> 2, nlat, nlon, iy, ix);
-                const float f = (v & 3) == 0 ? q.x : (v & 3) == 1 ? q.y : (v & 3) == 2 ? q.z : q.w;
-                const uint32_t low3 = (uint32_t)__double2loint((double)f) >> 29;
-                w[v / 10 - w0] |= low3 << (3 * (v % 10));
-            }
-            b = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        recb[idx] = b;
-    }
-}
-
-/* integrator records of tables that already exist as float32 records (a REC = 1 kernel variant selected later) */
-__global__ void k_recb_from_rec(const float4* __restrict__ rec, uint4* __restrict__ recb, size_t total)
-{
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int ch = (int)(idx % TCR_REC_F4);
-        const float4* cell = rec + (idx - ch);
-        uint4 b;
-        if (ch < TCR_RECB_CH) {
-            const float4 r = cell[ch];
-            b = make_uint4((uint32_t)__double2hiint((double)r.x), (uint32_t)__double2hiint((double)r.y),
-                           (uint32_t)__double2hiint((double)r.z), (uint32_t)__double2hiint((double)r.w));
-        } else {
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
-            const int w0 = (ch - TCR_RECB_CH) * 4;
-            for (int v = w0 * 10; v < (w0 + 4) * 10 && v < 4 * TCR_RECB_CH; ++v) {
-                const float4 q = cell[v >> 2];
-                const float f = (v & 3) == 0 ? q.x : (v & 3) == 1 ? q.y : (v & 3) == 2 ? q.z : q.w;
-                w[v / 10 - w0] |= ((uint32_t)__double2loint((double)f) >> 29) << (3 * (v % 10));
-            }
-            b = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-        recb[idx] = b;
     }
 }
 
@@ -804,11 +754,9 @@ enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
  * table is read from HBM/L2 (64 B per evaluation); only emitted samples go to HBM.
  * THREADS x MINB fixes the register budget (launch bounds): <256,1> 255 registers, <128,3> 168,
  * <128,4> 128 -- chosen at run time by tcr_set_tuning, default by measurement.   */
-template <int THREADS, int MINB, int KSMEM, int CTA_LOCKSTEP, int REC, int PARK>
+template <int THREADS, int MINB, int KSMEM, int CTA_LOCKSTEP>
 __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
 {
-    static_assert(REC == 0 || REC == 1, "record path: 0 float32 records, 1 integrator records");
-    static_assert(PARK == 0 || KSMEM == 2, "state parking shares the staging area behind the stage vectors");
     /* Stage storage, "stage" j = 0..7: K0 (FSAL derivative), K1..K5, K6, and the step's end state y_new.
      * KSMEM = 1: K1..K5 (dead during an RHS evaluation) live in shared memory, [stage][component][thread],
      * which frees 40 registers; KSMEM = 2: all eight (64 registers); KSMEM = 0: registers only. */
@@ -1051,38 +999,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
 
             double dy[4] = {0, 0, 0, 0};
             TcrRhsAux aux = {0, 0, 0, {0, 0, 0, 0}};
-            if constexpr (PARK != 0) {
-                /* PARK: the RHS needs ~120 registers of its own and only (te, ye, ym, ftab, hbl) of the storm: the
-                 * rest of the storm's state (12 doubles, 6 words) waits in shared memory while it runs -- the area
-                 * the drain-phase packing uses between macro steps -- which brings the kernel under 128 / 144
-                 * registers without local-memory spills, i.e. 16 / 14 warps per SM instead of 12.  The empty asm
-                 * statements keep the compiler from forwarding the stores to the loads. */
-                double* pk = k_smem + 32 * THREADS + threadIdx.x;
-                pk[0 * THREADS] = y[0]; pk[1 * THREADS] = y[1]; pk[2 * THREADS] = y[2]; pk[3 * THREADS] = y[3];
-                pk[4 * THREADS] = t; pk[5 * THREADS] = h; pk[6 * THREADS] = h_abs; pk[7 * THREADS] = t_new;
-                pk[8 * THREADS] = g; pk[9 * THREADS] = min_step; pk[10 * THREADS] = h0; pk[11 * THREADS] = d1;
-                pk[12 * THREADS] = __longlong_as_double((long long)sid);
-                pk[13 * THREADS] = __hiloint2double(n_out, n_attempts);
-                pk[14 * THREADS] = __hiloint2double(status, (int)row);
-                pk[15 * THREADS] = __hiloint2double(nfev, (rejected ? 1 : 0) | (new_step ? 2 : 0) | (any_v ? 4 : 0) | (drained ? 8 : 0));
-                asm volatile("" ::: "memory");
-            }
-            if (ev) { tcr_rhs<REC>(cx, ym, ftab, hbl, te, ye, dy, aux); }
-            if constexpr (PARK != 0) {
-                asm volatile("" ::: "memory");
-                const double* pk = k_smem + 32 * THREADS + threadIdx.x;
-                y[0] = pk[0 * THREADS]; y[1] = pk[1 * THREADS]; y[2] = pk[2 * THREADS]; y[3] = pk[3 * THREADS];
-                t = pk[4 * THREADS]; h = pk[5 * THREADS]; h_abs = pk[6 * THREADS]; t_new = pk[7 * THREADS];
-                g = pk[8 * THREADS]; min_step = pk[9 * THREADS]; h0 = pk[10 * THREADS]; d1 = pk[11 * THREADS];
-                sid = (int64_t)__double_as_longlong(pk[12 * THREADS]);
-                n_out = __double2hiint(pk[13 * THREADS]); n_attempts = __double2loint(pk[13 * THREADS]);
-                status = __double2hiint(pk[14 * THREADS]); row = (unsigned int)__double2loint(pk[14 * THREADS]);
-                nfev = __double2hiint(pk[15 * THREADS]);
-                const int fl = __double2loint(pk[15 * THREADS]);
-                rejected = fl & 1; new_step = (fl & 2) != 0; any_v = (fl & 4) != 0; drained = (fl & 8) != 0;
-                trk = A.track + (A.track_row ? (size_t)row : (size_t)sid) * row_doubles;
-            }
-            if (ev) ++nfev;
+            if (ev) { tcr_rhs(cx, ym, ftab, hbl, te, ye, dy, aux); ++nfev; }
 
             /* ---- consume ---- */
             if (mode == M_RK) {
@@ -1240,7 +1157,7 @@ __global__ void __launch_bounds__(128) k_rhs_eval(const __grid_constant__ TcrCtx
     const double yi[4] = {y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]};
     double dy[4];
     TcrRhsAux aux = {0, 0, 0, {0, 0, 0, 0}};
-    tcr_rhs<0>(cx, ym[i], ftab + (size_t)i * cx.p.n_steps * 4, 0.5 * cx.p.Ck / h_bl[i], t[i], yi, dy, aux);
+    tcr_rhs(cx, ym[i], ftab + (size_t)i * cx.p.n_steps * 4, 0.5 * cx.p.Ck / h_bl[i], t[i], yi, dy, aux);
 #pragma unroll
     for (int k = 0; k < 4; ++k) { dydt[4 * i + k] = dy[k]; env[4 * i + k] = aux.wf[k]; }
 }
@@ -1380,6 +1297,7 @@ struct SeedArgs {
     int32_t* code; int32_t* basin; int32_t* month;
     double* lon; double* lat; double* v0; double* m0; double* pi_gen;      /* pi_gen may be NULL */
     unsigned int* blk_count;            /* [gridDim.x] attempts of the block that go on to gen_track (may be NULL) */
+    int rank, world;                    /* within-year sharding: this rank integrates the attempts k with k % world == rank */
 };
 
 __device__ __forceinline__ double tcr_mask_at(const uint2 r[4], int b, const TcrCell& c)
@@ -1437,34 +1355,45 @@ __global__ void __launch_bounds__(256) k_seed(const __grid_constant__ TcrCtx cx,
             double val = tcr_mask_at(r, i, c);
             if (val > best) { best = val; bi = i; }
         }
-        TcrCell ce;
-        tcr_cell_at(cx.tab.lon, cx.tab.lat, gen_lon, gen_lat, ce);
-        const float4* rec = tcr_record(cx.tab, A.ym_base[yr] + mon - 1, ce);
-        pi = tcr_bilin(__ldg(rec + CH_VPOT), ce);
         double q = (fabs(gen_lat) - p.lat_vort_fac) / 12.0;
         if (q < 0.0) q = 0.0;
         if (q > 1.0) q = 1.0;
         const double prob = tcr_pow(q, p.lat_vort_power[bi]);
-        tcr_draw2(A.run_seed, key, k, 2, 0, u);
-        double bs, bc;
-        tcr_sincos2pi(u[1], &bs, &bc);
-        const double randn = sqrt(-2.0 * tcr_log(1.0 - u[0])) * bc;
-        v0 = p.seed_v_init + randn;
-        const double rh = tcr_bilin(__ldg(rec + CH_RH), ce);
-        const double mi = p.minit_amp / (1.0 + tcr_exp(-(rh - p.minit_center) * p.minit_slope)) + p.minit_offset;
-        m0 = mi > 0.0 ? mi : 0.0;
+        const bool counted = !exhausted && best > 1e-3 && r_lowlat < prob;
+        /* the whole-year path (pi_gen == NULL) only needs what the sequential loop would have looked at: the potential
+         * intensity of a COUNTED attempt (compute.py:162-169) and the initial state of a PASSED one (:172-175); the
+         * test hook (tcr_seed_attempts) evaluates everything for every attempt */
+        const bool full = A.pi_gen != nullptr;
+        TcrCell ce;
+        const float4* rec = nullptr;
+        if (full || counted) {
+            tcr_cell_at(cx.tab.lon, cx.tab.lat, gen_lon, gen_lat, ce);
+            rec = tcr_record(cx.tab, A.ym_base[yr] + mon - 1, ce);
+            pi = tcr_bilin(__ldg(rec + CH_VPOT), ce);
+        }
         if (exhausted) code = 3;
-        else if (best > 1e-3 && r_lowlat < prob) code = pi > p.pi_gen_min ? 2 : 1;
+        else if (counted) code = pi > p.pi_gen_min ? 2 : 1;
         else code = 0;
+        if (full || code == 2) {
+            tcr_draw2(A.run_seed, key, k, 2, 0, u);
+            double bs, bc;
+            tcr_sincos2pi(u[1], &bs, &bc);
+            const double randn = sqrt(-2.0 * tcr_log(1.0 - u[0])) * bc;
+            v0 = p.seed_v_init + randn;
+            const double rh = tcr_bilin(__ldg(rec + CH_RH), ce);
+            const double mi = p.minit_amp / (1.0 + tcr_exp(-(rh - p.minit_center) * p.minit_slope)) + p.minit_offset;
+            m0 = mi > 0.0 ? mi : 0.0;
+        }
         A.code[idx] = code; A.basin[idx] = bi; A.month[idx] = mon;
-        A.lon[idx] = gen_lon; A.lat[idx] = gen_lat; A.v0[idx] = v0; A.m0[idx] = m0;
+        if (full || code == 2) { A.lon[idx] = gen_lon; A.lat[idx] = gen_lat; A.v0[idx] = v0; A.m0[idx] = m0; }
         if (A.pi_gen) A.pi_gen[idx] = pi;
     }
     if (A.blk_count) {
         __shared__ unsigned int s_cnt;
         if (threadIdx.x == 0) s_cnt = 0u;
         __syncthreads();
-        const unsigned pass = __ballot_sync(TCR_FULL, code == 2);
+        const bool own = A.world <= 1 || (int)(k % A.world) == A.rank;
+        const unsigned pass = __ballot_sync(TCR_FULL, code == 2 && own);
         if ((threadIdx.x & 31) == 0 && pass) atomicAdd(&s_cnt, (unsigned int)__popc(pass));
         __syncthreads();
         if (threadIdx.x == 0) A.blk_count[blockIdx.x] = s_cnt;
@@ -1532,6 +1461,7 @@ struct AssignArgs {
     int32_t* att_slot; int64_t* consumed;
     int32_t* s_ym; double* s_lon; double* s_lat; double* s_v0; double* s_m0; double* s_hbl;
     int64_t* s_att; int32_t* s_key;
+    int rank, world;
 };
 
 __global__ void __launch_bounds__(256) k_assign_slots(const __grid_constant__ TcrCtx cx, const AssignArgs A)
@@ -1540,7 +1470,11 @@ __global__ void __launch_bounds__(256) k_assign_slots(const __grid_constant__ Tc
     const int64_t total = A.wave_off[A.n_years];
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int code = idx < total ? A.code[idx] : -1;
+    int code = idx < total ? A.code[idx] : -1;
+    int yr = 0;
+    if (idx < total) while (yr + 1 < A.n_years && idx >= A.wave_off[yr + 1]) ++yr;
+    /* within-year sharding: a passing attempt another rank owns is not integrated here */
+    if (code == 2 && A.world > 1 && (int)((A.k0[yr] + (idx - A.wave_off[yr])) % A.world) != A.rank) code = 0;
     const unsigned pass = __ballot_sync(TCR_FULL, code == 2);
     if (lane == 0) warp_cnt[wid] = (unsigned int)__popc(pass);
     __syncthreads();
@@ -1549,8 +1483,6 @@ __global__ void __launch_bounds__(256) k_assign_slots(const __grid_constant__ Tc
     unsigned int rank = __popc(pass & ((1u << lane) - 1u));
     for (int w = 0; w < wid; ++w) rank += warp_cnt[w];
     const unsigned int s = A.blk_off[blockIdx.x] + rank;
-    int yr = 0;
-    while (yr + 1 < A.n_years && idx >= A.wave_off[yr + 1]) ++yr;
     if (s >= A.slot_cap) {
         A.att_slot[idx] = -2;
         atomicMin(reinterpret_cast<unsigned long long*>(A.consumed + yr), (unsigned long long)(idx - A.wave_off[yr]));
@@ -1578,23 +1510,27 @@ struct WaveStatsArgs {
     const int32_t* code; const int32_t* basin; const int32_t* month; const int32_t* att_slot;
     const int32_t* n_time; const int32_t* nfev; const uint32_t* flags;
     uint8_t* att_kept;                   /* [total attempts]                                     */
-    unsigned long long* wave_tot;        /* [n_years][4] counted, integrated, storm-steps, RHS    */
-    unsigned int* wave_hist;             /* [n_years][7*12] counted attempts per (basin, month)   */
+    /* wave_glob [n_years][86] u32: counted attempts per (basin, month), their sum, exhausted redraw chains -- what within-year sharding
+     * all-reduces (each rank counts the attempts it owns); wave_loc [n_years][3] u64: integrated storms, their
+     * samples and RHS evaluations -- this rank's share, never reduced                                       */
+    unsigned int* wave_glob; unsigned long long* wave_loc;
+    const int64_t* k0; int rank, world;
 };
 
 __global__ void __launch_bounds__(256) k_wave_stats(const WaveStatsArgs A)
 {
-    __shared__ unsigned int s_hist[TCR_N_BASINS * 12];
-    __shared__ unsigned long long s_tot[4];
+    __shared__ unsigned int s_hist[TCR_N_BASINS * 12 + 2];
+    __shared__ unsigned long long s_tot[3];
     const int64_t total = A.wave_off[A.n_years];
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int tid = threadIdx.x;
+    const int NG = TCR_N_BASINS * 12 + 2;                   /* 84 (basin, month) bins, counted attempts, exhausted redraw chains */
     /* year of the block's first attempt: the shared accumulators belong to it */
     const int64_t first = (int64_t)blockIdx.x * blockDim.x;
     int yr0 = 0;
     while (yr0 + 1 < A.n_years && first >= A.wave_off[yr0 + 1]) ++yr0;
-    for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) s_hist[i] = 0u;
-    if (tid < 4) s_tot[tid] = 0ull;
+    for (int i = tid; i < NG; i += blockDim.x) s_hist[i] = 0u;
+    if (tid < 3) s_tot[tid] = 0ull;
     __syncthreads();
     if (idx < total) {
         int yr = yr0;
@@ -1603,7 +1539,9 @@ __global__ void __launch_bounds__(256) k_wave_stats(const WaveStatsArgs A)
         uint8_t kept = 0;
         if (li < A.consumed[yr]) {
             const int code = A.code[idx], slot = A.att_slot[idx];
-            const bool counted = (code == 1 || code == 2);
+            const bool own = A.world <= 1 || (int)((A.k0[yr] + li) % A.world) == A.rank;
+            const bool counted = (code == 1 || code == 2) && own;
+            if (code == 3 && own) atomicAdd(yr == yr0 ? &s_hist[NG - 1] : &A.wave_glob[yr * NG + NG - 1], 1u);
             unsigned long long steps = 0, rhs = 0;
             if (slot >= 0) {
                 steps = (unsigned long long)A.n_time[slot]; rhs = (unsigned long long)A.nfev[slot];
@@ -1611,22 +1549,22 @@ __global__ void __launch_bounds__(256) k_wave_stats(const WaveStatsArgs A)
             }
             const int bin = counted ? A.basin[idx] * 12 + A.month[idx] - 1 : 0;
             if (yr == yr0) {
-                if (counted) { atomicAdd(&s_hist[bin], 1u); atomicAdd(&s_tot[0], 1ull); }
-                if (slot >= 0) { atomicAdd(&s_tot[1], 1ull); atomicAdd(&s_tot[2], steps); atomicAdd(&s_tot[3], rhs); }
+                if (counted) { atomicAdd(&s_hist[bin], 1u); atomicAdd(&s_hist[NG - 2], 1u); }
+                if (slot >= 0) { atomicAdd(&s_tot[0], 1ull); atomicAdd(&s_tot[1], steps); atomicAdd(&s_tot[2], rhs); }
             } else {                                        /* block straddles a year boundary: rare */
-                if (counted) { atomicAdd(&A.wave_hist[yr * TCR_N_BASINS * 12 + bin], 1u); atomicAdd(&A.wave_tot[yr * 4 + 0], 1ull); }
+                if (counted) { atomicAdd(&A.wave_glob[yr * NG + bin], 1u); atomicAdd(&A.wave_glob[yr * NG + NG - 2], 1u); }
                 if (slot >= 0) {
-                    atomicAdd(&A.wave_tot[yr * 4 + 1], 1ull); atomicAdd(&A.wave_tot[yr * 4 + 2], steps);
-                    atomicAdd(&A.wave_tot[yr * 4 + 3], rhs);
+                    atomicAdd(&A.wave_loc[yr * 3 + 0], 1ull); atomicAdd(&A.wave_loc[yr * 3 + 1], steps);
+                    atomicAdd(&A.wave_loc[yr * 3 + 2], rhs);
                 }
             }
         }
         A.att_kept[idx] = kept;
     }
     __syncthreads();
-    for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x)
-        if (s_hist[i]) atomicAdd(&A.wave_hist[yr0 * TCR_N_BASINS * 12 + i], s_hist[i]);
-    if (tid < 4 && s_tot[tid]) atomicAdd(&A.wave_tot[yr0 * 4 + tid], s_tot[tid]);
+    for (int i = tid; i < NG; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(&A.wave_glob[yr0 * NG + i], s_hist[i]);
+    if (tid < 3 && s_tot[tid]) atomicAdd(&A.wave_loc[yr0 * 3 + tid], s_tot[tid]);
 }
 
 struct SelectArgs {
@@ -1635,7 +1573,7 @@ struct SelectArgs {
     const int64_t* consumed;    /* [n_years] attempts of the year's range that were fully processed   */
     const int32_t* code; const int32_t* basin; const int32_t* month; const int32_t* att_slot;
     const int32_t* n_time; const int32_t* nfev;
-    const uint8_t* att_kept; const unsigned long long* wave_tot; const unsigned int* wave_hist;   /* k_wave_stats */
+    const uint8_t* att_kept; const unsigned int* wave_glob; const unsigned long long* wave_loc;   /* k_wave_stats */
     int32_t* nt;                /* [n_years] kept so far (in/out)                              */
     int64_t* used;              /* [n_years] attempts consumed by this wave: i*+1, or consumed[y] */
     int32_t* row_slot;          /* [n_years][n_tracks] slot of a row assigned in THIS wave, else -1 */
@@ -1650,7 +1588,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
 {
     __shared__ int warp_tot[32];
     __shared__ int s_running, s_istar;
-    __shared__ unsigned long long s_acc[5];
+    __shared__ unsigned long long s_acc[6];
     __shared__ unsigned int s_hist[TCR_N_BASINS * 12];
     const int yr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (A.pool_ctl[1]) return;
@@ -1661,7 +1599,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
     const int nt0 = A.nt[yr];
     const int want = A.n_tracks - nt0;
     if (tid == 0) { s_running = 0; s_istar = -1; }
-    if (tid < 5) s_acc[tid] = 0ull;
+    if (tid < 6) s_acc[tid] = 0ull;
     for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) s_hist[i] = 0u;
     __syncthreads();
     /* pass 1: rank the kept storms in attempt order, find i* = attempt of the want-th kept.
@@ -1708,7 +1646,7 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
                         A.row_slot[(size_t)yr * A.n_tracks + row] = slot;
                         A.tc_month[(size_t)yr * A.n_tracks + row] = (double)A.month[off + i];
                         A.tc_basin[(size_t)yr * A.n_tracks + row] = A.basin[off + i];
-                        atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot]);
+                        if (slot >= 0) atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot]);   /* < 0: another rank's storm */
                         if (rank == want) s_istar = (int)i;
                     }
                 }
@@ -1722,27 +1660,31 @@ __global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
     const int64_t i_star = s_istar;
     const int64_t last = i_star >= 0 ? i_star : W - 1;      /* attempts consumed: 0..last */
     /* pass 2: the over-shoot (last, W) only; the totals over [0, W) come from k_wave_stats */
-    unsigned long long w_counted = 0, w_integ = 0, w_steps = 0, w_rhs = 0;
+    unsigned long long w_counted = 0, w_integ = 0, w_steps = 0, w_rhs = 0, w_exh = 0;
     for (int64_t i = last + 1 + tid; i < W; i += blockDim.x) {
         const int code = A.code[off + i];
         const int slot = A.att_slot[off + i];
         if (code == 1 || code == 2) { ++w_counted; atomicAdd(&s_hist[A.basin[off + i] * 12 + A.month[off + i] - 1], 1u); }
+        if (code == 3) ++w_exh;
         if (slot >= 0) { ++w_integ; w_steps += (unsigned long long)A.n_time[slot]; w_rhs += (unsigned long long)A.nfev[slot]; }
     }
     if (w_counted) atomicAdd(&s_acc[0], w_counted);
+    if (w_exh) atomicAdd(&s_acc[5], w_exh);
     if (w_integ) { atomicAdd(&s_acc[1], w_integ); atomicAdd(&s_acc[2], w_steps); atomicAdd(&s_acc[3], w_rhs); }
     __syncthreads();
+    const int NG = TCR_N_BASINS * 12 + 2;
     for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x)
-        A.n_seeds[(size_t)yr * TCR_N_BASINS * 12 + i] += (double)(A.wave_hist[yr * TCR_N_BASINS * 12 + i] - s_hist[i]);
+        A.n_seeds[(size_t)yr * TCR_N_BASINS * 12 + i] += (double)(A.wave_glob[yr * NG + i] - s_hist[i]);
     if (tid == 0) {
         tcr_year_stats& s = A.stats[yr];
-        const unsigned long long* tot = A.wave_tot + yr * 4;
+        const unsigned long long* tot = A.wave_loc + yr * 3;
         const int got = min(want, s_running);
         s.attempts = A.k0[yr] + last + 1;
-        s.counted_seeds += (int64_t)(tot[0] - s_acc[0]);
-        s.integrated += (int64_t)(tot[1] - s_acc[1]);
-        s.storm_steps += (int64_t)(tot[2] - s_acc[2]);
-        s.rhs_evals += (int64_t)(tot[3] - s_acc[3]);
+        s.counted_seeds += (int64_t)((unsigned long long)A.wave_glob[yr * NG + NG - 2] - s_acc[0]);
+        s.redraw_exhausted += (int64_t)((unsigned long long)A.wave_glob[yr * NG + NG - 1] - s_acc[5]);
+        s.integrated += (int64_t)(tot[0] - s_acc[1]);
+        s.storm_steps += (int64_t)(tot[1] - s_acc[2]);
+        s.rhs_evals += (int64_t)(tot[2] - s_acc[3]);
         s.kept_steps += (int64_t)s_acc[4];
         s.wasted_integrated += (int64_t)s_acc[1];
         s.wasted_steps += (int64_t)s_acc[2];

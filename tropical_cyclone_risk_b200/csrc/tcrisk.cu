@@ -117,7 +117,7 @@ struct tcr_handle {
     size_t smem_optin = 0;
     int64_t launches = 0;
     /* tables */
-    DevBuf rec, recb, stage, prep;     /* rec: float32 cell records; recb: the integrator's widened twin */
+    DevBuf rec, stage, prep;
     AxisBuf ax_lon, ax_lat;
     int nlat = 0, nlon = 0, n_ym = 0;
     size_t month_f4 = 0;
@@ -130,7 +130,12 @@ struct tcr_handle {
     bool have_static = false, have_masks = false;
     /* tuning */
     int integ_variant = 17, oversub_permille = 1020, interp_variant = 0;
-    bool use_recb = false;       /* a REC = 1 variant is selected: tables also exist as integrator records */
+    /* within-year sharding (tcr_set_shard): rank r of `world` integrates the attempts k with k % world == r */
+    int shard_rank = 0, shard_world = 1;
+    tcr_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    bool use_recp = false;       /* a REC = 2 variant is selected: point records are derived from the cell records before each run */
+    bool recp_stale = true;       /* a REC = 1 variant is selected: tables also exist as integrator records */
     /* survival statistics of earlier tcr_run_years calls on this handle: size the first wave */
     double hint_kept_rate = 0.0, hint_pass_rate = 0.0;
     std::vector<double> hint_year_rate;     /* per year slot of the previous call (same n_years): survival differs by year */
@@ -283,7 +288,7 @@ int tcr_destroy(tcr_handle* h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     h->ws.release_all();
-    DevBuf* bufs[] = {&h->rec, &h->recb, &h->stage, &h->prep, &h->bathy, &h->land, &h->masks, &h->sincos};
+    DevBuf* bufs[] = {&h->rec, &h->stage, &h->prep, &h->bathy, &h->land, &h->masks, &h->sincos};
     for (DevBuf* b : bufs) b->release();
     AxisBuf* axs[] = {&h->ax_lon, &h->ax_lat, &h->ax_lon_b, &h->ax_lat_b, &h->ax_lon_l, &h->ax_lat_l, &h->ax_lon_m, &h->ax_lat_m};
     for (AxisBuf* a : axs) a->buf.release();
@@ -313,21 +318,8 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 {
     if (!h) return set_err("null handle");
     if (integ_variant > 0) {
-        if (integ_variant > 25) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
+        if (integ_variant > 21) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
         h->integ_variant = integ_variant - 1;
-        const int v = h->integ_variant;
-        const bool need_recb = v == 21;                                   /* the REC = 1 variant */
-        if (need_recb && !h->use_recb) {
-            h->use_recb = true;
-            if (h->rec.p) {                                              /* tables already built: derive their twins */
-                CK(cudaSetDevice(h->device));
-                const size_t total = h->month_f4 * (size_t)h->n_ym;
-                if (h->recb.ensure(total * sizeof(uint4))) return -1;
-                k_recb_from_rec<<<grid_for(total, 256, h->num_sms), 256, 0, h->stream>>>(h->rec.as<float4>(), h->recb.as<uint4>(), total);
-                CKK(h);
-                h->ctx.tab.recb = h->recb.as<uint4>();
-            }
-        }
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
     if (max_wave_slots > 0) h->max_slots = max_wave_slots;
@@ -341,6 +333,15 @@ int tcr_set_interp_variant(tcr_handle* h, int variant)
     if (variant < 0 || variant > 6)
         return set_err("interp variant must be 0 (LDG), 1 (TMA bulk), 2 / 3 (LDG, 4 / 5 CTAs per SM) or 4 (cp.async pipeline)");
     h->interp_variant = variant;
+    return 0;
+}
+
+int tcr_set_shard(tcr_handle* h, int rank, int world, tcr_allreduce_fn fn, void* user)
+{
+    if (!h) return set_err("null handle");
+    if (world < 1 || rank < 0 || rank >= world) return set_err("tcr_set_shard: rank %d of %d", rank, world);
+    if (world > 1 && !fn) return set_err("tcr_set_shard: world > 1 needs an all-reduce callback");
+    h->shard_rank = rank; h->shard_world = world; h->allreduce = fn; h->allreduce_user = user;
     return 0;
 }
 
@@ -446,12 +447,9 @@ int tcr_alloc_tables(tcr_handle* h, int n_ym, int nlat, int nlon, const double* 
     if (make_axis(h, lon, nlon, h->ax_lon, tb.lon) || make_axis(h, lat, nlat, h->ax_lat, tb.lat)) return -1;
     h->month_f4 = (size_t)(nlat - 1) * (nlon - 1) * TCR_REC_F4;
     if (h->rec.ensure(h->month_f4 * sizeof(float4) * (size_t)n_ym)) return -1;
-    if (h->use_recb) { if (h->recb.ensure(h->month_f4 * sizeof(uint4) * (size_t)n_ym)) return -1; }
-    else h->recb.release();
     if (h->stage.ensure((size_t)TCR_N_FIELDS * nlat * nlon * sizeof(float))) return -1;
     h->nlat = nlat; h->nlon = nlon; h->n_ym = n_ym;
     tb.rec = h->rec.as<float4>();
-    tb.recb = h->use_recb ? h->recb.as<uint4>() : nullptr;
     tb.ncx = nlon - 1; tb.ncy = nlat - 1; tb.n_ym = n_ym;
     return 0;
 }
@@ -465,8 +463,7 @@ int tcr_upload_month_dev(tcr_handle* h, int ym, const float* d_planes)
     {
         LaunchTimer lt_(h, TCR_K_BUILD);
         k_build_month<<<grid_for(h->month_f4, 256, h->num_sms), 256, 0, h->stream>>>(
-            d_planes, h->rec.as<float4>() + h->month_f4 * (size_t)ym,
-            h->use_recb ? h->recb.as<uint4>() + h->month_f4 * (size_t)ym : nullptr, h->nlat, h->nlon);
+            d_planes, h->rec.as<float4>() + h->month_f4 * (size_t)ym, h->nlat, h->nlon);
     }
     CKK(h);
     return 0;
@@ -485,8 +482,7 @@ int tcr_upload_months(tcr_handle* h, int ym0, int n_months, const float* planes)
     {
         LaunchTimer lt_(h, TCR_K_BUILD);
         dim3 grid((unsigned)grid_for(h->month_f4, 256, h->num_sms), (unsigned)n_months);
-        k_build_month<<<grid, 256, 0, h->stream>>>(h->stage.as<float>(), h->rec.as<float4>() + h->month_f4 * (size_t)ym0,
-                                               h->use_recb ? h->recb.as<uint4>() + h->month_f4 * (size_t)ym0 : nullptr, h->nlat, h->nlon);
+        k_build_month<<<grid, 256, 0, h->stream>>>(h->stage.as<float>(), h->rec.as<float4>() + h->month_f4 * (size_t)ym0, h->nlat, h->nlon);
     }
     CKK(h);
     return 0;
@@ -632,7 +628,7 @@ static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_yea
     }
     if (w.counters.ensure(64)) return -1;
     const size_t ny = (size_t)std::max(n_years, 1);
-    if (w.wave_tot.ensure(ny * (4 * 8 + TCR_N_BASINS * 12 * 4))) return -1;
+    if (w.wave_tot.ensure(ny * (3 * 8 + (TCR_N_BASINS * 12 + 2) * 4) + 16)) return -1;
     if (w.year_i64.ensure((4 * ny + 1) * 8) || w.year_i32.ensure(3 * ny * 4) || w.stats.ensure(ny * sizeof(tcr_year_stats))) return -1;
     return 0;
 }
@@ -662,7 +658,7 @@ static int launch_fourier_table(tcr_handle* h, int64_t n_upper, const unsigned i
 
 }  // extern "C"
 
-template <int THREADS, int MINB, int KSMEM, int LOCKSTEP = 0, int REC = 0, int PARK = 0>
+template <int THREADS, int MINB, int KSMEM, int LOCKSTEP = 0>
 static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_upper)
 {
     const int warps_per_cta = THREADS / 32;
@@ -676,8 +672,8 @@ static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_uppe
     /* KSMEM 2: eight stage vectors + the 18-word staging area of the drain-phase packing */
     const size_t smem = KSMEM == 2 ? (size_t)(32 + 18) * THREADS * sizeof(double) : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
     LaunchTimer lt_(h, TCR_K_INTEGRATE);
-    cudaFuncSetAttribute(k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC, PARK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_integrate<THREADS, MINB, KSMEM, LOCKSTEP, REC, PARK><<<grid, THREADS, smem, h->stream>>>(h->ctx, a);
+    cudaFuncSetAttribute(k_integrate<THREADS, MINB, KSMEM, LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_integrate<THREADS, MINB, KSMEM, LOCKSTEP><<<grid, THREADS, smem, h->stream>>>(h->ctx, a);
 }
 
 static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
@@ -704,10 +700,6 @@ static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
     case 18: launch_integrate_variant<192, 3, 2, 63>(h, a, n_upper); break;      /* 96 registers, 18 warps/SM */
     case 19: launch_integrate_variant<224, 2, 2, 63>(h, a, n_upper); break;      /* 144 registers, 14 warps/SM */
     case 20: launch_integrate_variant<384, 1, 2, 63>(h, a, n_upper); break;      /* one 12-warp CTA per SM */
-    case 21: launch_integrate_variant<192, 2, 2, 63, 1>(h, a, n_upper); break;   /* integrator records: widened corners, ten 256-bit loads, no F2F */
-    case 22: launch_integrate_variant<192, 2, 2, 63, 0, 1>(h, a, n_upper); break;   /* PARK: storm state parked in smem during the RHS */
-    case 23: launch_integrate_variant<224, 2, 2, 63, 0, 1>(h, a, n_upper); break;   /* 128 registers, 14 warps/SM */
-    case 24: launch_integrate_variant<256, 2, 2, 63, 0, 1>(h, a, n_upper); break;   /* 128 registers, 16 warps/SM */
     default: return set_err("unknown integrate variant %d", h->integ_variant);
     }
     CKK(h);
@@ -938,6 +930,24 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
     int64_t slot_cap = w.slot_cap;
     if (h->max_slots > 0) slot_cap = std::min(slot_cap, h->max_slots);
     if (w.row_slot.ensure(rows * 4)) return -1;
+    const int world = h->shard_world, srank = h->shard_rank;
+    /* collective on the handle's stream through the caller's callback (NCCL in production); dtype 0 u8, 1 i32, 2 i64; op 0 sum, 1 min */
+    auto allreduce = [&](void* d_buf, int64_t count, int dtype, int op) -> int {
+        if (h->allreduce(h->allreduce_user, d_buf, count, dtype, op, (void*)s) != 0) return set_err("tcr_run_years: all-reduce callback failed");
+        return 0;
+    };
+    if (world > 1) {
+        /* every rank must cut the attempt stream into the same waves: agree on the smaller capacities, and on the
+         * survival hints that size the waves (rank 0's) */
+        int64_t* pin = reinterpret_cast<int64_t*>(h->pinned) + 4096;
+        int64_t* d_tmp = w.year_i64.as<int64_t>();
+        pin[0] = cap; pin[1] = slot_cap;
+        CK(cudaMemcpyAsync(d_tmp, pin, 16, cudaMemcpyHostToDevice, s));
+        if (allreduce(d_tmp, 2, 2, 1)) return -1;
+        CK(cudaMemcpyAsync(pin, d_tmp, 16, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        cap = pin[0]; slot_cap = pin[1];
+    }
 
     /* result block on the device */
     double *d_lon, *d_lat, *d_v, *d_m, *d_vmax, *d_env, *d_month, *d_seeds;
@@ -950,6 +960,13 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         d_lon = base; d_lat = d_lon + rows * ns; d_v = d_lat + rows * ns; d_m = d_v + rows * ns; d_vmax = d_m + rows * ns;
         d_env = d_vmax + rows * ns; d_month = d_env + rows * ns * 4; d_seeds = d_month + rows;
         d_basin = reinterpret_cast<int32_t*>(d_seeds + (size_t)n_years * 84);
+    }
+    if (world > 1) {
+        /* a row is written by the rank that integrated its storm and stays all-zero bits elsewhere: the ranks' blocks
+         * then merge by an integer sum (exact for every bit pattern, NaN padding and signed zeros included) */
+        CK(cudaMemsetAsync(d_lon, 0, rows * ns * 8, s)); CK(cudaMemsetAsync(d_lat, 0, rows * ns * 8, s));
+        CK(cudaMemsetAsync(d_v, 0, rows * ns * 8, s)); CK(cudaMemsetAsync(d_m, 0, rows * ns * 8, s));
+        CK(cudaMemsetAsync(d_vmax, 0, rows * ns * 8, s)); CK(cudaMemsetAsync(d_env, 0, rows * ns * 32, s));
     }
     CK(cudaMemsetAsync(d_month, 0xff, rows * 8, s));
     CK(cudaMemsetAsync(d_basin, 0xff, rows * 4, s));
@@ -1025,13 +1042,22 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
             want_total += wy;
         }
         const double scale = want_total > (double)cap ? (double)cap / want_total : 1.0;
+        for (int y = 0; y < n_years; ++y) W[y] = want[y] > 0.0 ? std::max<int64_t>(64, (int64_t)(want[y] * scale)) : 0;
+        if (world > 1) {
+            /* the ranks must issue identical attempt ranges: take the smallest proposal of each year (the proposals only
+             * differ when the handles were tuned differently or remember different survival rates) */
+            int64_t* pin = reinterpret_cast<int64_t*>(h->pinned) + 4096;
+            memcpy(pin, W.data(), (size_t)n_years * 8);
+            CK(cudaMemcpyAsync(d_used, pin, (size_t)n_years * 8, cudaMemcpyHostToDevice, s));
+            if (allreduce(d_used, n_years, 2, 1)) return -1;
+            CK(cudaMemcpyAsync(pin, d_used, (size_t)n_years * 8, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            memcpy(W.data(), pin, (size_t)n_years * 8);
+        }
         int64_t total = 0;
         for (int y = 0; y < n_years; ++y) {
-            int64_t wy = 0;
-            if (want[y] > 0.0) wy = std::max<int64_t>(64, (int64_t)(want[y] * scale));
-            W[y] = wy;
             hoff[y] = total;
-            total += wy;
+            total += W[y];
             hoff[n_years + 1 + y] = k0[y];
         }
         hoff[n_years] = total;
@@ -1048,6 +1074,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         sa.lon = w.a_lon.as<double>(); sa.lat = w.a_lat.as<double>(); sa.v0 = w.a_v0.as<double>(); sa.m0 = w.a_m0.as<double>();
         sa.pi_gen = nullptr;
         sa.blk_count = w.blk_count.as<unsigned int>();
+        sa.rank = srank; sa.world = world;
         AssignArgs as;
         memset(&as, 0, sizeof as);
         as.n_years = n_years; as.wave_off = d_wave_off; as.k0 = d_k0; as.ym_base = d_ym_base; as.year_key = d_key;
@@ -1058,6 +1085,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         as.s_ym = w.s_ym.as<int32_t>(); as.s_lon = w.s_lon.as<double>(); as.s_lat = w.s_lat.as<double>();
         as.s_v0 = w.s_v0.as<double>(); as.s_m0 = w.s_m0.as<double>(); as.s_hbl = w.s_hbl.as<double>();
         as.s_att = w.s_att.as<int64_t>(); as.s_key = w.s_key.as<int32_t>();
+        as.rank = srank; as.world = world;
         {
             LaunchTimer lt_(h, TCR_K_SEED);
             k_seed<<<seed_blocks, 256, 0, s>>>(h->ctx, sa);
@@ -1104,16 +1132,22 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         wa.code = sa.code; wa.basin = sa.basin; wa.month = sa.month; wa.att_slot = as.att_slot;
         wa.n_time = a.n_time; wa.nfev = a.nfev; wa.flags = a.flags;
         wa.att_kept = w.att_kept.as<uint8_t>();
-        wa.wave_tot = w.wave_tot.as<unsigned long long>();
-        wa.wave_hist = reinterpret_cast<unsigned int*>(wa.wave_tot + 4 * (size_t)n_years);
-        CK(cudaMemsetAsync(w.wave_tot.p, 0, (size_t)n_years * (4 * 8 + TCR_N_BASINS * 12 * 4), s));
+        const int NG = TCR_N_BASINS * 12 + 2;
+        wa.wave_loc = w.wave_tot.as<unsigned long long>();
+        wa.wave_glob = reinterpret_cast<unsigned int*>(wa.wave_loc + 3 * (size_t)n_years);       /* [n_years][86] + overflow word */
+        wa.k0 = d_k0; wa.rank = srank; wa.world = world;
+        CK(cudaMemsetAsync(w.wave_tot.p, 0, (size_t)n_years * (3 * 8 + NG * 4) + 16, s));
+        if (world > 1) {
+            /* a year whose range one rank had to cut (slot capacity) is cut for everybody */
+            if (allreduce(d_consumed, n_years, 2, 1)) return -1;
+        }
 
         SelectArgs se;
         memset(&se, 0, sizeof se);
         se.n_tracks = n_tracks; se.wave_off = d_wave_off; se.k0 = d_k0; se.consumed = d_consumed;
         se.code = sa.code; se.basin = sa.basin; se.month = sa.month; se.att_slot = as.att_slot;
         se.n_time = a.n_time; se.nfev = a.nfev;
-        se.att_kept = wa.att_kept; se.wave_tot = wa.wave_tot; se.wave_hist = wa.wave_hist;
+        se.att_kept = wa.att_kept; se.wave_glob = wa.wave_glob; se.wave_loc = wa.wave_loc;
         se.nt = d_nt; se.used = d_used; se.row_slot = w.row_slot.as<int32_t>();
         se.tc_month = d_month; se.tc_basin = d_basin; se.n_seeds = d_seeds;
         se.stats = w.stats.as<tcr_year_stats>();
@@ -1121,6 +1155,14 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         {
             LaunchTimer lt_(h, TCR_K_SELECT);
             k_wave_stats<<<seed_blocks, 256, 0, s>>>(wa);
+            if (world > 1) {
+                /* the ranks' kept flags, counted-seed histograms and pool-overflow flags become global: after this every
+                 * rank selects the same rows (the one survivor-count exchange per wave of SURVEY 8e) */
+                unsigned int* d_ovf = wa.wave_glob + (size_t)n_years * NG;
+                CK(cudaMemcpyAsync(d_ovf, d_pool + 1, 4, cudaMemcpyDeviceToDevice, s));
+                if (allreduce(wa.att_kept, (total + 3) / 4 * 4, 0, 0) || allreduce(wa.wave_glob, (int64_t)n_years * NG + 1, 1, 0)) return -1;
+                CK(cudaMemcpyAsync(d_pool + 1, d_ovf, 4, cudaMemcpyDeviceToDevice, s));
+            }
             k_select<<<n_years, 1024, 0, s>>>(se);
         }
         CKK(h);

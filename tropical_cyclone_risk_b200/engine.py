@@ -80,6 +80,25 @@ class Engine:
         (x1000).  Results never depend on these."""
         _lib.check(self.lib.tcr_set_tuning(self._h, integ_variant, max_wave, max_slots, oversub_permille))
 
+    def set_shard(self, rank, world, allreduce=None):
+        """Within-year sharding (tcr_set_shard): run_years becomes collective over `world` engines; this one integrates
+        the attempts k with k % world == rank.  allreduce(ptr, count, dtype, op, stream) -> None performs the in-place
+        all-reduce of a device buffer (dtype 0 u8 / 1 i32 / 2 i64, op 0 sum / 1 min); see gather.dist_allreduce."""
+        if allreduce is None:
+            cb = _lib.ALLREDUCE_FN()
+        else:
+            def tramp(user, ptr, count, dtype, op, stream):
+                try:
+                    allreduce(int(ptr), int(count), int(dtype), int(op), int(stream or 0))
+                    return 0
+                except Exception:                                  # never let an exception cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return -1
+            cb = _lib.ALLREDUCE_FN(tramp)
+        self._allreduce_cb = cb                                    # keep the trampoline alive as long as the handle uses it
+        _lib.check(self.lib.tcr_set_shard(self._h, int(rank), int(world), cb, None))
+
     def set_interp_variant(self, variant):
         _lib.check(self.lib.tcr_set_interp_variant(self._h, int(variant)))
 

@@ -44,6 +44,43 @@ def bind_to_gpu_numa(local_rank):
         return "unbound (%s)" % type(e).__name__
 
 
+_TORCH_DTYPES = {0: ("|u1", "uint8"), 1: ("<i4", "int32"), 2: ("<i8", "int64")}
+
+
+class _DevView:
+    """A device buffer owned by libtcrisk.so, exposed to torch without a copy (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = dict(shape=(int(count),), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+def device_tensor(ptr, count, dtype_code, device):
+    import torch
+    typestr, name = _TORCH_DTYPES[dtype_code]
+    return torch.as_tensor(_DevView(ptr, count, typestr), device=device)
+
+
+def dist_allreduce(device, group=None):
+    """The all-reduce callback of Engine.set_shard over torch.distributed (NCCL on GPUs): in place, stream-ordered on
+    torch's current stream -- which must be the stream the engine runs on (Engine.set_stream)."""
+    import torch
+    import torch.distributed as dist
+
+    def fn(ptr, count, dtype_code, op, stream):
+        t = device_tensor(ptr, count, dtype_code, device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN if op == 1 else dist.ReduceOp.SUM, group=group)
+    return fn
+
+
+def merge_sharded_block(block, group=None):
+    """Blocks of within-year-sharded ranks -> the complete block on every rank: rows a rank did not integrate are
+    all-zero bits, so the merge is an INTEGER sum of the float64 bit patterns (exact for NaN padding and signed zeros)."""
+    import torch
+    import torch.distributed as dist
+    dist.all_reduce(block.view(torch.int64), op=dist.ReduceOp.SUM, group=group)
+    return block
+
+
 def nccl_gather(block, out=None):
     """all_gather_into_tensor of equal-sized 1-D device blocks -> [world][n] on every rank."""
     import torch

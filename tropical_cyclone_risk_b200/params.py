@@ -46,7 +46,7 @@ class TcrYearStats(C.Structure):
         ("attempts", C.c_int64), ("counted_seeds", C.c_int64), ("integrated", C.c_int64),
         ("storm_steps", C.c_int64), ("kept_steps", C.c_int64), ("rhs_evals", C.c_int64),
         ("wasted_integrated", C.c_int64), ("wasted_steps", C.c_int64), ("wasted_rhs_evals", C.c_int64),
-        ("n_kept", C.c_int32), ("n_waves", C.c_int32),
+        ("n_kept", C.c_int32), ("n_waves", C.c_int32), ("redraw_exhausted", C.c_int64),
     ]
 
 
