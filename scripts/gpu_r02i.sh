@@ -1,0 +1,24 @@
+#!/bin/bash
+# round 2, visit I: straight-line RHS (integrate variant 22) -- parity under the whole GPU suite, A/B against variant 18
+TAG=${1:-r02i}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+TCR_INTEG_VARIANT=22 timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_v22.log 2>&1; echo "pytest(v22) exit $?"; tail -5 $OUT/pytest_gpu_v22.log | cut -c1-400
+run() {  # name, env, args
+  env $2 timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu --no-interp $3 > $OUT/bench_$1.json 2> $OUT/bench_$1.err
+  python - <<PY
+import json
+try:
+    d=json.load(open("$OUT/bench_$1.json"))
+    print("$1: value %.3e e2e %.3e ms/step %.2f integrate avg %.3f ms share %.2f waves %s"%(d["value"],d["e2e"]["value"],d["ms_per_step"],d["roofline"]["avg_launch_ms"],d["roofline"]["share_of_step"],d["details"]["waves_per_step"]), {k:round(v,3) for k,v in d["details"]["kernel_share_of_step"].items()})
+except Exception as e:
+    print("$1 failed", e); print(open("$OUT/bench_$1.err").read()[-2000:])
+PY
+}
+run cfg1_v18 "A=1" "--basin NA --years 10 --tracks 1000"
+run cfg1_v22 "A=1" "--basin NA --years 10 --tracks 1000 --integ-variant 22"
+run cfg2_v18 "A=1" ""
+run cfg2_v22 "A=1" "--integ-variant 22"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_integrate -s 4 -c 1 -f -o $OUT/prof_integrate \
+    python bench.py --basin NA --years 10 --tracks 1000 --steps 2 --warmup 3 --no-cpu --no-interp --integ-variant 22 > $OUT/ncu_integrate.log 2>&1
+python scripts/ncu_summary.py $OUT/prof_integrate.ncu-rep 50 > $OUT/prof_integrate_summary.txt 2>&1

@@ -6,7 +6,8 @@ import os
 from .params import TcrParams, TcrYearStats
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtcrisk.so")
+# TCR_LIB_PATH: an instrumented build of the same sources (scripts/probes), never a different implementation
+LIB_PATH = os.environ.get("TCR_LIB_PATH") or os.path.join(_HERE, "libtcrisk.so")
 
 SYMBOLS = (
     "tcr_create", "tcr_destroy", "tcr_last_error", "tcr_set_stream", "tcr_synchronize", "tcr_version",

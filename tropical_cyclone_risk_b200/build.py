@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libtcrisk.so")
 
 SOURCES = ["tcrisk.cu"]
-DEPS = ["tcrisk.cu", "tcr_kernels.cuh", "tcr_device.cuh", "tcr_preproc.cuh",
+DEPS = ["tcrisk.cu", "tcr_kernels.cuh", "tcr_device.cuh", "tcr_rhs_fast.cuh", "tcr_preproc.cuh",
         os.path.join(ROOT, "include", "tcrisk.h"), os.path.join(ROOT, "include", "tcr_libm.h")]
 
 NVCC_FLAGS = [

@@ -4,6 +4,7 @@
  */
 #pragma once
 #include "tcr_device.cuh"
+#include "tcr_rhs_fast.cuh"
 
 #define TCR_FULL 0xffffffffu
 
@@ -722,6 +723,28 @@ __global__ void __launch_bounds__(FTM_THREADS, 1) k_fourier_table_mma(const __gr
 /* the integrator: Coupled_FAST.gen_track (coupled_fast.py:229-267) incl. scipy's RK45        */
 /* driver loop, t_eval dense output and the terminal event                                    */
 /* ======================================================================================== */
+/* The storm's Fourier table was written by the previous kernel and is long gone from L2 when the integrator reads it:
+ * every evaluation of every lane would start with an HBM round trip for its node pair (an RK attempt spans about six
+ * one-hour nodes, so nearly every stage brackets a new pair) and the warp waits for the slowest of its 32 lanes.  The
+ * access is sequential in time, so the lane asks L2 for the 128-byte lines of the nodes in [t0, t1] ahead of use.   */
+template <int LINES>
+__device__ __forceinline__ void tcr_ftab_prefetch(const TcrCtx& cx, const double* __restrict__ ftab, double t0, double t1)
+{
+    const int n = cx.p.n_steps;
+    int i0 = tcr_floor_guess(t0 * cx.inv_t_step), i1 = tcr_floor_guess(t1 * cx.inv_t_step) + 1;
+    if (i0 < 0) i0 = 0;
+    if (i0 > n - 1) i0 = n - 1;
+    if (i1 < i0) i1 = i0;
+    if (i1 > n - 1) i1 = n - 1;
+    const unsigned long long a0 = (unsigned long long)(ftab + (size_t)i0 * 4) & ~127ull;
+    const unsigned long long a1 = (unsigned long long)(ftab + (size_t)i1 * 4 + 3);
+#pragma unroll
+    for (int k = 0; k < LINES; ++k) {
+        const unsigned long long a = a0 + 128ull * k;
+        if (a <= a1) asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+    }
+}
+
 struct IntegArgs {
     int64_t n;                         /* number of storms (slots) if n_dev == NULL           */
     const unsigned int* n_dev;         /* device-side count (run_years)                       */
@@ -740,6 +763,7 @@ struct IntegArgs {
     int32_t* cand_list; unsigned int* cand_count;   /* TC candidates (NULL: not collected)    */
     int lane_cap;                      /* lanes per warp that take storms (small batches)     */
     int pack;                          /* drain-phase packing of the surviving storms on/off  */
+    int prefetch;                      /* L2 prefetch of the Fourier-table lines ahead of the storm's clock on/off */
 };
 
 enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
@@ -754,9 +778,12 @@ enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
  * table is read from HBM/L2 (64 B per evaluation); only emitted samples go to HBM.
  * THREADS x MINB fixes the register budget (launch bounds): <256,1> 255 registers, <128,3> 168,
  * <128,4> 128 -- chosen at run time by tcr_set_tuning, default by measurement.   */
-template <int THREADS, int MINB, int KSMEM, int CTA_LOCKSTEP>
+template <int THREADS, int MINB, int KSMEM, int LOCKSTEP_FAST>
 __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_constant__ TcrCtx cx, const IntegArgs A)
 {
+    /* LOCKSTEP_FAST = slot mask of the CTA-wide re-alignment barriers (bits 0-5) + 256 for the straight-line RHS */
+    constexpr int CTA_LOCKSTEP = LOCKSTEP_FAST & 255;
+    constexpr bool FAST_RHS = (LOCKSTEP_FAST & 256) != 0;
     /* Stage storage, "stage" j = 0..7: K0 (FSAL derivative), K1..K5, K6, and the step's end state y_new.
      * KSMEM = 1: K1..K5 (dead during an RHS evaluation) live in shared memory, [stage][component][thread],
      * which frees 40 registers; KSMEM = 2: all eight (64 registers); KSMEM = 0: registers only. */
@@ -928,6 +955,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                             trk = A.track + (A.track_row ? (size_t)row : (size_t)sid) * row_doubles;
                             nfev = 0; n_out = 0; n_attempts = 0; any_v = false; t = 0.0; status = 100;
                             mode = M_INIT0;
+                            if (A.prefetch) tcr_ftab_prefetch<3>(cx, ftab, 0.0, 10.0 * cx.t_step);
                         }
                     }
                     if ((int64_t)base + cnt >= n) drained = true;
@@ -999,7 +1027,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
 
             double dy[4] = {0, 0, 0, 0};
             TcrRhsAux aux = {0, 0, 0, {0, 0, 0, 0}};
-            if (ev) { tcr_rhs(cx, ym, ftab, hbl, te, ye, dy, aux); ++nfev; }
+            if (ev) {
+                if constexpr (FAST_RHS) {
+                    /* straight-line evaluation (tcr_rhs_fast.cuh); an evaluation that left the common case of any
+                     * of its operations is repeated by the specification form */
+                    if (tcr_rhs_fast(cx, ym, ftab, hbl, te, ye, dy, aux)) {
+                        double yy[4] = {ye[0], ye[1], ye[2], ye[3]}, dd[4];
+                        TcrRhsAux ax2;
+                        tcr_rhs_slow(cx, ym, ftab, hbl, te, yy, dd, &ax2);
+                        dy[0] = dd[0]; dy[1] = dd[1]; dy[2] = dd[2]; dy[3] = dd[3];
+                        aux = ax2;
+                    }
+                } else {
+                    tcr_rhs(cx, ym, ftab, hbl, te, ye, dy, aux);
+                }
+                ++nfev;
+            }
 
             /* ---- consume ---- */
             if (mode == M_RK) {
@@ -1132,6 +1175,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 for (int i = 0; i < 4; ++i) { y[i] = ynl[i]; Ks(0, i, Kg(6, i)); }
                 new_step = true;
                 if (status != 100) finalize(status);
+                else if (A.prefetch) tcr_ftab_prefetch<5>(cx, ftab, t_new + 0.9 * h_abs, t_new + 2.2 * h_abs);
             } else {
                 double fac = 0.9 * tcr_pow(err, -0.2);
                 if (!(fac > 0.2)) fac = 0.2;

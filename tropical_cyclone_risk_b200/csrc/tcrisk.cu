@@ -129,7 +129,7 @@ struct tcr_handle {
     AxisBuf ax_lon_b, ax_lat_b, ax_lon_l, ax_lat_l, ax_lon_m, ax_lat_m;
     bool have_static = false, have_masks = false;
     /* tuning */
-    int integ_variant = 17, oversub_permille = 1020, interp_variant = 0;
+    int integ_variant = 21, oversub_permille = 1020, interp_variant = 0;
     /* within-year sharding (tcr_set_shard): rank r of `world` integrates the attempts k with k % world == r */
     int shard_rank = 0, shard_world = 1;
     tcr_allreduce_fn allreduce = nullptr;
@@ -256,6 +256,10 @@ int tcr_create(int device, const tcr_params* p, tcr_handle** out)
         return set_err("tcr_create: this library is built for sm_100a (Blackwell B200); device %d is sm_%d%d", device, prop.major, prop.minor);
     tcr_handle* h = new tcr_handle();
     h->device = device;
+    if (const char* iv = getenv("TCR_INTEG_VARIANT")) {                 /* A/B runs and tests of a non-default integrate variant */
+        const int v = atoi(iv);
+        if (v >= 1 && v <= 31) h->integ_variant = v - 1;
+    }
     h->num_sms = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
     memset(&h->ctx, 0, sizeof h->ctx);
@@ -318,7 +322,7 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 {
     if (!h) return set_err("null handle");
     if (integ_variant > 0) {
-        if (integ_variant > 21) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
+        if (integ_variant > 31) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
         h->integ_variant = integ_variant - 1;
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
@@ -367,6 +371,16 @@ int tcr_kernel_time(tcr_handle* h, int kernel_class, double* ms, int64_t* launch
     if (launches) *launches = h->class_launches[kernel_class];
     return 0;
 }
+
+#ifdef TCR_DEBUG_BAD
+/* instrumented builds only (scripts/probes/bad_sites.py): how often each operation of the straight-line RHS left its common case */
+int tcr_debug_bad(unsigned long long* out, int reset)
+{
+    if (cudaMemcpyFromSymbol(out, tcr_dbg_bad, sizeof(unsigned long long) * 33) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[33] = {0}; cudaMemcpyToSymbol(tcr_dbg_bad, z, sizeof z); }
+    return 0;
+}
+#endif
 
 int tcr_host_alloc(size_t bytes, void** out)
 {
@@ -668,6 +682,7 @@ static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_uppe
     int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
     a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
     { static const int pack_on = getenv("TCR_NO_PACK") ? 0 : 1; a.pack = pack_on; }
+    { static const int pf_on = getenv("TCR_NO_PREFETCH") ? 0 : 1; a.prefetch = pf_on; }
     a.pool_first = (unsigned int)grid * THREADS;                      /* lanes own rows [0, grid x THREADS) */
     /* KSMEM 2: eight stage vectors + the 18-word staging area of the drain-phase packing */
     const size_t smem = KSMEM == 2 ? (size_t)(32 + 18) * THREADS * sizeof(double) : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
@@ -700,6 +715,16 @@ static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
     case 18: launch_integrate_variant<192, 3, 2, 63>(h, a, n_upper); break;      /* 96 registers, 18 warps/SM */
     case 19: launch_integrate_variant<224, 2, 2, 63>(h, a, n_upper); break;      /* 144 registers, 14 warps/SM */
     case 20: launch_integrate_variant<384, 1, 2, 63>(h, a, n_upper); break;      /* one 12-warp CTA per SM */
+    case 21: launch_integrate_variant<192, 2, 2, 63 + 256>(h, a, n_upper); break; /* variant 17 with the straight-line RHS (tcr_rhs_fast.cuh) */
+    case 22: launch_integrate_variant<192, 2, 2, 3 + 256>(h, a, n_upper); break;  /* ... re-aligned at slots 0, 1 only */
+    case 23: launch_integrate_variant<192, 2, 2, 0 + 256>(h, a, n_upper); break;  /* ... free-running warps (no drain packing) */
+    case 24: launch_integrate_variant<192, 2, 2, 21 + 256>(h, a, n_upper); break; /* ... slots 0, 2, 4 */
+    case 25: launch_integrate_variant<256, 2, 2, 63 + 256>(h, a, n_upper); break; /* 128 registers, 16 warps/SM */
+    case 26: launch_integrate_variant<256, 2, 2, 0 + 256>(h, a, n_upper); break;
+    case 27: launch_integrate_variant<192, 3, 2, 0 + 256>(h, a, n_upper); break;  /* 96 registers, 18 warps/SM */
+    case 28: launch_integrate_variant<128, 3, 2, 63 + 256>(h, a, n_upper); break; /* three lock-step groups of 4 warps per SM */
+    case 29: launch_integrate_variant<96, 4, 2, 63 + 256>(h, a, n_upper); break;  /* four groups of 3 warps */
+    case 30: launch_integrate_variant<64, 6, 2, 63 + 256>(h, a, n_upper); break;  /* six groups of 2 warps */
     default: return set_err("unknown integrate variant %d", h->integ_variant);
     }
     CKK(h);
