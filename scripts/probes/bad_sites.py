@@ -15,8 +15,7 @@ import numpy as np                                                   # noqa: E40
 from tropical_cyclone_risk_b200 import _lib, workload                # noqa: E402
 from tropical_cyclone_risk_b200.engine import Engine                 # noqa: E402
 
-SITES = ["state", "fs_index", "locate", "cos", "chol_sqrt", "chol_div", "fourier_div", "S_free", "dy_div", "u_T", "log", "exp",
-         "z_div", "S", "exp_div", "log_div"]
+SITES = ["state", "fs_index", "locate", "cos", "cholesky_pivot", "range", "range_fourier", "-", "polar", "-", "log", "exp", "range_mixing"]
 
 
 def main():

@@ -723,28 +723,6 @@ __global__ void __launch_bounds__(FTM_THREADS, 1) k_fourier_table_mma(const __gr
 /* the integrator: Coupled_FAST.gen_track (coupled_fast.py:229-267) incl. scipy's RK45        */
 /* driver loop, t_eval dense output and the terminal event                                    */
 /* ======================================================================================== */
-/* The storm's Fourier table was written by the previous kernel and is long gone from L2 when the integrator reads it:
- * every evaluation of every lane would start with an HBM round trip for its node pair (an RK attempt spans about six
- * one-hour nodes, so nearly every stage brackets a new pair) and the warp waits for the slowest of its 32 lanes.  The
- * access is sequential in time, so the lane asks L2 for the 128-byte lines of the nodes in [t0, t1] ahead of use.   */
-template <int LINES>
-__device__ __forceinline__ void tcr_ftab_prefetch(const TcrCtx& cx, const double* __restrict__ ftab, double t0, double t1)
-{
-    const int n = cx.p.n_steps;
-    int i0 = tcr_floor_guess(t0 * cx.inv_t_step), i1 = tcr_floor_guess(t1 * cx.inv_t_step) + 1;
-    if (i0 < 0) i0 = 0;
-    if (i0 > n - 1) i0 = n - 1;
-    if (i1 < i0) i1 = i0;
-    if (i1 > n - 1) i1 = n - 1;
-    const unsigned long long a0 = (unsigned long long)(ftab + (size_t)i0 * 4) & ~127ull;
-    const unsigned long long a1 = (unsigned long long)(ftab + (size_t)i1 * 4 + 3);
-#pragma unroll
-    for (int k = 0; k < LINES; ++k) {
-        const unsigned long long a = a0 + 128ull * k;
-        if (a <= a1) asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
-    }
-}
-
 struct IntegArgs {
     int64_t n;                         /* number of storms (slots) if n_dev == NULL           */
     const unsigned int* n_dev;         /* device-side count (run_years)                       */
@@ -763,7 +741,6 @@ struct IntegArgs {
     int32_t* cand_list; unsigned int* cand_count;   /* TC candidates (NULL: not collected)    */
     int lane_cap;                      /* lanes per warp that take storms (small batches)     */
     int pack;                          /* drain-phase packing of the surviving storms on/off  */
-    int prefetch;                      /* L2 prefetch of the Fourier-table lines ahead of the storm's clock on/off */
 };
 
 enum { M_IDLE = 0, M_INIT0 = 1, M_INIT1 = 2, M_WAIT = 3, M_RK = 4 };
@@ -807,9 +784,27 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
     int64_t sid = -1;
     int ym = 0, nfev = 0, n_out = 0, status = 0, n_attempts = 0;
     bool rejected = false, new_step = false, any_v = false;
-    double hbl = 0.0, t = 0.0, h = 0.0, h_abs = 0.0, t_new = 0.0, g = 0.0, min_step = 0.0;
-    double h0 = 0.0, d1 = 0.0;
-    double y[4] = {0, 0, 0, 0};
+    /* Step-control state.  With KSMEM = 2 it lives in shared memory (the rows of the drain-phase staging area are each
+     * thread's "home" slots): it is touched a few times per RK attempt but would otherwise hold 24 registers across every
+     * RHS evaluation, where the register file is the scarce resource (168 per thread at 12 warps per SM).
+     * home rows: 0-3 y, 4 t, 5 h_abs, 6 g, 7 min_step, 8 h, 9 t_new, 10 h0, 11 d1; rows 12-17 are the packing mailbox */
+    constexpr bool HOMES = (KSMEM == 2);
+    double* const hs = k_smem + (HOMES ? 32 * THREADS + (int)threadIdx.x : 0);
+    double hbl = 0.0;
+    double r_y[4] = {0, 0, 0, 0}, r_t = 0.0, r_h = 0.0, r_h_abs = 0.0, r_t_new = 0.0, r_g = 0.0, r_min_step = 0.0, r_h0 = 0.0, r_d1 = 0.0;
+    auto Y = [&](int i) -> double& { return HOMES ? hs[i * THREADS] : r_y[i]; };
+    double& t = HOMES ? hs[4 * THREADS] : r_t;
+    double& h_abs = HOMES ? hs[5 * THREADS] : r_h_abs;
+    double& g = HOMES ? hs[6 * THREADS] : r_g;
+    double& min_step = HOMES ? hs[7 * THREADS] : r_min_step;
+    double& h = HOMES ? hs[8 * THREADS] : r_h;
+    double& t_new = HOMES ? hs[9 * THREADS] : r_t_new;
+    double& h0 = HOMES ? hs[10 * THREADS] : r_h0;
+    double& d1 = HOMES ? hs[11 * THREADS] : r_d1;
+    if (HOMES) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) hs[i * THREADS] = 0.0;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
@@ -878,14 +873,24 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                     total += c; warps_used += (c > 0); if (w < wid) before += c;
                 }
                 if (total > 0 && total <= 32 * (warps_used - 1)) {
-                    double* stg = k_smem + 32 * THREADS;                 /* [18][THREADS] staging behind the stage vectors */
-                    if (mode != M_IDLE) {
+                    /* the live storm of rank r moves to thread r: its home rows (y, t, h_abs, g, min_step) and K0 are
+                     * read first, then written into thread r's rows; what it keeps in registers goes through the mailbox */
+                    double* const stg = k_smem + 32 * THREADS;
+                    const bool live = mode != M_IDLE;
+                    double py[4] = {0, 0, 0, 0}, pk[4] = {0, 0, 0, 0}, pt = 0.0, ph = 0.0, pg = 0.0, pm = 0.0;
+                    if (live) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { py[i] = Y(i); pk[i] = Kg(0, i); }
+                        pt = t; ph = h_abs; pg = g; pm = min_step;
+                    }
+                    __syncthreads();
+                    if (live) {
                         const int r = before + __popc(act_b & ((1u << lane) - 1u));
                         double* d = stg + r;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) { d[i * THREADS] = y[i]; d[(4 + i) * THREADS] = Kg(0, i); }
-                        d[8 * THREADS] = t; d[9 * THREADS] = h_abs; d[10 * THREADS] = g; d[11 * THREADS] = hbl;
-                        d[12 * THREADS] = min_step;
+                        for (int i = 0; i < 4; ++i) { d[i * THREADS] = py[i]; k_smem[k_off(0, i) + r] = pk[i]; }
+                        d[4 * THREADS] = pt; d[5 * THREADS] = ph; d[6 * THREADS] = pg; d[7 * THREADS] = pm;
+                        d[12 * THREADS] = hbl;
                         d[13 * THREADS] = __longlong_as_double((long long)sid);
                         d[14 * THREADS] = __hiloint2double(ym, nfev);
                         d[15 * THREADS] = __hiloint2double(n_out, n_attempts);
@@ -895,10 +900,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                     __syncthreads();
                     if ((int)threadIdx.x < total) {
                         const double* d = stg + threadIdx.x;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) { y[i] = d[i * THREADS]; Ks(0, i, d[(4 + i) * THREADS]); }
-                        t = d[8 * THREADS]; h_abs = d[9 * THREADS]; g = d[10 * THREADS]; hbl = d[11 * THREADS];
-                        min_step = d[12 * THREADS];
+                        hbl = d[12 * THREADS];
                         sid = (int64_t)__double_as_longlong(d[13 * THREADS]);
                         ym = __double2hiint(d[14 * THREADS]); nfev = __double2loint(d[14 * THREADS]);
                         n_out = __double2hiint(d[15 * THREADS]); n_attempts = __double2loint(d[15 * THREADS]);
@@ -912,7 +914,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                     } else {
                         mode = M_IDLE;             /* the queue is drained: this lane never needs a row again */
                     }
-                    __syncthreads();                                     /* staging reusable by the next packing */
+                    __syncthreads();                                     /* mailbox reusable by the next packing */
                 }
             }
         }
@@ -949,13 +951,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                         if (my < n) {
                             sid = my;
                             ym = A.ym[sid];
-                            y[0] = A.lon0[sid]; y[1] = A.lat0[sid]; y[2] = A.v0[sid]; y[3] = A.m0[sid];
+                            Y(0) = A.lon0[sid]; Y(1) = A.lat0[sid]; Y(2) = A.v0[sid]; Y(3) = A.m0[sid];
                             hbl = 0.5 * p.Ck / A.h_bl[sid];          /* storm-constant prefactor of dv/dt, dm/dt */
                             ftab = A.ftab + (size_t)sid * ns * 4;
                             trk = A.track + (A.track_row ? (size_t)row : (size_t)sid) * row_doubles;
                             nfev = 0; n_out = 0; n_attempts = 0; any_v = false; t = 0.0; status = 100;
                             mode = M_INIT0;
-                            if (A.prefetch) tcr_ftab_prefetch<3>(cx, ftab, 0.0, 10.0 * cx.t_step);
                         }
                     }
                     if ((int64_t)base + cnt >= n) drained = true;
@@ -982,35 +983,35 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 case 0:
                     te = t + RK_C1 * h;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) ye[i] = fma(Kg(0, i) * RK_A10, h, y[i]);
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(Kg(0, i) * RK_A10, h, Y(i));
                     break;
                 case 1:
                     te = t + RK_C2 * h;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(Kg(1, i), RK_A21, Kg(0, i) * RK_A20), h, y[i]);
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(Kg(1, i), RK_A21, Kg(0, i) * RK_A20), h, Y(i));
                     break;
                 case 2:
                     te = t + RK_C3 * h;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(Kg(2, i), RK_A32, fma(Kg(1, i), RK_A31, Kg(0, i) * RK_A30)), h, y[i]);
+                    for (int i = 0; i < 4; ++i) ye[i] = fma(fma(Kg(2, i), RK_A32, fma(Kg(1, i), RK_A31, Kg(0, i) * RK_A30)), h, Y(i));
                     break;
                 case 3:
                     te = t + RK_C4 * h;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        ye[i] = fma(fma(Kg(3, i), RK_A43, fma(Kg(2, i), RK_A42, fma(Kg(1, i), RK_A41, Kg(0, i) * RK_A40))), h, y[i]);
+                        ye[i] = fma(fma(Kg(3, i), RK_A43, fma(Kg(2, i), RK_A42, fma(Kg(1, i), RK_A41, Kg(0, i) * RK_A40))), h, Y(i));
                     break;
                 case 4:
                     te = t + 1.0 * h;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        ye[i] = fma(fma(Kg(4, i), RK_A54, fma(Kg(3, i), RK_A53, fma(Kg(2, i), RK_A52, fma(Kg(1, i), RK_A51, Kg(0, i) * RK_A50)))), h, y[i]);
+                        ye[i] = fma(fma(Kg(4, i), RK_A54, fma(Kg(3, i), RK_A53, fma(Kg(2, i), RK_A52, fma(Kg(1, i), RK_A51, Kg(0, i) * RK_A50)))), h, Y(i));
                     break;
                 default:
                     te = t + h;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        ye[i] = fma(h, fma(Kg(5, i), RK_B5, fma(Kg(4, i), RK_B4, fma(Kg(3, i), RK_B3, fma(Kg(2, i), RK_B2, Kg(0, i) * RK_B0)))), y[i]);
+                        ye[i] = fma(h, fma(Kg(5, i), RK_B5, fma(Kg(4, i), RK_B4, fma(Kg(3, i), RK_B3, fma(Kg(2, i), RK_B2, Kg(0, i) * RK_B0)))), Y(i));
                         Ks(7, i, ye[i]);
                     }
                     break;
@@ -1018,7 +1019,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
             } else if (mode == M_INIT0) {
                 ev = true; te = 0.0;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ye[i] = y[i];
+                for (int i = 0; i < 4; ++i) ye[i] = Y(i);
             } else if (mode == M_INIT1) {
                 ev = true; te = 0.0 + h0;
 #pragma unroll
@@ -1070,22 +1071,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         Ks(0, i, dy[i]);
-                        double scale = atol + fabs(y[i]) * rtol;
-                        sa[i] = y[i] / scale; sb[i] = dy[i] / scale;
+                        double scale = atol + fabs(Y(i)) * rtol;
+                        sa[i] = Y(i) / scale; sb[i] = dy[i] / scale;
                     }
                     double d0 = tcr_rms4(sa);
                     d1 = tcr_rms4(sb);
                     if (d0 < 1e-5 || d1 < 1e-5) h0 = 1e-6; else h0 = 0.01 * d0 / d1;
                     if (t_bound < h0) h0 = t_bound;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) Ks(7, i, fma(h0, dy[i], y[i]));
+                    for (int i = 0; i < 4; ++i) Ks(7, i, fma(h0, dy[i], Y(i)));
                     mode = M_INIT1;
                 }
             } else if (mode == M_INIT1) {
                 double sc[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    double scale = atol + fabs(y[i]) * rtol;
+                    double scale = atol + fabs(Y(i)) * rtol;
                     sc[i] = (dy[i] - Kg(0, i)) / scale;
                 }
                 double d2 = tcr_rms4(sc) / h0, h1;
@@ -1096,7 +1097,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 if (t_bound < hh) hh = t_bound;
                 if (max_step < hh) hh = max_step;
                 h_abs = hh;
-                g = tcr_event(p, y);
+                { const double yl[4] = {Y(0), Y(1), Y(2), Y(3)}; g = tcr_event(p, yl); }
                 mode = M_WAIT;
             }
         }
@@ -1107,7 +1108,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
             const double ynl[4] = {Kg(7, 0), Kg(7, 1), Kg(7, 2), Kg(7, 3)};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                double ay = fabs(y[i]), an = fabs(ynl[i]);
+                double ay = fabs(Y(i)), an = fabs(ynl[i]);
                 double mx = (tcr_isnan(ay) || tcr_isnan(an)) ? NAN : (ay > an ? ay : an);
                 double scale = atol + mx * rtol;
                 double e = fma(Kg(6, i), RK_E6, fma(Kg(5, i), RK_E5, fma(Kg(4, i), RK_E4, fma(Kg(3, i), RK_E3, fma(Kg(2, i), RK_E2, Kg(0, i) * RK_E0)))));
@@ -1140,6 +1141,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                     }
                     const double hd = t_new - t_old, yhd = tcr_rcp_seed(hd);
                     const double k0l[4] = {Kg(0, 0), Kg(0, 1), Kg(0, 2), Kg(0, 3)};
+                    const double yl[4] = {Y(0), Y(1), Y(2), Y(3)};
                     /* four samples per trip, computed unconditionally (the last trip repeats its final
                      * sample) so that the four dependent chains interleave; only the stores are guarded */
                     for (int k0 = n_out; k0 < i_new; k0 += 4) {
@@ -1155,7 +1157,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                                 acc = fma(Q1[i], p2, acc);
                                 acc = fma(Q2[i], p3, acc);
                                 acc = fma(Q3[i], p4, acc);
-                                o[u][i] = fma(hd, acc, y[i]);
+                                o[u][i] = fma(hd, acc, yl[i]);
                             }
                         }
 #pragma unroll
@@ -1172,10 +1174,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 }
                 t = t_new;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) { y[i] = ynl[i]; Ks(0, i, Kg(6, i)); }
+                for (int i = 0; i < 4; ++i) { Y(i) = ynl[i]; Ks(0, i, Kg(6, i)); }
                 new_step = true;
                 if (status != 100) finalize(status);
-                else if (A.prefetch) tcr_ftab_prefetch<5>(cx, ftab, t_new + 0.9 * h_abs, t_new + 2.2 * h_abs);
             } else {
                 double fac = 0.9 * tcr_pow(err, -0.2);
                 if (!(fac > 0.2)) fac = 0.2;

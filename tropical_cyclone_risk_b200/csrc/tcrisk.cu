@@ -682,7 +682,6 @@ static void launch_integrate_variant(tcr_handle* h, IntegArgs& a, int64_t n_uppe
     int64_t lanes = (n_upper + (int64_t)grid * warps_per_cta - 1) / ((int64_t)grid * warps_per_cta);
     a.lane_cap = (int)std::max<int64_t>(1, std::min<int64_t>(32, lanes));
     { static const int pack_on = getenv("TCR_NO_PACK") ? 0 : 1; a.pack = pack_on; }
-    { static const int pf_on = getenv("TCR_NO_PREFETCH") ? 0 : 1; a.prefetch = pf_on; }
     a.pool_first = (unsigned int)grid * THREADS;                      /* lanes own rows [0, grid x THREADS) */
     /* KSMEM 2: eight stage vectors + the 18-word staging area of the drain-phase packing */
     const size_t smem = KSMEM == 2 ? (size_t)(32 + 18) * THREADS * sizeof(double) : KSMEM == 1 ? (size_t)20 * THREADS * sizeof(double) : 0;
