@@ -84,10 +84,14 @@ __global__ void k_build_axis(const double* __restrict__ ax, TcrNode* __restrict_
     }
 }
 
-/* tcr_rcp_seed of the constant divisors of the RHS (out[0] = earth_R, out[1] = pi) */
-__global__ void k_build_consts(double earth_R, double* __restrict__ out)
+/* tcr_rcp_seed of the constant divisors of the RHS (out[0] = earth_R, out[1] = pi); out[2], out[3] = sine of the genesis
+ * latitude bounds -- the same tcr_sin every seeding thread used to evaluate for itself */
+__global__ void k_build_consts(double earth_R, double gen_lat_min, double gen_lat_max, double* __restrict__ out)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = tcr_rcp_seed(earth_R); out[1] = tcr_rcp_seed(TCR_PI); }
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        out[0] = tcr_rcp_seed(earth_R); out[1] = tcr_rcp_seed(TCR_PI);
+        out[2] = tcr_sin(TCR_DEG2RAD * gen_lat_min); out[3] = tcr_sin(TCR_DEG2RAD * gen_lat_max);
+    }
 }
 
 /* storm-independent harmonics of the output time grid: sc[j][k] = {sin, cos}(2 pi (k+1) t_j / T_Fs) */
@@ -528,16 +532,24 @@ __global__ void k_coef_from_philox(const __grid_constant__ TcrCtx cx, const unsi
                                    const int64_t* __restrict__ slot_att, const int32_t* __restrict__ slot_key,
                                    uint32_t run_seed, double2* __restrict__ coef)
 {
+    /* thread = one Philox block = the two phases (2 j, 2 j + 1) of a slot: 30 threads per slot, 32 bytes written each */
+    constexpr int HALF = TCR_N_PHASES / 2;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t slot = idx / TCR_N_PHASES;
+    int64_t slot = idx / HALF;
     if (slot >= (int64_t)*n_slots) return;
-    int pair = (int)(idx - slot * TCR_N_PHASES);
+    const int j = (int)(idx - slot * HALF);
     double u[2];
-    tcr_draw2(run_seed, slot_key[slot], slot_att[slot], (uint32_t)(pair >> 1), 1u, u);
-    double s, c;
-    tcr_sincos2pi(u[pair & 1], &s, &c);
-    double amp = cx.p.fourier_amp[pair % TCR_N_HARM];
-    coef[idx] = make_double2(amp * c, amp * s);
+    tcr_draw2(run_seed, slot_key[slot], slot_att[slot], (uint32_t)j, 1u, u);
+    double2 out[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        double s, c;
+        tcr_sincos2pi(u[e], &s, &c);
+        const double amp = cx.p.fourier_amp[(2 * j + e) % TCR_N_HARM];
+        out[e] = make_double2(amp * c, amp * s);
+    }
+    double2* dst = coef + slot * TCR_N_PHASES + 2 * j;
+    dst[0] = out[0]; dst[1] = out[1];
 }
 
 /* ======================================================================================== */
@@ -1347,7 +1359,10 @@ struct SeedArgs {
 
 __device__ __forceinline__ double tcr_mask_at(const uint2 r[4], int b, const TcrCell& c)
 {
-    auto byte = [&](const uint2& q) { return (double)(((b < 4 ? q.x : q.y) >> (8 * (b & 3))) & 0xffu); };
+    /* (double)byte without the conversion pipe: 2^52 + byte is exact */
+    auto byte = [&](const uint2& q) {
+        return __hiloint2double(0x43300000, (int)(((b < 4 ? q.x : q.y) >> (8 * (b & 3))) & 0xffu)) - 4503599627370496.0;
+    };
     return tcr_bilin_fitpack(byte(r[0]), byte(r[1]), byte(r[2]), byte(r[3]), c);
 }
 
@@ -1376,7 +1391,7 @@ __global__ void __launch_bounds__(256) k_seed(const __grid_constant__ TcrCtx cx,
         const double* b = p.basin_bounds;
         double u[2];
         tcr_draw2(A.run_seed, key, k, 0, 0, u);
-        const double y_min = tcr_sin(TCR_DEG2RAD * p.gen_lat_min), y_max = tcr_sin(TCR_DEG2RAD * p.gen_lat_max);
+        const double y_min = cx.gen_y_min, y_max = cx.gen_y_max;
         gen_lon = b[0] + (b[2] - b[0]) * u[0];
         gen_lat = tcr_asin(y_min + (y_max - y_min) * u[1]) * 180.0 / TCR_PI;
         int redraw = 0;
@@ -1395,9 +1410,20 @@ __global__ void __launch_bounds__(256) k_seed(const __grid_constant__ TcrCtx cx,
         tcr_draw2(A.run_seed, key, k, 1, 0, u);
         mon = 1 + (int)floor(u[0] * 12.0);
         const double r_lowlat = u[1];
-        double best = -INFINITY;
-        for (int i = 0; i < TCR_N_BASINS; ++i) {
-            double val = tcr_mask_at(r, i, c);
+        /* arg max over the seven basin masks (first maximum wins, compute.py:150-153).  A basin whose four corner bytes
+         * are zero interpolates to +0 exactly and can only win as basin 0 of an all-zero cell, so only the basins present
+         * at the cell are evaluated: one or two instead of seven */
+        const unsigned ox = r[0].x | r[1].x | r[2].x | r[3].x, oy = r[0].y | r[1].y | r[2].y | r[3].y;
+        double best = (ox & 0xffu) ? tcr_mask_at(r, 0, c) : 0.0;
+        bi = 0;
+        unsigned present = 0u;
+#pragma unroll
+        for (int i = 1; i < TCR_N_BASINS; ++i)
+            if (((i < 4 ? ox : oy) >> (8 * (i & 3))) & 0xffu) present |= 1u << i;
+        while (present) {
+            const int i = __ffs((int)present) - 1;
+            present &= present - 1u;
+            const double val = tcr_mask_at(r, i, c);
             if (val > best) { best = val; bi = i; }
         }
         double q = (fabs(gen_lat) - p.lat_vort_fac) / 12.0;

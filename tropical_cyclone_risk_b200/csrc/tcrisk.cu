@@ -271,11 +271,13 @@ int tcr_create(int device, const tcr_params* p, tcr_handle** out)
     h->ctx.inv_t_step = 1.0 / h->ctx.t_step;
     k_build_sincos<<<(p->n_steps + 127) / 128, 128, 0, h->stream>>>(h->ctx, h->sincos.as<double2>());
     double* d_consts = reinterpret_cast<double*>(h->pinned);          /* pinned memory is device-accessible (UVA) */
-    k_build_consts<<<1, 32, 0, h->stream>>>(p->earth_R, d_consts);
+    k_build_consts<<<1, 32, 0, h->stream>>>(p->earth_R, p->gen_lat_min, p->gen_lat_max, d_consts);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     h->ctx.y_earth_R = d_consts[0];
     h->ctx.y_pi = d_consts[1];
+    h->ctx.gen_y_min = d_consts[2];
+    h->ctx.gen_y_max = d_consts[3];
     if (e != cudaSuccess) {
         set_err("tcr_create: harmonic table build failed: %s", cudaGetErrorString(e));
         h->sincos.release(); cudaFreeHost(h->pinned); delete h;
@@ -1122,7 +1124,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         const int64_t slots_upper = std::min<int64_t>(slot_cap, total);
         {
             LaunchTimer lt_(h, TCR_K_COEF);
-            k_coef_from_philox<<<(unsigned)((slots_upper * TCR_N_PHASES + 255) / 256), 256, 0, s>>>(
+            k_coef_from_philox<<<(unsigned)((slots_upper * (TCR_N_PHASES / 2) + 255) / 256), 256, 0, s>>>(
                 h->ctx, d_nslots, as.s_att, as.s_key, run_seed, w.coef.as<double2>());
         }
         CKK(h);
