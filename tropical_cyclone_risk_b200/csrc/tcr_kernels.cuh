@@ -1383,30 +1383,76 @@ __global__ void __launch_bounds__(256) k_seed(const __grid_constant__ TcrCtx cx,
     int code = -1;
     int bi = 0, mon = 1, yr = 0;
     int64_t k = 0;
+    int32_t key = 0;
     double gen_lon = 0, gen_lat = 0, v0 = 0, m0 = 0, pi = 0;
-    if (idx < total) {
+    const bool active = idx < total;
+    const double* b = p.basin_bounds;
+    TcrCell c;
+    uint2 r[4];
+    bool pending = false, exhausted = false;
+    if (active) {
         while (yr + 1 < A.n_years && idx >= A.wave_off[yr + 1]) ++yr;
         k = A.k0[yr] + (idx - A.wave_off[yr]);
-        const int32_t key = A.year_key[yr];
-        const double* b = p.basin_bounds;
+        key = A.year_key[yr];
         double u[2];
         tcr_draw2(A.run_seed, key, k, 0, 0, u);
         const double y_min = cx.gen_y_min, y_max = cx.gen_y_max;
         gen_lon = b[0] + (b[2] - b[0]) * u[0];
         gen_lat = tcr_asin(y_min + (y_max - y_min) * u[1]) * 180.0 / TCR_PI;
-        int redraw = 0;
-        bool exhausted = false;
-        TcrCell c;
-        uint2 r[4];
-        for (;;) {
-            tcr_mask_cell(cx.mk, gen_lon, gen_lat, c, r);
-            if (!(tcr_mask_at(r, 7, c) < 1e-2)) break;
-            if (redraw >= p.max_redraws) { exhausted = true; break; }
-            tcr_draw2(A.run_seed, key, k, 3u + (uint32_t)redraw, 0, u);
-            gen_lon = b[0] + (b[2] - b[0]) * u[0];
-            gen_lat = b[1] + (b[3] - b[1]) * u[1];
-            ++redraw;
+        tcr_mask_cell(cx.mk, gen_lon, gen_lat, c, r);
+        pending = tcr_mask_at(r, 7, c) < 1e-2;
+    }
+    /* The ocean-point redraw (compute.py:144-148: `while f_b.ev(lon, lat) < 1e-2: redraw uniformly in the box`).  Redraw r
+     * of attempt k is a pure function of (k, r), so it need not be evaluated by the attempt's own lane: the lanes of the
+     * warp whose first draw hit the ocean would otherwise idle through the tail of the slowest lane's loop (on the global
+     * box 12 of 32 lanes were active on average).  Every round the 32 lanes are dealt out to the still-pending attempts
+     * and test their next g = 32 / pending redraws at once; the first hit in redraw order wins, and the winner is
+     * re-evaluated by its owner afterwards (one full-width pass).  Redraws are capped at max_redraws (code 3). */
+    {
+        const int lane = threadIdx.x & 31;
+        int next_r = 0, rstar = -1;
+        unsigned pend = __ballot_sync(TCR_FULL, pending);
+        while (pend) {
+            const int m = __popc(pend);
+            const int g = 32 / m;
+            const int j = lane / g;
+            const bool has = j < m;
+            const int owner = has ? (int)__fns(pend, 0, j + 1) : 0;
+            const long long k_o = __shfl_sync(TCR_FULL, (long long)k, owner);
+            const int32_t key_o = __shfl_sync(TCR_FULL, key, owner);
+            const int r_o = __shfl_sync(TCR_FULL, next_r, owner) + (lane - j * g);
+            bool okr = false;
+            if (has && r_o < p.max_redraws) {
+                double uu[2];
+                tcr_draw2(A.run_seed, key_o, (int64_t)k_o, 3u + (uint32_t)r_o, 0, uu);
+                const double lo = b[0] + (b[2] - b[0]) * uu[0], la = b[1] + (b[3] - b[1]) * uu[1];
+                TcrCell cc;
+                uint2 rr[4];
+                tcr_mask_cell(cx.mk, lo, la, cc, rr);
+                okr = !(tcr_mask_at(rr, 7, cc) < 1e-2);
+            }
+            const unsigned hit = __ballot_sync(TCR_FULL, okr);
+            if (pending) {
+                const int pos = __popc(pend & ((1u << lane) - 1u));
+                const unsigned grp = (hit >> (pos * g)) & (g == 32 ? 0xffffffffu : ((1u << g) - 1u));
+                if (grp) { rstar = next_r + __ffs((int)grp) - 1; pending = false; }
+                else {
+                    next_r += g;
+                    if (next_r >= p.max_redraws) { exhausted = true; rstar = p.max_redraws - 1; pending = false; }
+                }
+            }
+            pend = __ballot_sync(TCR_FULL, pending);
         }
+        if (active && rstar >= 0) {
+            double uu[2];
+            tcr_draw2(A.run_seed, key, k, 3u + (uint32_t)rstar, 0, uu);
+            gen_lon = b[0] + (b[2] - b[0]) * uu[0];
+            gen_lat = b[1] + (b[3] - b[1]) * uu[1];
+            tcr_mask_cell(cx.mk, gen_lon, gen_lat, c, r);
+        }
+    }
+    if (active) {
+        double u[2];
         tcr_draw2(A.run_seed, key, k, 1, 0, u);
         mon = 1 + (int)floor(u[0] * 12.0);
         const double r_lowlat = u[1];
