@@ -4,7 +4,7 @@ TAG=${1:-quick}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -x -q ${2:+-k "$2"} > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -3 $OUT/pytest_gpu.log | cut -c1-300
-for cfg in "cfg2:" "cfg1:--basin NA --years 10 --tracks 1000"; do
+for cfg in "cfg2:" "cfg1:--basin NA --years 10 --tracks 1000" "cfg3rank:--years 5 --tracks 20000"; do
 name=${cfg%%:*}; args=${cfg#*:}
 timeout 900 python bench.py --no-cpu --no-interp $args > $OUT/bench_$name.json 2> $OUT/bench_$name.err; python - <<PY
 import json

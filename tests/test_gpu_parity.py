@@ -144,7 +144,7 @@ def test_integrate_golden_seeds_bit_exact(na_case, na_eng):
     _check_integrate(na_eng, na_case, (np.zeros(n, np.int32), g["lon0"], g["lat0"], g["v0"], g["m0"], g["h_bl"], g["phases"]))
 
 
-@pytest.mark.parametrize("variant", list(range(1, 32)))
+@pytest.mark.parametrize("variant", list(range(1, 33)))
 def test_integrate_random_bit_exact(na_case, na_eng, variant):
     """every register-budget variant of the integrate kernel (tcr_set_tuning)"""
     na_eng.set_tuning(integ_variant=variant)

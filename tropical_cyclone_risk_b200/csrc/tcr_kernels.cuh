@@ -1685,7 +1685,7 @@ __global__ void __launch_bounds__(256) k_wave_stats(const WaveStatsArgs A)
 }
 
 struct SelectArgs {
-    int n_tracks;
+    int n_years, n_tracks;
     const int64_t* wave_off; const int64_t* k0;
     const int64_t* consumed;    /* [n_years] attempts of the year's range that were fully processed   */
     const int32_t* code; const int32_t* basin; const int32_t* month; const int32_t* att_slot;
@@ -1697,115 +1697,183 @@ struct SelectArgs {
     double* tc_month; int32_t* tc_basin; double* n_seeds;    /* outputs (device)               */
     tcr_year_stats* stats;      /* [n_years] device accumulators                               */
     const unsigned int* pool_ctl;   /* [1] != 0: the track pool overflowed -- the wave is void, nothing is committed */
+    /* scratch of the three selection kernels (a year's attempt range starts on a 256-attempt block boundary) */
+    unsigned int* blk_kept;     /* [blocks] kept storms of the block (k_count_kept)                      */
+    unsigned int* blk_pref;     /* [blocks] kept storms of the year before the block (k_select_scan)     */
+    int64_t* istar;             /* [n_years] attempt of the want-th kept storm, -1: not reached, -2: no work */
+    int32_t* total_kept;        /* [n_years] kept storms in the year's processed range                   */
+    unsigned long long* sel_acc;    /* [n_years][6] over-shoot: counted, integrated, steps, rhs; kept steps; exhausted */
+    unsigned int* sel_hist;     /* [n_years][84] over-shoot counted attempts per (basin, month)          */
 };
 
-#define SEL_ITEMS 8
-#define SEL_WORDS 4
-__global__ void __launch_bounds__(1024) k_select(const SelectArgs A)
+/* The sequential acceptance `while nt < n_tracks` (util/compute.py:134, 205-207) as an ordered selection in three
+ * fully parallel steps (round 1 scanned a year's kept flags with ONE CTA: 5 % of the step at 20 000 tracks per year,
+ * where a year is 40 M attempts): kept storms per 256-attempt block -> per-year exclusive scan of the block counts,
+ * which also locates i* = the attempt of the want-th kept storm -> every attempt finds its own rank (block prefix +
+ * ballot rank), emits its row if rank <= want, or adds itself to the over-shoot statistics if it lies beyond i*.   */
+__global__ void __launch_bounds__(256) k_count_kept(const uint8_t* __restrict__ att_kept, int64_t total, unsigned int* __restrict__ blk_kept)
 {
-    __shared__ int warp_tot[32];
-    __shared__ int s_running, s_istar;
-    __shared__ unsigned long long s_acc[6];
-    __shared__ unsigned int s_hist[TCR_N_BASINS * 12];
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = __syncthreads_count(idx < total && att_kept[idx] != 0);
+    if (threadIdx.x == 0) blk_kept[blockIdx.x] = (unsigned int)c;
+}
+
+__global__ void __launch_bounds__(1024) k_select_scan(const SelectArgs A)
+{
+    __shared__ unsigned int warp_tot[32];
+    __shared__ unsigned int s_running;
+    __shared__ long long s_bstar;
     const int yr = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int r = tid; r < A.n_tracks; r += blockDim.x) A.row_slot[(size_t)yr * A.n_tracks + r] = -1;
     if (A.pool_ctl[1]) return;
     const int64_t off = A.wave_off[yr];
     const int64_t W = A.consumed[yr];
-    for (int r = tid; r < A.n_tracks; r += blockDim.x) A.row_slot[(size_t)yr * A.n_tracks + r] = -1;
-    if (W == 0) { if (tid == 0) A.used[yr] = 0; return; }
-    const int nt0 = A.nt[yr];
-    const int want = A.n_tracks - nt0;
-    if (tid == 0) { s_running = 0; s_istar = -1; }
-    if (tid < 6) s_acc[tid] = 0ull;
-    for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) s_hist[i] = 0u;
+    if (W == 0) { if (tid == 0) { A.istar[yr] = -2; A.total_kept[yr] = 0; } return; }
+    const unsigned int want = (unsigned int)(A.n_tracks - A.nt[yr]);
+    const int64_t b0 = off >> 8, nb = (W + 255) >> 8;          /* blocks holding processed attempts */
+    if (tid == 0) { s_running = 0u; s_bstar = -1; }
     __syncthreads();
-    /* pass 1: rank the kept storms in attempt order, find i* = attempt of the want-th kept.
-     * Each thread owns SEL_WORDS x 8 consecutive attempts (8-byte loads of kept flags when aligned):
-     * 32768 attempts per trip of the CTA, so a year of ~360 000 attempts takes 11 block scans. */
-    const uint8_t* kb = A.att_kept + off;
-    const bool al8 = (((uintptr_t)kb) & 7) == 0;
-    for (int64_t base = 0; base < W; base += (int64_t)blockDim.x * SEL_ITEMS * SEL_WORDS) {
-        const int64_t i0 = base + (int64_t)tid * SEL_ITEMS * SEL_WORDS;
-        unsigned long long bits[SEL_WORDS];
-        int cnt = 0;
+    for (int64_t base = 0; base < nb; base += 1024 * 4) {
+        unsigned int v[4], sum = 0u;
 #pragma unroll
-        for (int w = 0; w < SEL_WORDS; ++w) {
-            const int64_t iw = i0 + w * SEL_ITEMS;
-            bits[w] = 0ull;
-            if (iw + SEL_ITEMS <= W && al8) bits[w] = *reinterpret_cast<const unsigned long long*>(kb + iw);
-            else
-                for (int j = 0; j < SEL_ITEMS; ++j) if (iw + j < W) bits[w] |= (unsigned long long)kb[iw + j] << (8 * j);
-            cnt += __popcll(bits[w]);
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = base + (int64_t)tid * 4 + j;
+            v[j] = i < nb ? A.blk_kept[b0 + i] : 0u;
+            sum += v[j];
         }
-        int incl = cnt;
+        unsigned int incl = sum;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(TCR_FULL, incl, d); if (lane >= d) incl += v; }
+        for (int d = 1; d < 32; d <<= 1) { unsigned int u = __shfl_up_sync(TCR_FULL, incl, d); if (lane >= d) incl += u; }
         if (lane == 31) warp_tot[wid] = incl;
         __syncthreads();
         if (wid == 0) {
-            int v = warp_tot[lane], sc = v;
+            unsigned int t = warp_tot[lane], sc = t;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { int u = __shfl_up_sync(TCR_FULL, sc, d); if (lane >= d) sc += u; }
-            warp_tot[lane] = sc - v;
+            for (int d = 1; d < 32; d <<= 1) { unsigned int u = __shfl_up_sync(TCR_FULL, sc, d); if (lane >= d) sc += u; }
+            warp_tot[lane] = sc - t;
         }
         __syncthreads();
-        int rank = s_running + warp_tot[wid] + incl - cnt;          /* kept storms before this thread's items */
-        if (cnt) {
-            for (int w = 0; w < SEL_WORDS; ++w) {
-                if (!bits[w]) continue;
-                for (int j = 0; j < SEL_ITEMS; ++j) {
-                    if (!((bits[w] >> (8 * j)) & 1ull)) continue;
-                    ++rank;                                          /* 1-based rank of this kept storm */
-                    if (rank <= want) {
-                        const int64_t i = i0 + w * SEL_ITEMS + j;
-                        const int row = nt0 + rank - 1;
-                        const int slot = A.att_slot[off + i];
-                        A.row_slot[(size_t)yr * A.n_tracks + row] = slot;
-                        A.tc_month[(size_t)yr * A.n_tracks + row] = (double)A.month[off + i];
-                        A.tc_basin[(size_t)yr * A.n_tracks + row] = A.basin[off + i];
-                        if (slot >= 0) atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot]);   /* < 0: another rank's storm */
-                        if (rank == want) s_istar = (int)i;
-                    }
-                }
+        unsigned int pref = s_running + warp_tot[wid] + incl - sum;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = base + (int64_t)tid * 4 + j;
+            if (i < nb) {
+                A.blk_pref[b0 + i] = pref;
+                if (want > 0u && pref < want && want <= pref + v[j]) s_bstar = (long long)i;      /* exactly one block qualifies */
+                pref += v[j];
             }
         }
         __syncthreads();
-        if (tid == blockDim.x - 1) s_running = rank;
+        if (tid == blockDim.x - 1) s_running = pref;
         __syncthreads();
-        if (s_istar >= 0) break;
     }
-    const int64_t i_star = s_istar;
-    const int64_t last = i_star >= 0 ? i_star : W - 1;      /* attempts consumed: 0..last */
-    /* pass 2: the over-shoot (last, W) only; the totals over [0, W) come from k_wave_stats */
-    unsigned long long w_counted = 0, w_integ = 0, w_steps = 0, w_rhs = 0, w_exh = 0;
-    for (int64_t i = last + 1 + tid; i < W; i += blockDim.x) {
-        const int code = A.code[off + i];
-        const int slot = A.att_slot[off + i];
-        if (code == 1 || code == 2) { ++w_counted; atomicAdd(&s_hist[A.basin[off + i] * 12 + A.month[off + i] - 1], 1u); }
-        if (code == 3) ++w_exh;
-        if (slot >= 0) { ++w_integ; w_steps += (unsigned long long)A.n_time[slot]; w_rhs += (unsigned long long)A.nfev[slot]; }
+    if (wid == 0) {
+        /* i* inside block b*: the (want - prefix)-th kept flag of its 256 bytes */
+        long long istar = -1;
+        if (s_bstar >= 0) {
+            const unsigned int need = want - A.blk_pref[b0 + s_bstar];
+            const uint8_t* kb = A.att_kept + off + s_bstar * 256;
+            unsigned int bits = 0u;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int64_t i = s_bstar * 256 + lane * 8 + j;
+                if (i < W && kb[lane * 8 + j]) bits |= 1u << j;
+            }
+            const unsigned int cnt = __popc(bits);
+            unsigned int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { unsigned int u = __shfl_up_sync(TCR_FULL, incl, d); if (lane >= d) incl += u; }
+            const unsigned int before = incl - cnt;
+            const bool mine = before < need && need <= incl;
+            int pos = -1;
+            if (mine) pos = lane * 8 + (int)__fns(bits, 0, (int)(need - before));
+            const unsigned int who = __ballot_sync(TCR_FULL, mine);
+            if (who) istar = s_bstar * 256 + __shfl_sync(TCR_FULL, pos, __ffs((int)who) - 1);
+        }
+        if (lane == 0) { A.istar[yr] = istar; A.total_kept[yr] = (int32_t)s_running; }
     }
-    if (w_counted) atomicAdd(&s_acc[0], w_counted);
-    if (w_exh) atomicAdd(&s_acc[5], w_exh);
-    if (w_integ) { atomicAdd(&s_acc[1], w_integ); atomicAdd(&s_acc[2], w_steps); atomicAdd(&s_acc[3], w_rhs); }
+}
+
+__global__ void __launch_bounds__(256) k_select_rows(const SelectArgs A)
+{
+    __shared__ unsigned int s_warp[8];
+    __shared__ unsigned long long s_acc[6];
+    __shared__ unsigned int s_hist[TCR_N_BASINS * 12];
+    if (A.pool_ctl[1]) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+    if (first >= A.wave_off[A.n_years]) return;
+    int yr = 0;
+    while (yr + 1 < A.n_years && first >= A.wave_off[yr + 1]) ++yr;          /* the whole block belongs to this year */
+    const int64_t off = A.wave_off[yr], W = A.consumed[yr];
+    const int64_t i_star = A.istar[yr];
+    if (i_star == -2) return;
+    const int64_t li = first - off + tid;
+    const int64_t last = i_star >= 0 ? i_star : W - 1;
+    if (first - off >= W) return;                                              /* beyond the processed range */
+    const bool over = first - off + 255 > last;                                /* block reaches into the over-shoot */
+    if (tid < 6) s_acc[tid] = 0ull;
+    if (over) for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) s_hist[i] = 0u;
+    const bool in = li < W;
+    const bool kept = in && li <= last && A.att_kept[first + tid] != 0;
+    const unsigned int kb = __ballot_sync(TCR_FULL, kept);
+    if (lane == 0) s_warp[wid] = __popc(kb);
     __syncthreads();
+    if (kept) {
+        unsigned int rank = A.blk_pref[blockIdx.x] + __popc(kb & ((1u << lane) - 1u)) + 1u;     /* 1-based, attempt order */
+        for (int w = 0; w < wid; ++w) rank += s_warp[w];
+        const int nt0 = A.nt[yr];
+        const int row = nt0 + (int)rank - 1;                   /* rank <= want because li <= i* (or i* was not reached) */
+        const int64_t idx = first + tid;
+        const int slot = A.att_slot[idx];
+        A.row_slot[(size_t)yr * A.n_tracks + row] = slot;
+        A.tc_month[(size_t)yr * A.n_tracks + row] = (double)A.month[idx];
+        A.tc_basin[(size_t)yr * A.n_tracks + row] = A.basin[idx];
+        if (slot >= 0) atomicAdd(&s_acc[4], (unsigned long long)A.n_time[slot]);       /* < 0: another rank's storm */
+    }
+    if (in && li > last) {                                     /* the over-shoot (last, W): what the sequential loop never ran */
+        const int64_t idx = first + tid;
+        const int code = A.code[idx], slot = A.att_slot[idx];
+        if (code == 1 || code == 2) { atomicAdd(&s_acc[0], 1ull); atomicAdd(&s_hist[A.basin[idx] * 12 + A.month[idx] - 1], 1u); }
+        if (code == 3) atomicAdd(&s_acc[5], 1ull);
+        if (slot >= 0) {
+            atomicAdd(&s_acc[1], 1ull); atomicAdd(&s_acc[2], (unsigned long long)A.n_time[slot]);
+            atomicAdd(&s_acc[3], (unsigned long long)A.nfev[slot]);
+        }
+    }
+    __syncthreads();
+    if (tid < 6 && s_acc[tid]) atomicAdd(&A.sel_acc[yr * 6 + tid], s_acc[tid]);
+    if (over) for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x) if (s_hist[i]) atomicAdd(&A.sel_hist[yr * TCR_N_BASINS * 12 + i], s_hist[i]);
+}
+
+__global__ void __launch_bounds__(128) k_select_finish(const SelectArgs A)
+{
+    if (A.pool_ctl[1]) return;
+    const int yr = blockIdx.x, tid = threadIdx.x;
+    const int64_t i_star = A.istar[yr];
+    if (i_star == -2) { if (tid == 0) A.used[yr] = 0; return; }
     const int NG = TCR_N_BASINS * 12 + 2;
     for (int i = tid; i < TCR_N_BASINS * 12; i += blockDim.x)
-        A.n_seeds[(size_t)yr * TCR_N_BASINS * 12 + i] += (double)(A.wave_glob[yr * NG + i] - s_hist[i]);
+        A.n_seeds[(size_t)yr * TCR_N_BASINS * 12 + i] += (double)(A.wave_glob[yr * NG + i] - A.sel_hist[yr * TCR_N_BASINS * 12 + i]);
     if (tid == 0) {
+        const int64_t W = A.consumed[yr];
+        const int64_t last = i_star >= 0 ? i_star : W - 1;
+        const unsigned long long* acc = A.sel_acc + yr * 6;
         tcr_year_stats& s = A.stats[yr];
         const unsigned long long* tot = A.wave_loc + yr * 3;
-        const int got = min(want, s_running);
+        const int nt0 = A.nt[yr];
+        const int want = A.n_tracks - nt0;
+        const int got = min(want, A.total_kept[yr]);
         s.attempts = A.k0[yr] + last + 1;
-        s.counted_seeds += (int64_t)((unsigned long long)A.wave_glob[yr * NG + NG - 2] - s_acc[0]);
-        s.redraw_exhausted += (int64_t)((unsigned long long)A.wave_glob[yr * NG + NG - 1] - s_acc[5]);
-        s.integrated += (int64_t)(tot[0] - s_acc[1]);
-        s.storm_steps += (int64_t)(tot[1] - s_acc[2]);
-        s.rhs_evals += (int64_t)(tot[2] - s_acc[3]);
-        s.kept_steps += (int64_t)s_acc[4];
-        s.wasted_integrated += (int64_t)s_acc[1];
-        s.wasted_steps += (int64_t)s_acc[2];
-        s.wasted_rhs_evals += (int64_t)s_acc[3];
+        s.counted_seeds += (int64_t)((unsigned long long)A.wave_glob[yr * NG + NG - 2] - acc[0]);
+        s.redraw_exhausted += (int64_t)((unsigned long long)A.wave_glob[yr * NG + NG - 1] - acc[5]);
+        s.integrated += (int64_t)(tot[0] - acc[1]);
+        s.storm_steps += (int64_t)(tot[1] - acc[2]);
+        s.rhs_evals += (int64_t)(tot[2] - acc[3]);
+        s.kept_steps += (int64_t)acc[4];
+        s.wasted_integrated += (int64_t)acc[1];
+        s.wasted_steps += (int64_t)acc[2];
+        s.wasted_rhs_evals += (int64_t)acc[3];
         s.n_kept = nt0 + got;
         s.n_waves += 1;
         A.nt[yr] = nt0 + got;

@@ -84,6 +84,7 @@ struct Workspace {
     int64_t att_cap = 0, slot_cap = 0;
     int64_t full_cap = 0;          /* slots that also own track / env / vmax rows (tcr_integrate)           */
     int64_t pool_rows = 0;         /* rows of the track pool (tcr_run_years): lanes in flight + candidates   */
+    bool mem_limited = false;      /* the capacities were set by the memory budget, not by the job            */
     int ns = 0;
     DevBuf code, basin, month, att_slot, a_lon, a_lat, a_v0, a_m0;   /* per attempt */
     DevBuf blk_count, blk_off;                                       /* per 256-attempt seed block */
@@ -103,7 +104,7 @@ struct Workspace {
                          &n_time, &status, &nfev, &flags, &cand, &track_row, &coef, &ftab, &track, &env, &vmax, &counters, &year_i64,
                          &year_i32, &row_slot, &stats, &out};
         for (DevBuf* b : all) b->release();
-        att_cap = slot_cap = full_cap = pool_rows = 0;
+        att_cap = slot_cap = full_cap = pool_rows = 0; mem_limited = false;
     }
 };
 
@@ -258,7 +259,7 @@ int tcr_create(int device, const tcr_params* p, tcr_handle** out)
     h->device = device;
     if (const char* iv = getenv("TCR_INTEG_VARIANT")) {                 /* A/B runs and tests of a non-default integrate variant */
         const int v = atoi(iv);
-        if (v >= 1 && v <= 31) h->integ_variant = v - 1;
+        if (v >= 1 && v <= 32) h->integ_variant = v - 1;
     }
     h->num_sms = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
@@ -324,7 +325,7 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 {
     if (!h) return set_err("null handle");
     if (integ_variant > 0) {
-        if (integ_variant > 31) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
+        if (integ_variant > 32) return set_err("integrate variant must be 1 (256 thr x 1 CTA/SM), 2 (128 x 3), 3 (128 x 4) or 4 (160 x 2)");
         h->integ_variant = integ_variant - 1;
     }
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
@@ -644,7 +645,8 @@ static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_yea
     }
     if (w.counters.ensure(64)) return -1;
     const size_t ny = (size_t)std::max(n_years, 1);
-    if (w.wave_tot.ensure(ny * (3 * 8 + (TCR_N_BASINS * 12 + 2) * 4) + 16)) return -1;
+    /* k_wave_stats totals + histogram, then the selection scratch: i*, kept totals, over-shoot accumulators + histogram */
+    if (w.wave_tot.ensure(ny * (3 * 8 + (TCR_N_BASINS * 12 + 2) * 4) + 16 + ny * (8 + 8 + 6 * 8 + TCR_N_BASINS * 12 * 4) + 64)) return -1;
     if (w.year_i64.ensure((4 * ny + 1) * 8) || w.year_i32.ensure(3 * ny * 4) || w.stats.ensure(ny * sizeof(tcr_year_stats))) return -1;
     return 0;
 }
@@ -726,6 +728,7 @@ static int launch_integrate(tcr_handle* h, IntegArgs& a, int64_t n_upper)
     case 28: launch_integrate_variant<128, 3, 2, 63 + 256>(h, a, n_upper); break; /* three lock-step groups of 4 warps per SM */
     case 29: launch_integrate_variant<96, 4, 2, 63 + 256>(h, a, n_upper); break;  /* four groups of 3 warps */
     case 30: launch_integrate_variant<64, 6, 2, 63 + 256>(h, a, n_upper); break;  /* six groups of 2 warps */
+    case 31: launch_integrate_variant<224, 2, 2, 63 + 256>(h, a, n_upper); break; /* 14 warps/SM */
     default: return set_err("unknown integrate variant %d", h->integ_variant);
     }
     CKK(h);
@@ -931,7 +934,10 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         if (h->max_wave > 0) want_att = std::min(want_att, h->max_wave);
         want_att = std::max<int64_t>(want_att, 4096);
         int64_t want_slot = std::min(want_att, std::max<int64_t>(4096, (int64_t)((double)want_att * pass_est) + 1024));
-        const bool fits = w0.ns == ns && w0.att_cap >= want_att && w0.slot_cap >= want_slot &&
+        /* a workspace that was sized by the memory budget is as large as it gets: asking the allocator again would only
+         * re-derive the same capacity from a slightly different free-memory reading, and a one-percent growth means
+         * freeing and re-allocating tens of gigabytes (measured: 150-350 ms per call, every call, at configs[3]'s shape) */
+        const bool fits = w0.ns == ns && (w0.att_cap >= want_att || w0.mem_limited) && (w0.slot_cap >= want_slot || w0.mem_limited) &&
                           (on_device || w0.out.bytes >= out_bytes + 256);
         if (!fits) {
             size_t free_b = 0, total_b = 0;
@@ -942,6 +948,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
             const int64_t cap_mem = (int64_t)((double)budget / ((double)kAttemptBytes + pass_est * (double)slot_bytes(ns)));
             /* 25 % headroom so that the next call's slightly different estimate still fits */
             int64_t att_cap = std::max<int64_t>(4096, std::min(cap_mem, want_att + want_att / 4));
+            w0.mem_limited = hinted && cap_mem < want_att + want_att / 4;     /* sized from measured survival rates: final */
             int64_t slot_cap = std::min(att_cap, std::max<int64_t>(4096, (int64_t)((double)att_cap * pass_est) + 1024));
             w0.env.release(); w0.vmax.release();                       /* only tcr_integrate keeps per-slot env / vmax rows */
             if (w0.full_cap > 0) { w0.track.release(); w0.full_cap = 0; w0.pool_rows = 0; }
@@ -1067,8 +1074,12 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
             want[y] = wy;
             want_total += wy;
         }
-        const double scale = want_total > (double)cap ? (double)cap / want_total : 1.0;
-        for (int y = 0; y < n_years; ++y) W[y] = want[y] > 0.0 ? std::max<int64_t>(64, (int64_t)(want[y] * scale)) : 0;
+        /* every year's range is a whole number of 256-attempt blocks (the selection kernels work per block): the rounding
+         * is paid for out of the capacity */
+        const double cap_eff = (double)std::max<int64_t>(256, cap - 256 * (int64_t)n_years);
+        const double scale = want_total > cap_eff ? cap_eff / want_total : 1.0;
+        for (int y = 0; y < n_years; ++y)
+            W[y] = want[y] > 0.0 ? ((std::max<int64_t>(64, (int64_t)(want[y] * scale)) + 255) & ~(int64_t)255) : 0;
         if (world > 1) {
             /* the ranks must issue identical attempt ranges: take the smallest proposal of each year (the proposals only
              * differ when the handles were tuned differently or remember different survival rates) */
@@ -1162,7 +1173,9 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         wa.wave_loc = w.wave_tot.as<unsigned long long>();
         wa.wave_glob = reinterpret_cast<unsigned int*>(wa.wave_loc + 3 * (size_t)n_years);       /* [n_years][86] + overflow word */
         wa.k0 = d_k0; wa.rank = srank; wa.world = world;
-        CK(cudaMemsetAsync(w.wave_tot.p, 0, (size_t)n_years * (3 * 8 + NG * 4) + 16, s));
+        const size_t wave_tot_bytes = (size_t)n_years * (3 * 8 + NG * 4) + 16;
+        const size_t sel_bytes = (size_t)n_years * (8 + 8 + 6 * 8 + TCR_N_BASINS * 12 * 4);
+        CK(cudaMemsetAsync(w.wave_tot.p, 0, ((wave_tot_bytes + 15) & ~(size_t)15) + sel_bytes, s));
         if (world > 1) {
             /* a year whose range one rank had to cut (slot capacity) is cut for everybody */
             if (allreduce(d_consumed, n_years, 2, 1)) return -1;
@@ -1170,7 +1183,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
 
         SelectArgs se;
         memset(&se, 0, sizeof se);
-        se.n_tracks = n_tracks; se.wave_off = d_wave_off; se.k0 = d_k0; se.consumed = d_consumed;
+        se.n_years = n_years; se.n_tracks = n_tracks; se.wave_off = d_wave_off; se.k0 = d_k0; se.consumed = d_consumed;
         se.code = sa.code; se.basin = sa.basin; se.month = sa.month; se.att_slot = as.att_slot;
         se.n_time = a.n_time; se.nfev = a.nfev;
         se.att_kept = wa.att_kept; se.wave_glob = wa.wave_glob; se.wave_loc = wa.wave_loc;
@@ -1178,6 +1191,15 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         se.tc_month = d_month; se.tc_basin = d_basin; se.n_seeds = d_seeds;
         se.stats = w.stats.as<tcr_year_stats>();
         se.pool_ctl = d_pool;
+        {
+            char* base = w.wave_tot.as<char>() + ((wave_tot_bytes + 15) & ~(size_t)15);
+            se.istar = reinterpret_cast<int64_t*>(base);
+            se.sel_acc = reinterpret_cast<unsigned long long*>(base + (size_t)n_years * 8);
+            se.total_kept = reinterpret_cast<int32_t*>(base + (size_t)n_years * (8 + 6 * 8));
+            se.sel_hist = reinterpret_cast<unsigned int*>(base + (size_t)n_years * (8 + 6 * 8 + 8));
+            se.blk_kept = w.blk_count.as<unsigned int>();          /* the seeding scan is done with both by now */
+            se.blk_pref = w.blk_off.as<unsigned int>();
+        }
         {
             LaunchTimer lt_(h, TCR_K_SELECT);
             k_wave_stats<<<seed_blocks, 256, 0, s>>>(wa);
@@ -1189,10 +1211,13 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
                 if (allreduce(wa.att_kept, (total + 3) / 4 * 4, 0, 0) || allreduce(wa.wave_glob, (int64_t)n_years * NG + 1, 1, 0)) return -1;
                 CK(cudaMemcpyAsync(d_pool + 1, d_ovf, 4, cudaMemcpyDeviceToDevice, s));
             }
-            k_select<<<n_years, 1024, 0, s>>>(se);
+            k_count_kept<<<seed_blocks, 256, 0, s>>>(se.att_kept, total, se.blk_kept);
+            k_select_scan<<<n_years, 1024, 0, s>>>(se);
+            k_select_rows<<<seed_blocks, 256, 0, s>>>(se);
+            k_select_finish<<<n_years, 128, 0, s>>>(se);
         }
         CKK(h);
-        h->launches += 1;
+        h->launches += 4;
 
         GatherArgs ga;
         memset(&ga, 0, sizeof ga);
