@@ -1,7 +1,9 @@
 """Channel layout of the HBM-resident monthly environment tables.
 
-One table per (year, month): float32 ``[nlat][nlon][N_CH]`` (channel-interleaved,
-80 B per grid point) on the basin-cropped, ascending ERA5-shaped grid.
+The caller uploads one set of N_CH float32 planes ``[N_CH][nlat][nlon]`` per (year, month) on the basin-cropped,
+ascending ERA5-shaped grid; on the device they become CELL RECORDS ``rec[ym][iy][ix][20]`` of float4 -- for each grid
+cell the four corner values of every channel (+1 pad), 320 B, one aligned read per bilinear look-up of all channels
+(k_build_month).
 
 Channel order follows the reference's own vector orders:
   * means  ``[ua250, va250, ua850, va850]``        (track/env_wind.py:22-26)
