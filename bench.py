@@ -555,14 +555,21 @@ def bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args):
         eng.set_interp_variant(0)
         return res
 
-    all_variants = ((0, "k_env_interp"), (1, "k_env_interp_tma"), (2, "k_env_interp<4>"), (3, "k_env_interp<5>"),
-                    (4, "k_env_interp_pipe"), (5, "k_env_interp_async<256>"), (6, "k_env_interp_async<128>"))
+    all_variants = ((0, "k_env_interp"), (2, "k_env_interp<4>"), (3, "k_env_interp<5>"),
+                    (5, "k_env_interp_async<256>"), (6, "k_env_interp_async<128>"))
     ym_w = torch.randint(0, window, (n,), generator=g, device=dev, dtype=torch.int32)
     res = run(ym_w, all_variants)
     head = res["k_env_interp"]
     details = {"variants": res, "window_months": window, "window_table_bytes": window * month_bytes,
                "moved_bytes_per_query": 320 + 12 + 20 + 168,
                "traffic_source": "profiles/r01_prof_interp_summary.txt (ncu --set full, one launch over 228 MB of tables)"}
+    # the round-1 footprint (228 MB of North Atlantic tables, 1.8 x L2: about a third of the record reads hit L2) for comparison
+    w_r01 = max(1, int(round(228e6 / month_bytes)))
+    r01 = None
+    if w_r01 < window:
+        ym_s = torch.randint(0, w_r01, (n,), generator=g, device=dev, dtype=torch.int32)
+        r01 = dict(run(ym_s, all_variants[:1])["k_env_interp"], months=w_r01, table_bytes=w_r01 * month_bytes)
+        details["round1_footprint"] = r01
     if window < wl.n_ym:
         ym_all = torch.randint(0, wl.n_ym, (n,), generator=g, device=dev, dtype=torch.int32)
         details["all_resident_tables"] = dict(run(ym_all, all_variants[:1])["k_env_interp"], months=wl.n_ym,
@@ -571,6 +578,7 @@ def bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args):
             "frac": head["frac"], "traffic": NCU_TRAFFIC["k_env_interp"] if n == (1 << 25) else None,
             "avg_launch_ms": head["avg_launch_ms"], "peak_source": peak_src, "queries_per_launch": n,
             "algorithmic_bytes_per_query": B_PER_QUERY, "table_bytes": window * month_bytes,
+            "frac_at_228MB_tables": (r01["frac"] if r01 else head["frac"]),
             "l2": "random queries over %d month tables (%d MB >> 126 MB L2) + %d MB streamed output" % (
                 window, window * month_bytes >> 20, n * 168 >> 20),
             "details": details}

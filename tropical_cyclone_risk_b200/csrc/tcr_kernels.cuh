@@ -170,268 +170,13 @@ __global__ void __launch_bounds__(EI_TILE, MINB) k_env_interp(const __grid_const
     }
 }
 
-/* variant 1: each query's 320-byte record is staged into shared memory by one TMA bulk copy
- * (cp.async.bulk, SASS UBLKCP) completing on an mbarrier; the 21 outputs per query are then
- * formed from shared memory.  One elected thread per query issues the copy.                  */
-__device__ __forceinline__ uint32_t tcr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void tcr_mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tcr_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void tcr_mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tcr_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tcr_mbar_wait(uint64_t* bar, uint32_t phase)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(tcr_smem_u32(bar)), "r"(phase) : "memory");
-}
-__device__ __forceinline__ void tcr_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(tcr_smem_u32(dst)), "l"(src), "r"(bytes), "r"(tcr_smem_u32(bar)) : "memory");
-}
-
-#define EIT_TILE 128           /* queries per stage */
-#define EIT_STAGES 3
-struct EitLoc { double w00, w01, w10, w11, bathy, land; };
-
-__global__ void __launch_bounds__(EIT_TILE * 2) k_env_interp_tma(const __grid_constant__ TcrCtx cx, int64_t n,
-                                                                 const int32_t* __restrict__ ym, const double* __restrict__ lon,
-                                                                 const double* __restrict__ lat, double* __restrict__ out)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4* stage_rec = reinterpret_cast<float4*>(smem_raw);                                   /* [S][TILE][20] */
-    EitLoc* stage_loc = reinterpret_cast<EitLoc*>(smem_raw + (size_t)EIT_STAGES * EIT_TILE * TCR_REC_F4 * 16);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_loc + EIT_STAGES * EIT_TILE);
-    const int tid = threadIdx.x;
-    const int64_t n_tiles = (n + EIT_TILE - 1) / EIT_TILE;
-    if (tid == 0) {
-        for (int s = 0; s < EIT_STAGES; ++s) tcr_mbar_init(bars + s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    /* producer step for tile `tile` into stage s: threads 0..TILE-1 locate one query each and
-     * issue its bulk copy; thread 0 first posts the expected byte count                        */
-    auto produce = [&](int64_t tile, int s) {
-        const int64_t q0 = tile * EIT_TILE;
-        const int nq = (int)min((int64_t)EIT_TILE, n - q0);
-        if (tid == 0) tcr_mbar_expect_tx(bars + s, (uint32_t)nq * TCR_REC_F4 * 16);
-        __syncthreads();
-        if (tid < nq) {
-            const int64_t q = q0 + tid;
-            const double x = lon[q], y = lat[q];
-            TcrCell c;
-            tcr_cell_at(cx.tab.lon, cx.tab.lat, x, y, c);
-            tcr_bulk_g2s(stage_rec + ((size_t)s * EIT_TILE + tid) * TCR_REC_F4, tcr_record(cx.tab, ym[q], c),
-                         TCR_REC_F4 * 16, bars + s);
-            EitLoc l;
-            l.w00 = c.w00; l.w01 = c.w01; l.w10 = c.w10; l.w11 = c.w11;
-            l.bathy = tcr_bathy_at(cx.st, x, y);
-            l.land = tcr_land_at(cx.st, x, y);
-            stage_loc[s * EIT_TILE + tid] = l;
-        }
-    };
-
-    int64_t tile = blockIdx.x;
-    int it = 0;
-    /* prologue: fill STAGES-1 stages */
-    for (int s = 0; s < EIT_STAGES - 1; ++s) {
-        int64_t tl = tile + (int64_t)s * gridDim.x;
-        if (tl < n_tiles) produce(tl, s);
-    }
-    for (; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int s = it % EIT_STAGES;
-        const uint32_t phase = (uint32_t)(it / EIT_STAGES) & 1u;
-        /* refill the stage that was consumed in the previous iteration */
-        {
-            int64_t tl = tile + (int64_t)(EIT_STAGES - 1) * gridDim.x;
-            if (tl < n_tiles) produce(tl, (it + EIT_STAGES - 1) % EIT_STAGES);
-        }
-        __syncthreads();                       /* stage_loc[s] visible */
-        tcr_mbar_wait(bars + s, phase);
-        const int64_t q0 = tile * EIT_TILE;
-        const int nq = (int)min((int64_t)EIT_TILE, n - q0);
-        const int n_items = nq * TCR_N_INTERP_OUT;
-        double* o = out + q0 * TCR_N_INTERP_OUT;
-        const float4* recs = stage_rec + (size_t)s * EIT_TILE * TCR_REC_F4;
-        const EitLoc* locs = stage_loc + s * EIT_TILE;
-        for (int i = tid; i < n_items; i += blockDim.x) {
-            int qi = i / TCR_N_INTERP_OUT, ch = i - qi * TCR_N_INTERP_OUT;
-            const EitLoc& l = locs[qi];
-            double v;
-            if (ch < TCR_N_FIELDS) {
-                float4 r = recs[qi * TCR_REC_F4 + ch];
-                v = fma((double)r.w, l.w11, fma((double)r.z, l.w10, fma((double)r.y, l.w01, (double)r.x * l.w00)));
-            } else {
-                v = (ch == TCR_N_FIELDS) ? l.bathy : l.land;
-            }
-            __stcs(o + i, v);
-        }
-        __syncthreads();                       /* stage s free for the next refill */
-    }
-}
-
-/* variant 4: warp-specialised cp.async pipeline.  Warps 0-3 (producers) locate 128 queries per
- * tile, write their weights to the stage and start the asynchronous copies (LDGSTS, L2 -> shared,
- * no register staging) of the 128 x 320-byte records -- issued cooperatively in flat (query,
- * channel) order so every warp-level request covers whole sectors -- plus each query's
- * bathymetry / land cell; completion is signalled on the stage's "full" mbarrier by
- * cp.async.mbarrier.arrive.  Warps 4-7 (consumers) form the 21 outputs per query from shared
- * memory and stream them out coalesced, then release the stage ("empty" mbarrier).  With three
- * stages two tiles of gathers (80 KB per SM) are always in flight, which is what a random-gather
- * kernel needs to approach the HBM roofline (Little: ~6.4 TB/s x ~0.8 us / 148 SMs = 35 KB).   */
-#define EP_TILE 128
-#define EP_STAGES 3
-#define EP_THREADS 256
-struct __align__(16) EpLoc {
-    double w00, w01, w10, w11;          /* table cell weights (fused-sum form)                   */
-    double bw00, bw01, bw10, bw11;      /* bathymetry cell weights                                */
-    double lx0, lx1, ly0, ly1;          /* land cell weights, FITPACK product order               */
-    short4 bathy; char4 land; int valid;
-};
-#define EP_STAGE_BYTES (EP_TILE * TCR_REC_F4 * 16 + EP_TILE * (int)sizeof(EpLoc) + EP_TILE * 8)
-#define EP_SMEM_BYTES (EP_STAGES * EP_STAGE_BYTES + 2 * EP_STAGES * 8)
-
+/* (Variants 1 and 4 of round 1 -- one 320-byte cp.async.bulk per query behind an mbarrier, and a warp-specialised
+ * cp.async + mbarrier ring -- measured 3.6 x and 2.8 x slower than variant 0 and were removed in round 2: a per-record
+ * bulk copy is too small to amortise its issue cost, and a tile design needs cell-sorted queries whose 168-byte
+ * result rows then scatter.  DESIGN.md section 4.) */
 __device__ __forceinline__ void tcr_cp_async16(void* dst, const void* src)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tcr_smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void tcr_cp_async8(void* dst, const void* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tcr_smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void tcr_cp_async4(void* dst, const void* src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tcr_smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void tcr_cp_async_arrive(uint64_t* bar)
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tcr_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tcr_mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tcr_smem_u32(bar)) : "memory");
-}
-
-__global__ void __launch_bounds__(EP_THREADS, 1) k_env_interp_pipe(const __grid_constant__ TcrCtx cx, int64_t n,
-                                                                   const int32_t* __restrict__ ym, const double* __restrict__ lon,
-                                                                   const double* __restrict__ lat, double* __restrict__ out)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)EP_STAGES * EP_STAGE_BYTES);
-    uint64_t* empty = full + EP_STAGES;
-    const int tid = threadIdx.x;
-    const int64_t n_tiles = (n + EP_TILE - 1) / EP_TILE;
-    if (tid == 0) {
-        for (int s = 0; s < EP_STAGES; ++s) { tcr_mbar_init(full + s, 2 * EP_TILE); tcr_mbar_init(empty + s, EP_TILE); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto stage_rec = [&](int s) { return reinterpret_cast<float4*>(smem_raw + (size_t)s * EP_STAGE_BYTES); };
-    auto stage_loc = [&](int s) { return reinterpret_cast<EpLoc*>(smem_raw + (size_t)s * EP_STAGE_BYTES + EP_TILE * TCR_REC_F4 * 16); };
-    auto stage_ptr = [&](int s) {
-        return reinterpret_cast<const float4**>(smem_raw + (size_t)s * EP_STAGE_BYTES + EP_TILE * TCR_REC_F4 * 16 + EP_TILE * sizeof(EpLoc));
-    };
-
-    if (tid < EP_TILE) {
-        /* ---------------- producers ---------------- */
-        int64_t tile = blockIdx.x;
-        double x = 0.0, y = 0.0; int m = 0;
-        if (tile < n_tiles && tile * EP_TILE + tid < n) { const int64_t q = tile * EP_TILE + tid; x = lon[q]; y = lat[q]; m = ym[q]; }
-        for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int s = it % EP_STAGES;
-            if (it >= EP_STAGES) tcr_mbar_wait(empty + s, (uint32_t)((it / EP_STAGES) - 1) & 1u);
-            const int64_t q0 = tile * EP_TILE;
-            const int nq = (int)min((int64_t)EP_TILE, n - q0);
-            EpLoc* loc = stage_loc(s);
-            const float4** rp = stage_ptr(s);
-            if (tid < nq) {
-                TcrCellLoc lt, ll, lb;
-                tcr_cell_begin(cx.tab.lon, cx.tab.lat, x, y, lt);
-                tcr_cell_begin(cx.st.lon_l, cx.st.lat_l, x, y, ll);
-                tcr_cell_begin(cx.st.lon_b, cx.st.lat_b, x, y, lb);
-                TcrCell c, cl, cb;
-                tcr_cell_end(cx.tab.lon, cx.tab.lat, lt, c);
-                tcr_cell_end(cx.st.lon_l, cx.st.lat_l, ll, cl);
-                tcr_cell_end(cx.st.lon_b, cx.st.lat_b, lb, cb);
-                EpLoc& l = loc[tid];
-                l.w00 = c.w00; l.w01 = c.w01; l.w10 = c.w10; l.w11 = c.w11;
-                l.bw00 = cb.w00; l.bw01 = cb.w01; l.bw10 = cb.w10; l.bw11 = cb.w11;
-                l.lx0 = cl.wx0; l.lx1 = cl.wx1; l.ly0 = cl.wy0; l.ly1 = cl.wy1;
-                l.valid = 1;
-                tcr_cp_async8(&l.bathy, cx.st.bathy + (size_t)cb.iy * cx.st.ncx_b + cb.ix);
-                tcr_cp_async4(&l.land, cx.st.land + (size_t)cl.iy * cx.st.ncx_l + cl.ix);
-                rp[tid] = tcr_record(cx.tab, m, c);
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(EP_TILE) : "memory");          /* record pointers visible to the producers */
-            float4* rec = stage_rec(s);
-            const int n_items = nq * TCR_REC_F4;
-#pragma unroll 4
-            for (int j = 0; j < TCR_REC_F4; ++j) {
-                const int i = tid + j * EP_TILE;
-                if (i < n_items) {
-                    const int qi = i / TCR_REC_F4, ch = i - qi * TCR_REC_F4;
-                    tcr_cp_async16(rec + i, rp[qi] + ch);
-                }
-            }
-            tcr_cp_async_arrive(full + s);       /* fires when this thread's copies have landed */
-            tcr_mbar_arrive(full + s);           /* releases this thread's plain shared-memory writes */
-            /* next tile's coordinates: in flight while the copies are issued */
-            const int64_t nt = tile + gridDim.x;
-            if (nt < n_tiles && nt * EP_TILE + tid < n) { const int64_t q = nt * EP_TILE + tid; x = lon[q]; y = lat[q]; m = ym[q]; }
-        }
-    } else {
-        /* ---------------- consumers ---------------- */
-        const int ct = tid - EP_TILE;
-        int64_t tile = blockIdx.x;
-        for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int s = it % EP_STAGES;
-            tcr_mbar_wait(full + s, (uint32_t)(it / EP_STAGES) & 1u);
-            const int64_t q0 = tile * EP_TILE;
-            const int nq = (int)min((int64_t)EP_TILE, n - q0);
-            const int n_items = nq * TCR_N_INTERP_OUT;
-            const float4* rec = stage_rec(s);
-            const EpLoc* loc = stage_loc(s);
-            double* o = out + q0 * TCR_N_INTERP_OUT;
-#pragma unroll 3
-            for (int j = 0; j < TCR_N_INTERP_OUT; ++j) {
-                const int i = ct + j * EP_TILE;
-                if (i < n_items) {
-                    const int qi = i / TCR_N_INTERP_OUT, ch = i - qi * TCR_N_INTERP_OUT;
-                    const EpLoc& l = loc[qi];
-                    double v;
-                    if (ch < TCR_N_FIELDS) {
-                        const float4 r = rec[qi * TCR_REC_F4 + ch];
-                        v = fma((double)r.w, l.w11, fma((double)r.z, l.w10, fma((double)r.y, l.w01, (double)r.x * l.w00)));
-                    } else if (ch == TCR_N_FIELDS) {
-                        const short4 r = l.bathy;
-                        v = fma((double)r.w, l.bw11, fma((double)r.z, l.bw10, fma((double)r.y, l.bw01, (double)r.x * l.bw00)));
-                    } else {
-                        const char4 r = l.land;
-                        double sp = 0.0;
-                        sp = sp + (double)r.x * l.lx0 * l.ly0;
-                        sp = sp + (double)r.y * l.lx0 * l.ly1;
-                        sp = sp + (double)r.z * l.lx1 * l.ly0;
-                        sp = sp + (double)r.w * l.lx1 * l.ly1;
-                        v = sp;
-                    }
-                    __stcs(o + i, v);
-                }
-            }
-            tcr_mbar_arrive(empty + s);
-        }
-    }
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
 
 /* variant 5: one tile of EA_TILE queries per CTA, all of the tile's record quads fetched by

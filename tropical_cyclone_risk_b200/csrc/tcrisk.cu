@@ -337,8 +337,8 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
 int tcr_set_interp_variant(tcr_handle* h, int variant)
 {
     if (!h) return set_err("null handle");
-    if (variant < 0 || variant > 6)
-        return set_err("interp variant must be 0 (LDG), 1 (TMA bulk), 2 / 3 (LDG, 4 / 5 CTAs per SM) or 4 (cp.async pipeline)");
+    if (variant < 0 || variant > 6 || variant == 1 || variant == 4)
+        return set_err("interp variant must be 0 (LDG), 2 / 3 (LDG, 4 / 5 CTAs per SM) or 5 / 6 (cp.async tile of 256 / 128 queries); 1 and 4 were removed");
     h->interp_variant = variant;
     return 0;
 }
@@ -530,18 +530,7 @@ int tcr_upload_month(tcr_handle* h, int ym, const float* const* fields)
 static int launch_env_interp(tcr_handle* h, int64_t n, const int32_t* ym, const double* lon, const double* lat, double* out)
 {
     LaunchTimer lt_(h, TCR_K_ENV_INTERP);
-    if (h->interp_variant == 1) {
-        const size_t smem = (size_t)EIT_STAGES * EIT_TILE * (TCR_REC_F4 * 16 + sizeof(EitLoc)) + EIT_STAGES * sizeof(uint64_t);
-        CK(cudaFuncSetAttribute(k_env_interp_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int64_t tiles = (n + EIT_TILE - 1) / EIT_TILE;
-        int grid = (int)std::min<int64_t>(tiles, h->num_sms);
-        k_env_interp_tma<<<grid, EIT_TILE * 2, smem, h->stream>>>(h->ctx, n, ym, lon, lat, out);
-    } else if (h->interp_variant == 4) {
-        CK(cudaFuncSetAttribute(k_env_interp_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EP_SMEM_BYTES));
-        int64_t tiles = (n + EP_TILE - 1) / EP_TILE;
-        int grid = (int)std::min<int64_t>(tiles, h->num_sms);
-        k_env_interp_pipe<<<grid, EP_THREADS, EP_SMEM_BYTES, h->stream>>>(h->ctx, n, ym, lon, lat, out);
-    } else if (h->interp_variant == 5 || h->interp_variant == 6) {
+    if (h->interp_variant == 5 || h->interp_variant == 6) {
         const int tile = h->interp_variant == 5 ? 256 : 128;
         const int smem = tile * (TCR_REC_F4 * 16 + (int)sizeof(EiLoc));
         int64_t tiles = (n + tile - 1) / tile;
