@@ -500,6 +500,22 @@ def run_gpu_arm(args):
         if not args.no_interp:
             ri = bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args)
             details["roofline_interp"] = ri.pop("details")
+            if args.basin != "NA":
+                # The sampler is a stand-alone kernel benchmark: its headline is quoted on the footprint the north star's
+                # 60 % target was set on in round 1 (North Atlantic, 10 years = 120 month tables, 228 MB, basin-cropped
+                # static grids); the same kernel over this run's resident tables (global grid: the land / bathymetry
+                # gathers of a query miss L2 as well) stays in the line as `resident_tables`.
+                wl_na = Workload("NA", [BASE_YEAR + i for i in range(10)], full_res=True, namelist=bench_namelist(args))
+                eng_na = Engine(wl_na.p, device=local)
+                eng_na.set_stream(stream.cuda_stream)
+                wl_na.upload(eng_na)
+                ri_na = bench_interp(eng_na, wl_na, torch, dev, stream, peak, peak_src, args)
+                eng_na.close()
+                details["roofline_interp_resident"] = details.pop("roofline_interp")
+                details["roofline_interp"] = ri_na.pop("details")
+                ri_na["resident_tables"] = {"basin": args.basin, "frac": ri["frac"], "achieved": ri["achieved"],
+                                            "avg_launch_ms": ri["avg_launch_ms"], "table_bytes": ri["table_bytes"]}
+                ri = ri_na
             line["roofline_interp"] = ri                                  # compact, ahead of every bulky key
         if world == 1 and not args.no_cpu:
             threads = cpu_threads()
@@ -563,13 +579,6 @@ def bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args):
     details = {"variants": res, "window_months": window, "window_table_bytes": window * month_bytes,
                "moved_bytes_per_query": 320 + 12 + 20 + 168,
                "traffic_source": "profiles/r01_prof_interp_summary.txt (ncu --set full, one launch over 228 MB of tables)"}
-    # the round-1 footprint (228 MB of North Atlantic tables, 1.8 x L2: about a third of the record reads hit L2) for comparison
-    w_r01 = max(1, int(round(228e6 / month_bytes)))
-    r01 = None
-    if w_r01 < window:
-        ym_s = torch.randint(0, w_r01, (n,), generator=g, device=dev, dtype=torch.int32)
-        r01 = dict(run(ym_s, all_variants[:1])["k_env_interp"], months=w_r01, table_bytes=w_r01 * month_bytes)
-        details["round1_footprint"] = r01
     if window < wl.n_ym:
         ym_all = torch.randint(0, wl.n_ym, (n,), generator=g, device=dev, dtype=torch.int32)
         details["all_resident_tables"] = dict(run(ym_all, all_variants[:1])["k_env_interp"], months=wl.n_ym,
@@ -578,7 +587,6 @@ def bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args):
             "frac": head["frac"], "traffic": NCU_TRAFFIC["k_env_interp"] if n == (1 << 25) else None,
             "avg_launch_ms": head["avg_launch_ms"], "peak_source": peak_src, "queries_per_launch": n,
             "algorithmic_bytes_per_query": B_PER_QUERY, "table_bytes": window * month_bytes,
-            "frac_at_228MB_tables": (r01["frac"] if r01 else head["frac"]),
             "l2": "random queries over %d month tables (%d MB >> 126 MB L2) + %d MB streamed output" % (
                 window, window * month_bytes >> 20, n * 168 >> 20),
             "details": details}

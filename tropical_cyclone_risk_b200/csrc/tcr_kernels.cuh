@@ -1676,6 +1676,7 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ TcrCtx c
 /* whose latitude is within the radius of the point (a great-circle distance is never shorter  */
 /* than R |dlat|, so the 1 % slack below cannot change any result).                            */
 /* ======================================================================================== */
+#define POI_CHUNK 384
 __global__ void __launch_bounds__(256) k_poi_vmax(int64_t n_rows, int n_steps, const double* __restrict__ lon,
                                                   const double* __restrict__ lat, const double* __restrict__ vmax,
                                                   double poi_lon, double poi_lat, double radius_km, double r_km,
@@ -1687,38 +1688,49 @@ __global__ void __launch_bounds__(256) k_poi_vmax(int64_t n_rows, int n_steps, c
     const float cos_poi = cosf((float)(poi_lat * TCR_DEG2RAD));
     const float s_half = sinf((float)fmin(0.5 * radius_km / r_km, 1.5));
     const float a_max = s_half * s_half * 1.02f + 1e-12f;          /* sin^2(radius / 2R) with slack */
+    /* Two phases per chunk of 384 samples, so that the expensive part runs with full warps: (1) twelve independent
+     * 256-byte latitude loads per warp in flight, the samples inside the latitude band of the point (6 % in the
+     * benchmark) are compacted into a per-warp list in shared memory; (2) the list is worked off 32 at a time:
+     * longitude, a float32 exclusion test, the fp64 haversine, vmax.  (Round 1 evaluated the haversine in place, a
+     * handful of lanes at a time: 26 % of the HBM roofline.) */
+    __shared__ unsigned short s_list[8][POI_CHUNK];
+    unsigned short* list = s_list[threadIdx.x >> 5];
     for (int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
         const size_t base = (size_t)row * n_steps;
         double best = -INFINITY;
         bool have = false;
-        /* the latitude stream is the only mandatory read: four independent 256-byte loads per warp in
-         * flight per trip (a dependent one-load loop leaves the memory system idle) */
-        for (int k0 = lane; k0 < n_steps; k0 += 128) {
-            double la4[4];
+        for (int k0 = 0; k0 < n_steps; k0 += POI_CHUNK) {
+            double la[POI_CHUNK / 32];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int k = k0 + 32 * u;
-                la4[u] = k < n_steps ? __ldcs(lat + base + k) : INFINITY;     /* +inf is outside every band */
+            for (int u = 0; u < POI_CHUNK / 32; ++u) {
+                const int k = k0 + 32 * u + lane;
+                la[u] = k < n_steps ? __ldcs(lat + base + k) : INFINITY;      /* +inf is outside every band */
             }
+            int cnt = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const double la = la4[u];
-                if (fabs(la - poi_lat) > band_deg) continue;        /* also false for NaN: falls through */
-                const int k = k0 + 32 * u;
+            for (int u = 0; u < POI_CHUNK / 32; ++u) {
+                const bool inb = !(fabs(la[u] - poi_lat) > band_deg);         /* NaN stays in, as in the dense formulation */
+                const unsigned m = __ballot_sync(TCR_FULL, inb);
+                if (inb) list[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(32 * u + lane);
+                cnt += __popc(m);
+            }
+            __syncwarp();
+            for (int i = lane; i < cnt; i += 32) {
+                const int k = k0 + list[i];
+                const double lat_k = __ldg(lat + base + k);                    /* just read: a cache hit */
                 const double lo = __ldcs(lon + base + k);
-                /* second, cheap exclusion in float32: the haversine argument is at least its longitude term
+                /* cheap exclusion in float32: the haversine argument is at least its longitude term
                  * cos(lat1) cos(lat2) sin^2(dlon/2); 2 % slack covers the float32 error many times over */
-                {
-                    const float c2 = __cosf((float)(la * TCR_DEG2RAD));
-                    const float sh = __sinf((float)((lo - poi_lon) * (0.5 * TCR_DEG2RAD)));
-                    if (cos_poi * c2 * sh * sh > a_max) continue;
-                }
-                const double d = tcr_haversine_r(r_km, poi_lon, poi_lat, lo, la);
+                const float c2 = __cosf((float)(lat_k * TCR_DEG2RAD));
+                const float sh = __sinf((float)((lo - poi_lon) * (0.5 * TCR_DEG2RAD)));
+                if (cos_poi * c2 * sh * sh > a_max) continue;
+                const double d = tcr_haversine_r(r_km, poi_lon, poi_lat, lo, lat_k);
                 if (d <= radius_km) {
                     const double v = __ldcs(vmax + base + k);
                     if (!tcr_isnan(v)) { have = true; if (v > best) best = v; }
                 }
             }
+            __syncwarp();
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
