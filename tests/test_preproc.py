@@ -425,17 +425,20 @@ def test_gpu_thermo_full_grid_sampled_oracle(engine):
 @pytest.mark.gpu
 def test_gpu_wind_stats_long_ungrouped_record_falls_back_to_smaller_tiles(engine):
     """3-hourly samples, no daily averaging: 248 single-sample groups do not fit a 64-point tile (254 KB of
-    shared memory) -- the library picks 32-point tiles; an hourly month does not fit at all and says so."""
-    from tropical_cyclone_risk_b200._lib import TcrError
+    shared memory) -- the library picks 32-point tiles; an hourly month (744 samples) does not fit a tile at all and is
+    streamed from global memory (k_wind_stats_stream) -- the reference's ungrouped semantics for any record length,
+    with and without missing samples."""
     ua, va = synth_winds(248, 2, 9, 40, seed=6)
     gs = np.arange(249, dtype=np.int32)
     got = engine.wind_stats(ua, va, 0, 1, gs)
     assert np.array_equal(got, po.wind_stats(series_of(ua, va, 0, 1), gs))
-    ua, va = synth_winds(744, 2, 2, 8, seed=6)
-    with pytest.raises(TcrError, match="daily groups"):
-        engine.wind_stats(ua, va, 0, 1, np.arange(745, dtype=np.int32))
-    got = engine.wind_stats(ua, va, 0, 1, np.arange(0, 745, 24, dtype=np.int32))          # ... but does as 31 daily groups
-    assert np.array_equal(got, po.wind_stats(series_of(ua, va, 0, 1), np.arange(0, 745, 24)))
+    for nan_frac in (0.0, 0.05):
+        ua, va = synth_winds(744, 2, 5, 67, seed=6, nan_frac=nan_frac)
+        gs = np.arange(745, dtype=np.int32)
+        got = engine.wind_stats(ua, va, 0, 1, gs)
+        assert np.array_equal(got, po.wind_stats(series_of(ua, va, 0, 1), gs), equal_nan=True)
+    got = engine.wind_stats(ua, va, 0, 1, np.arange(0, 745, 24, dtype=np.int32))          # the same record as 31 daily groups
+    assert np.array_equal(got, po.wind_stats(series_of(ua, va, 0, 1), np.arange(0, 745, 24)), equal_nan=True)
 
 
 def test_wind_oracle_nan_policy_matches_pandas():

@@ -205,6 +205,55 @@ __global__ void __launch_bounds__(NT) k_wind_stats_single(const WindStatArgs A)
     ws_moments<float, P, NT>(dm, sx, A.n_groups, cta0, A.n_pts, A.out);
 }
 
+/* Ungrouped records too long for a shared-memory month tile (an hourly month: 744 samples): the same sums and demeaned
+ * products in the same order, one thread per grid point, the series read from global memory twice (coalesced across
+ * the points of a warp; 2 x the HBM traffic of the tiled kernels).  ws_moments is the specification of the arithmetic. */
+__global__ void __launch_bounds__(256) k_wind_stats_stream(const WindStatArgs A)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n_pts) return;
+    const int n_groups = A.n_groups;
+    const size_t gs = (size_t)A.t_stride;
+    const float* x[4] = {A.src[0] + p, A.src[1] + p, A.src[2] + p, A.src[3] + p};
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+    for (int g = 0; g < n_groups; ++g) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) s[v] += (double)__ldg(x[v] + g * gs);
+    }
+    double m[4], m2[10];
+    if ((s[0] != s[0]) || (s[1] != s[1]) || (s[2] != s[2]) || (s[3] != s[3])) {
+        int k = 0;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j <= i; ++j, ++k) {
+                double mi;
+                ws_pair_general<float>(x[i], x[j], gs, n_groups, i == j, &mi, &m2[k]);
+                if (i == j) m[i] = mi;
+            }
+    } else {
+        const double n = (double)n_groups, n1 = (double)(n_groups - 1);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) m[v] = s[v] / n;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) m2[k] = 0.0;
+#pragma unroll 2
+        for (int g = 0; g < n_groups; ++g) {
+            const double d0 = (double)__ldg(x[0] + g * gs) - m[0], d1 = (double)__ldg(x[1] + g * gs) - m[1],
+                         d2 = (double)__ldg(x[2] + g * gs) - m[2], d3 = (double)__ldg(x[3] + g * gs) - m[3];
+            const double p00 = d0 * d0, p10 = d1 * d0, p11 = d1 * d1, p20 = d2 * d0, p21 = d2 * d1;
+            const double p22 = d2 * d2, p30 = d3 * d0, p31 = d3 * d1, p32 = d3 * d2, p33 = d3 * d3;
+            m2[0] += p00; m2[1] += p10; m2[2] += p11; m2[3] += p20; m2[4] += p21;
+            m2[5] += p22; m2[6] += p30; m2[7] += p31; m2[8] += p32; m2[9] += p33;
+        }
+        m2[0] /= n; m2[1] /= n1; m2[2] /= n; m2[3] /= n1; m2[4] /= n1;
+        m2[5] /= n; m2[6] /= n1; m2[7] /= n1; m2[8] /= n1; m2[9] /= n;
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) __stcs(A.out + (size_t)v * A.n_pts + p, m[v]);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) __stcs(A.out + (size_t)(4 + k) * A.n_pts + p, m2[k]);
+}
+
 /* Grouped input: daily means first. */
 template <int VEC, int KSPLIT, int U>
 __global__ void __launch_bounds__(128 * KSPLIT) k_wind_stats(const WindStatArgs A)

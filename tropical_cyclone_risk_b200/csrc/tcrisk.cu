@@ -1462,6 +1462,8 @@ int tcr_wind_stats(tcr_handle* h, int n_time, int64_t n_pts, int64_t t_stride,
     /* default kernels: 64 points per CTA when the month tile fits into shared memory, else 32 (long ungrouped records) */
     int pick = single ? 11 : 9;
     if (variant < 0 && single && ((size_t)n_groups * 4 * 64 + 8 * 64) * sizeof(float) > h->smem_optin) pick = 10;
+    /* an ungrouped record whose month tile does not fit even at 32 points per CTA (an hourly month) streams from global memory */
+    if (variant < 0 && single && ((size_t)n_groups * 4 * 32 + 8 * 32) * sizeof(float) > h->smem_optin) pick = 15;
     if (variant < 0 && !single && (size_t)(n_groups + 1) * 4 * 64 * sizeof(double) > h->smem_optin) pick = 8;
     switch (variant >= 0 ? variant : pick) {
     case 10: rc = launch_wind_stats_single<32, 64>(h, a); break;
@@ -1469,6 +1471,15 @@ int tcr_wind_stats(tcr_handle* h, int n_time, int64_t n_pts, int64_t t_stride,
     case 12: rc = launch_wind_stats_single<32, 128>(h, a); break;
     case 13: rc = launch_wind_stats_single<64, 256>(h, a); break;
     case 14: rc = launch_wind_stats_single<128, 256>(h, a); break;
+    case 15: {
+        if (!single) { rc = set_err("tcr_wind_stats: the streaming kernel is for ungrouped records"); break; }
+        const int64_t grid = (a.n_pts + 255) / 256;
+        if (grid > 0x7fffffffLL) { rc = set_err("tcr_wind_stats: too many grid points"); break; }
+        LaunchTimer lt_(h, TCR_K_WINDSTAT);
+        k_wind_stats_stream<<<(unsigned)grid, 256, 0, h->stream>>>(a);
+        rc = 0;
+        break;
+    }
     case 0: rc = launch_wind_stats<1, 1, 8>(h, a); break;
     case 1: rc = launch_wind_stats<2, 1, 8>(h, a); break;
     default:
