@@ -15,7 +15,7 @@ w.upload(eng)
 rng = np.random.default_rng(0)
 n = 3000
 ym = rng.integers(0, 2, n).astype(np.int32); lon = rng.uniform(255, 365, n); lat = rng.uniform(-5, 65, n)
-for v in (0, 4, 5):
+for v in (0, 5, 6):
     eng.set_interp_variant(v); eng.env_interp(ym, lon, lat)
 eng.set_interp_variant(0)
 n = 700
@@ -28,6 +28,8 @@ eng2 = Engine(w2.p, device=0); w2.upload(eng2)
 r = eng2.run_years([0], [2002], 7, 6)
 print("run_years ok", r["stats"][0]["storm_steps"])
 print("poi", np.isfinite(eng2.poi_vmax(r["lon"][0], r["lat"][0], r["vmax"][0], 300.0, 25.0, 500.0)).sum())
+r = eng2.run_years([0, 0], [2003, 2004], 9, 40)            # two years, several 256-attempt blocks each: the selection kernels
+print("run_years (2 years x 40) ok", [s["attempts"] for s in r["stats"]])
 # pre-processing kernels: ungrouped / grouped wind statistics (aligned and ragged rows), thermodynamics
 from tropical_cyclone_risk_b200 import synth_thermo
 for shape in ((19, 64), (7, 33)):
@@ -35,6 +37,8 @@ for shape in ((19, 64), (7, 33)):
     ua[3, 0, 2, 5] = np.nan
     eng2.wind_stats(ua, va, 0, 1, np.arange(25, dtype=np.int32))
     eng2.wind_stats(ua, va, 0, 1, np.arange(0, 25, 4, dtype=np.int32))
+ua = rng.normal(0, 8, (744, 2, 3, 40)).astype(np.float32); va = rng.normal(0, 6, (744, 2, 3, 40)).astype(np.float32)
+eng2.wind_stats(ua, va, 0, 1, np.arange(745, dtype=np.int32))          # hourly month, ungrouped: the streaming kernel
 eng2.set_entropy_table(*synth_thermo.fixture_table())
 p, ta, hus, sst, psl = synth_thermo.soundings(700, seed=2)
 print("thermo", float(np.nanmean(eng2.thermo_month(p, ta, hus, sst, psl, 1.0, 13)[0])))
