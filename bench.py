@@ -48,13 +48,20 @@ B_PER_QUERY = 396          # stand-alone sampler: 300 B + 16 B query + 80 B resu
 B_PER_STEP_TRACK = 32      # lon, lat, v, m float64 written by the integrator per emitted sample
 B_PER_STORM_PICKUP = 1004  # 60 double2 Fourier coefficients + 5 doubles + 1 int per integrated seed
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
-# workload (profiles/r01_prof_integrate_summary.txt, profiles/r01_prof_interp_summary.txt); None for other workloads
-NCU_TRAFFIC = {"k_env_interp": 10.154e9 + 5.608e9, "k_wind_stats": 1.030e9 + 0.113e9, "k_thermo": 0.2494e9 + 0.0074e9}
-# k_integrate, keyed by workload (basin_years_tracks_steps): the committed ncu capture of one launch of THAT workload
+# workload (profiles/r02_prof_interp_summary.txt, r02_prof_poi_summary.txt; wind statistics / thermodynamics: r01 captures, kernels unchanged); None for other workloads
+NCU_TRAFFIC = {"k_env_interp": 10.152e9 + 5.609e9, "k_wind_stats": 1.030e9 + 0.113e9, "k_thermo": 0.2494e9 + 0.0074e9,
+               "k_poi_vmax": 2.003e9 + 0.0065e9}
+# k_integrate, keyed by workload (basin_years_tracks_steps): the committed ncu capture of THAT workload
 NCU_INTEGRATE = {
-    "NA_10_1000_361": {"source": "profiles/r01_prof_integrate_summary.txt", "traffic": 2.061e9 + 1.818e9,
-                       "fp64_pipe_pct_of_peak": 25.1, "issue_slots_busy_pct": 31.4, "lanes_per_instruction": 23.1,
-                       "l2_hit_pct": 83.4, "dram_pct_of_peak": 4.9, "registers": 168, "warps_per_sm": 12},
+    "NA_10_1000_361": {"source": "profiles/r02_prof_integrate_summary.txt (ncu --set full, one launch)", "traffic": 2.079e9 + 1.828e9,
+                       "fp64_pipe_pct_of_peak": 31.7, "issue_slots_busy_pct": 36.9, "lanes_per_instruction": 23.3,
+                       "l2_hit_pct": 83.0, "dram_pct_of_peak": 5.9, "registers": 168, "warps_per_sm": 12,
+                       "l1_data_pipe_wavefronts_pct": 31.2},
+    # a launch of this workload touches tens of gigabytes of workspace: `--set full` (about 40 replays with memory save /
+    # restore) is not practical, the DRAM counters alone were collected over nine consecutive launches = one step
+    "GL_40_5000_361": {"source": "profiles/r02_integrate_cfg2_dram.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, "
+                                 "nine consecutive launches = one step; average per launch)",
+                       "traffic": 27.85e9 + 13.46e9, "l2_hit_pct": 74.2},
 }
 
 
@@ -578,7 +585,7 @@ def bench_interp(eng, wl, torch, dev, stream, peak, peak_src, args):
     head = res["k_env_interp"]
     details = {"variants": res, "window_months": window, "window_table_bytes": window * month_bytes,
                "moved_bytes_per_query": 320 + 12 + 20 + 168,
-               "traffic_source": "profiles/r01_prof_interp_summary.txt (ncu --set full, one launch over 228 MB of tables)"}
+               "traffic_source": "profiles/r02_prof_interp_summary.txt (ncu --set full, one launch over 228 MB of tables)"}
     if window < wl.n_ym:
         ym_all = torch.randint(0, wl.n_ym, (n,), generator=g, device=dev, dtype=torch.int32)
         details["all_resident_tables"] = dict(run(ym_all, all_variants[:1])["k_env_interp"], months=wl.n_ym,
@@ -615,7 +622,8 @@ def bench_poi(eng, torch, dev, peak, peak_src, ns, n_rows=400000):
     moved = 8.0 * samples + 16.0 * in_band + 8.0 * n_rows          # lat always; lon + vmax inside the band; one result per track
     ach = moved / (ms / cnt * 1e-3) / 1e9
     return {"kernel": "k_poi_vmax", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": None, "peak_source": peak_src, "avg_launch_ms": ms / cnt, "launches": cnt, "tracks": n_rows,
+            "traffic": NCU_TRAFFIC["k_poi_vmax"] if (n_rows, ns) == (400000, 361) else None,
+            "peak_source": peak_src, "avg_launch_ms": ms / cnt, "launches": cnt, "tracks": n_rows,
             "algorithmic_bytes": moved, "samples_per_s": samples / (ms / cnt * 1e-3),
             "note": "bytes = 8 B latitude per sample + 16 B (lon, vmax) for the %.1f %% of samples inside the latitude band of "
                     "the point + 8 B per track; the notebook's dense formulation would read 24 B per sample" % (100.0 * in_band / samples),

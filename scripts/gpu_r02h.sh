@@ -33,10 +33,13 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_en
 echo "== ncu full: front/back-end kernels of the step"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_fourier|k_select|k_postprocess|k_seed|k_gather|k_coef" -s 20 -c 6 -f -o $OUT/prof_others \
     python bench.py --basin NA --years 10 --tracks 1000 --steps 2 --warmup 3 --no-cpu --no-interp > $OUT/ncu_others.log 2>&1
-for r in integrate interp; do
+echo "== ncu full: return-period kernel"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_poi_vmax -s 3 -c 1 -f -o $OUT/prof_poi \
+    python bench.py --basin NA --years 1 --tracks 100 --steps 1 --warmup 1 --no-cpu > $OUT/ncu_poi.log 2>&1
+for r in integrate interp poi; do
     [ -f $OUT/prof_$r.ncu-rep ] && python scripts/ncu_summary.py $OUT/prof_$r.ncu-rep 40 > $OUT/prof_${r}_summary.txt 2>&1
 done
 [ -f $OUT/prof_others.ncu-rep ] && ncu -i $OUT/prof_others.ncu-rep --page raw --csv > $OUT/prof_others_raw.csv 2>/dev/null
-rm -f $OUT/prof_others.ncu-rep $OUT/prof_interp.ncu-rep
+rm -f $OUT/prof_others.ncu-rep $OUT/prof_interp.ncu-rep $OUT/prof_poi.ncu-rep
 fi
 ls -la $OUT

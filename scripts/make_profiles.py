@@ -58,7 +58,7 @@ def main():
             f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  python bench.py --steps 2 --warmup 3 --no-cpu --interp-queries 4194304\n")
             f.write("# per-launch times are cold-cache and serialised: compare SHARES with bench.py's kernel_share_of_step\n")
             f.write(launch_table(lc) + "\n")
-    for rep, args in (("prof_integrate", []), ("prof_interp", []), ("prof_windstats", []), ("prof_thermo", []), ("prof_others", None)):
+    for rep, args in (("prof_integrate", []), ("prof_interp", []), ("prof_poi", []), ("prof_windstats", []), ("prof_thermo", []), ("prof_others", None)):
         path = os.path.join(src, rep + ".ncu-rep")
         pre_made = os.path.join(src, rep + "_summary.txt")         # summarised on the GPU box (gpu_round.sh)
         pre_raw = os.path.join(src, rep + "_raw.csv")
