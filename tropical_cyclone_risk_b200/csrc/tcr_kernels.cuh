@@ -1154,47 +1154,58 @@ __global__ void __launch_bounds__(256) k_seed(const __grid_constant__ TcrCtx cx,
      * and test their next g = 32 / pending redraws at once; the first hit in redraw order wins, and the winner is
      * re-evaluated by its owner afterwards (one full-width pass).  Redraws are capped at max_redraws (code 3). */
     {
+        __shared__ unsigned char s_owner[8][32];              /* per warp: lane of the j-th pending attempt */
+        unsigned char* own = s_owner[threadIdx.x >> 5];
         const int lane = threadIdx.x & 31;
-        int next_r = 0, rstar = -1;
+        int next_r = 0;
+        bool moved = false;                                    /* the genesis point was replaced by a redraw */
         unsigned pend = __ballot_sync(TCR_FULL, pending);
         while (pend) {
             const int m = __popc(pend);
             const int g = 32 / m;
+            const int pos = __popc(pend & ((1u << lane) - 1u));
+            if (pending) own[pos] = (unsigned char)lane;
+            __syncwarp();
             const int j = lane / g;
             const bool has = j < m;
-            const int owner = has ? (int)__fns(pend, 0, j + 1) : 0;
+            const int owner = has ? (int)own[j] : 0;
             const long long k_o = __shfl_sync(TCR_FULL, (long long)k, owner);
             const int32_t key_o = __shfl_sync(TCR_FULL, key, owner);
             const int r_o = __shfl_sync(TCR_FULL, next_r, owner) + (lane - j * g);
             bool okr = false;
+            double lo = 0.0, la = 0.0;
             if (has && r_o < p.max_redraws) {
                 double uu[2];
                 tcr_draw2(A.run_seed, key_o, (int64_t)k_o, 3u + (uint32_t)r_o, 0, uu);
-                const double lo = b[0] + (b[2] - b[0]) * uu[0], la = b[1] + (b[3] - b[1]) * uu[1];
+                lo = b[0] + (b[2] - b[0]) * uu[0]; la = b[1] + (b[3] - b[1]) * uu[1];
                 TcrCell cc;
                 uint2 rr[4];
                 tcr_mask_cell(cx.mk, lo, la, cc, rr);
                 okr = !(tcr_mask_at(rr, 7, cc) < 1e-2);
             }
             const unsigned hit = __ballot_sync(TCR_FULL, okr);
+            /* the owner takes the point of its first hit -- or, when the redraws are exhausted, of the last one tested --
+             * from the helper lane that evaluated it */
+            const unsigned grp = pending ? (hit >> (pos * g)) & (g == 32 ? 0xffffffffu : ((1u << g) - 1u)) : 0u;
+            const bool last_round = pending && !grp && next_r + g >= p.max_redraws;
+            int src = lane;
+            if (grp) src = pos * g + __ffs((int)grp) - 1;
+            else if (last_round && p.max_redraws > next_r) src = pos * g + (p.max_redraws - 1 - next_r);
+            const double lo_w = __shfl_sync(TCR_FULL, lo, src), la_w = __shfl_sync(TCR_FULL, la, src);
             if (pending) {
-                const int pos = __popc(pend & ((1u << lane) - 1u));
-                const unsigned grp = (hit >> (pos * g)) & (g == 32 ? 0xffffffffu : ((1u << g) - 1u));
-                if (grp) { rstar = next_r + __ffs((int)grp) - 1; pending = false; }
+                if (grp) { gen_lon = lo_w; gen_lat = la_w; moved = true; pending = false; }
                 else {
                     next_r += g;
-                    if (next_r >= p.max_redraws) { exhausted = true; rstar = p.max_redraws - 1; pending = false; }
+                    if (next_r >= p.max_redraws) {
+                        exhausted = true; pending = false;
+                        if (src != lane) { gen_lon = lo_w; gen_lat = la_w; moved = true; }
+                    }
                 }
             }
+            __syncwarp();
             pend = __ballot_sync(TCR_FULL, pending);
         }
-        if (active && rstar >= 0) {
-            double uu[2];
-            tcr_draw2(A.run_seed, key, k, 3u + (uint32_t)rstar, 0, uu);
-            gen_lon = b[0] + (b[2] - b[0]) * uu[0];
-            gen_lat = b[1] + (b[3] - b[1]) * uu[1];
-            tcr_mask_cell(cx.mk, gen_lon, gen_lat, c, r);
-        }
+        if (moved) tcr_mask_cell(cx.mk, gen_lon, gen_lat, c, r);
     }
     if (active) {
         double u[2];
