@@ -328,6 +328,25 @@ def test_run_years_independent_of_wave_size(na_year, na_year_eng):
     assert not _same(a["lon"][0], a["lon"][1])
 
 
+def test_run_years_many_years_tiny_waves(na_year, na_year_eng):
+    """Sixteen years in one call with a wave capacity below one 256-attempt block per year (the library raises it to two
+    blocks per year: the selection kernels work per block): every year equals the same year run alone."""
+    keys = list(range(2001, 2017))
+    na_year_eng.set_tuning(max_wave=1 << 40, max_slots=1 << 40, oversub_permille=1020)
+    ref = [na_year_eng.run_years([0], [k], 11, 3) for k in keys[:4]]
+    na_year_eng.set_tuning(max_wave=1000, oversub_permille=1020)
+    try:
+        r = na_year_eng.run_years([0] * len(keys), keys, 11, 3)
+    finally:
+        na_year_eng.set_tuning(max_wave=1 << 40, max_slots=1 << 40, oversub_permille=1020)
+    for i, one in enumerate(ref):
+        for key in ("lon", "lat", "v", "m", "vmax", "env", "tc_month", "tc_basin", "n_seeds"):
+            assert _same(r[key][i], one[key][0]), (i, key)
+        for key in ("attempts", "counted_seeds", "n_kept"):
+            assert r["stats"][i][key] == one["stats"][0][key], (i, key)
+    assert all(s["n_kept"] == 3 for s in r["stats"])
+
+
 def test_year_properties_full_size(na_year, na_year_eng):
     """Size-independent properties at a BASELINE-sized year (NA, 1000 tracks): every row is a kept
     storm (NaN-padded tail, vmax >= 18 somewhere, v >= 15 somewhere), counters are consistent."""

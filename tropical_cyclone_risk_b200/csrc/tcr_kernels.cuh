@@ -1662,6 +1662,7 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ TcrCtx c
     const double* trk = A.track + (size_t)A.track_row[slot] * ns * 4;
     const double* ftab = A.ftab + (size_t)slot * ns * 4;
     const size_t o = (size_t)row * ns;
+    const bool env_al16 = (reinterpret_cast<uintptr_t>(A.o_env) & 15) == 0;
     for (int k = lane; k < ns; k += 32) {
         double2 a = make_double2(NAN, NAN), b = a, e0 = a, e1 = a;
         double vm = NAN;
@@ -1675,8 +1676,13 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ TcrCtx c
         }
         A.o_lon[o + k] = a.x; A.o_lat[o + k] = a.y; A.o_v[o + k] = b.x; A.o_m[o + k] = b.y;
         A.o_vmax[o + k] = vm;
-        double2* eo = reinterpret_cast<double2*>(A.o_env + (o + k) * 4);
-        eo[0] = e0; eo[1] = e1;
+        double* ep = A.o_env + (o + k) * 4;
+        if (env_al16) {
+            double2* eo = reinterpret_cast<double2*>(ep);
+            eo[0] = e0; eo[1] = e1;
+        } else {                        /* the caller's env section starts on an odd double (odd rows x odd n_steps before it) */
+            ep[0] = e0.x; ep[1] = e0.y; ep[2] = e1.x; ep[3] = e1.y;
+        }
     }
 }
 

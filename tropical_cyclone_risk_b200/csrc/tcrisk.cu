@@ -921,7 +921,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         }
         int64_t want_att = std::max<int64_t>(65536, (int64_t)(need * 1.05));
         if (h->max_wave > 0) want_att = std::min(want_att, h->max_wave);
-        want_att = std::max<int64_t>(want_att, 4096);
+        want_att = std::max<int64_t>(want_att, std::max<int64_t>(4096, 512 * (int64_t)n_years));   /* at least two 256-attempt blocks per year */
         int64_t want_slot = std::min(want_att, std::max<int64_t>(4096, (int64_t)((double)want_att * pass_est) + 1024));
         /* a workspace that was sized by the memory budget is as large as it gets: asking the allocator again would only
          * re-derive the same capacity from a slightly different free-memory reading, and a one-percent growth means
@@ -936,7 +936,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
             if (budget > out_bytes) budget -= out_bytes;
             const int64_t cap_mem = (int64_t)((double)budget / ((double)kAttemptBytes + pass_est * (double)slot_bytes(ns)));
             /* 25 % headroom so that the next call's slightly different estimate still fits */
-            int64_t att_cap = std::max<int64_t>(4096, std::min(cap_mem, want_att + want_att / 4));
+            int64_t att_cap = std::max<int64_t>(std::max<int64_t>(4096, 512 * (int64_t)n_years), std::min(cap_mem, want_att + want_att / 4));
             w0.mem_limited = hinted && cap_mem < want_att + want_att / 4;     /* sized from measured survival rates: final */
             int64_t slot_cap = std::min(att_cap, std::max<int64_t>(4096, (int64_t)((double)att_cap * pass_est) + 1024));
             w0.env.release(); w0.vmax.release();                       /* only tcr_integrate keeps per-slot env / vmax rows */
@@ -948,7 +948,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
     }
     Workspace& w = h->ws;
     int64_t cap = w.att_cap;
-    if (h->max_wave > 0) cap = std::min(cap, h->max_wave);
+    if (h->max_wave > 0) cap = std::min(cap, std::max<int64_t>(h->max_wave, 512 * (int64_t)n_years));
     int64_t slot_cap = w.slot_cap;
     if (h->max_slots > 0) slot_cap = std::min(slot_cap, h->max_slots);
     if (w.row_slot.ensure(rows * 4)) return -1;
