@@ -458,6 +458,25 @@ def test_cfg5_wp_900s_properties():
         eng.close()
 
 
+def test_odd_row_counts_device_resident_block(na_year, na_year_eng):
+    """Odd tracks x odd years x odd n_steps: the env section of a device-resident result block then starts on an odd
+    double (8-byte aligned only).  Same rows as the blocking call, which lays its block out itself."""
+    import torch
+    from tropical_cyclone_risk_b200.pipeline import YearPipeline
+    torch.cuda.set_device(0)
+    for n_years, n_tracks in ((1, 3), (3, 5)):
+        keys = [2001 + i for i in range(n_years)]
+        pipe = YearPipeline(na_year_eng, n_years, n_tracks, depth=1)
+        try:
+            t, _ = pipe.submit([0] * n_years, keys, 17)
+            got = {k: np.array(v) for k, v in pipe.result(t).items()}
+        finally:
+            pipe.drain()
+        want = na_year_eng.run_years([0] * n_years, keys, 17, n_tracks)
+        for key in ("lon", "lat", "v", "m", "vmax", "env", "tc_month", "tc_basin", "n_seeds"):
+            assert _same(got[key], want[key]), (n_years, n_tracks, key)
+
+
 def test_year_pipeline_matches_blocking_call(na_year, na_year_eng):
     """Double-buffered batches (download of batch i overlapping batch i+1) return exactly what the
     blocking call returns, for every batch in flight."""
