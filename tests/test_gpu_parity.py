@@ -458,6 +458,57 @@ def test_cfg5_wp_900s_properties():
         eng.close()
 
 
+def _ring_vs_tables(case, year_key, run_seed, n_tracks):
+    """tcr_run_years with the Fourier rings the integrator fills on demand (the default) against the same call with full
+    tables tabulated ahead of it (TCR_FTAB_RING=0 at tcr_create): every output bit and every counter."""
+    import os
+    res = []
+    for ring in ("1", "0"):
+        old = os.environ.get("TCR_FTAB_RING")
+        os.environ["TCR_FTAB_RING"] = ring
+        try:
+            eng = _engine(case)
+        finally:
+            if old is None:
+                del os.environ["TCR_FTAB_RING"]
+            else:
+                os.environ["TCR_FTAB_RING"] = old
+        try:
+            res.append(eng.run_years([0], [year_key], run_seed, n_tracks))
+            if ring == "1":
+                # tiny waves: rings of rows that are recycled many times, candidates that keep theirs
+                eng.set_tuning(max_wave=2048, max_slots=700, oversub_permille=1100)
+                res.append(eng.run_years([0], [year_key], run_seed, n_tracks))
+        finally:
+            eng.close()
+    a, a_small, b = res
+    for key in ("lon", "lat", "v", "m", "vmax", "env", "tc_month", "tc_basin", "n_seeds"):
+        assert _same(a[key], b[key]), key
+        assert _same(a_small[key], b[key]), key
+    for key in ("attempts", "counted_seeds", "integrated", "storm_steps", "kept_steps", "rhs_evals", "n_kept"):
+        assert a["stats"][0][key] == b["stats"][0][key] == a_small["stats"][0][key], key
+    return a
+
+
+def test_fourier_ring_equals_full_tables(gl_year):
+    """361 nodes: rings of 128 (two segments of 64; an RK attempt spans at most 25 nodes)."""
+    r = _ring_vs_tables(gl_year, 2002, 7, 400)
+    n_time = np.sum(~np.isnan(r["lon"][0]), axis=1)
+    assert n_time.max() > 200                     # storms that walk through several ring segments and wrap the ring
+
+
+def test_fourier_ring_equals_full_tables_900s():
+    """1441 nodes at 900 s: an attempt spans up to 97 nodes, rings of 256."""
+    import types
+    from tropical_cyclone_risk_b200 import namelist as nl
+    nl900 = types.SimpleNamespace(**{k: getattr(nl, k) for k in dir(nl) if not k.startswith("__")})
+    nl900.output_interval_s = 900
+    case = Case("WP", [2006], namelist=nl900)
+    r = _ring_vs_tables(case, 2006, 11, 150)
+    n_time = np.sum(~np.isnan(r["lon"][0]), axis=1)
+    assert n_time.max() > 600
+
+
 def test_odd_row_counts_device_resident_block(na_year, na_year_eng):
     """Odd tracks x odd years x odd n_steps: the env section of a device-resident result block then starts on an odd
     double (8-byte aligned only).  Same rows as the blocking call, which lays its block out itself."""

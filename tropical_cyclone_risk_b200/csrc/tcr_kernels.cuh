@@ -95,14 +95,17 @@ __global__ void k_build_consts(double earth_R, double gen_lat_min, double gen_la
 }
 
 /* storm-independent harmonics of the output time grid: sc[j][k] = {sin, cos}(2 pi (k+1) t_j / T_Fs) */
-__global__ void k_build_sincos(const __grid_constant__ TcrCtx cx, double2* __restrict__ sc)
+__global__ void k_build_sincos(const __grid_constant__ TcrCtx cx, double2* __restrict__ sc, double2* __restrict__ sct)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cx.p.n_steps) return;
     double2 h[TCR_N_HARM];
     tcr_harmonics(cx, tcr_node_time(cx, j), h);
 #pragma unroll
-    for (int k = 0; k < TCR_N_HARM; ++k) sc[(size_t)j * TCR_N_HARM + k] = h[k];
+    for (int k = 0; k < TCR_N_HARM; ++k) {
+        sc[(size_t)j * TCR_N_HARM + k] = h[k];
+        sct[(size_t)k * cx.p.n_steps + j] = h[k];
+    }
 }
 
 /* ======================================================================================== */
@@ -480,12 +483,83 @@ __global__ void __launch_bounds__(FTM_THREADS, 1) k_fourier_table_mma(const __gr
 /* the integrator: Coupled_FAST.gen_track (coupled_fast.py:229-267) incl. scipy's RK45        */
 /* driver loop, t_eval dense output and the terminal event                                    */
 /* ======================================================================================== */
+/* One segment of a storm's Fourier ring: nodes [j0, j0 + seg) of its four series from its 60 coefficient pairs, by the 32
+ * lanes of the calling warp (lane L takes nodes j0 + L, j0 + 32 + L of every 64-node pass) -- the fma chains of
+ * k_fourier_table, so the bits of the full tables.  Called warp-uniformly from the integrator's macro-step boundary.
+ * stage != 0: shared-space address of six warp-private rows of 32 doubles (pitch bytes apart) that hold the coefficient pairs
+ * during the fill (pair e at row e / 16, column pair e % 16): every lane then reads them as broadcast LDS instead of keeping
+ * 60 global loads in flight.  Not inlined: the integrator's register allocation (168, no spills) stays what it was.          */
+__device__ __noinline__ void tcr_ring_fill(const TcrCtx& cx, const double2* __restrict__ coef, double* __restrict__ ring_row,
+                                           int j0, int seg, int mask, uint32_t stage, uint32_t pitch)
+{
+    const int lane = threadIdx.x & 31;
+    const int ns = cx.p.n_steps;
+    if (stage) {
+#pragma unroll
+        for (int e = lane; e < TCR_N_PHASES; e += 32) {
+            const double2 cf = __ldg(coef + e);
+            asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(stage + (uint32_t)(e >> 4) * pitch + (uint32_t)(e & 15) * 16u), "d"(cf.x), "d"(cf.y) : "memory");
+        }
+        __syncwarp();
+    }
+    for (int jb = j0; jb < j0 + seg; jb += 64) {
+        const int ja = jb + lane, jc = jb + 32 + lane;
+        /* harmonic-major copy of the {sin, cos} table: the 32 lanes' nodes are 512 contiguous bytes per harmonic (the
+         * node-major rows are 240 B apart: 32 L1 wavefronts per load instead of 4, and the L1 data pipe is the integrator's
+         * busiest unit) */
+        const double2* sa = cx.sct + min(ja, ns - 1);
+        const double2* sb = cx.sct + min(jc, ns - 1);
+        double Fa[4] = {0.0, 0.0, 0.0, 0.0}, Fb[4] = {0.0, 0.0, 0.0, 0.0};
+        if (stage) {
+#pragma unroll
+            for (int k = 0; k < TCR_N_HARM; ++k) {
+                const double2 a = __ldg(sa + (size_t)k * ns), b = __ldg(sb + (size_t)k * ns);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = i * TCR_N_HARM + k;
+                    double2 ab;
+                    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(ab.x), "=d"(ab.y) : "r"(stage + (uint32_t)(e >> 4) * pitch + (uint32_t)(e & 15) * 16u));
+                    Fa[i] = fma(ab.x, a.x, Fa[i]); Fa[i] = fma(ab.y, a.y, Fa[i]);
+                    Fb[i] = fma(ab.x, b.x, Fb[i]); Fb[i] = fma(ab.y, b.y, Fb[i]);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < TCR_N_HARM; ++k) {
+                const double2 a = __ldg(sa + (size_t)k * ns), b = __ldg(sb + (size_t)k * ns);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double2 ab = __ldg(coef + i * TCR_N_HARM + k);
+                    Fa[i] = fma(ab.x, a.x, Fa[i]); Fa[i] = fma(ab.y, a.y, Fa[i]);
+                    Fb[i] = fma(ab.x, b.x, Fb[i]); Fb[i] = fma(ab.y, b.y, Fb[i]);
+                }
+            }
+        }
+        if (ja < ns && ja < j0 + seg) {
+            double2* d = reinterpret_cast<double2*>(ring_row + (size_t)(ja & mask) * 4);
+            d[0] = make_double2(Fa[0], Fa[1]); d[1] = make_double2(Fa[2], Fa[3]);
+        }
+        if (jc < ns && jc < j0 + seg) {
+            double2* d = reinterpret_cast<double2*>(ring_row + (size_t)(jc & mask) * 4);
+            d[0] = make_double2(Fb[0], Fb[1]); d[1] = make_double2(Fb[2], Fb[3]);
+        }
+    }
+    __syncwarp();                              /* the staging rows and the ring nodes are the warp's to read / overwrite again */
+}
+
 struct IntegArgs {
     int64_t n;                         /* number of storms (slots) if n_dev == NULL           */
     const unsigned int* n_dev;         /* device-side count (run_years)                       */
     const int32_t* ym;                 /* [n] table index                                     */
     const double* lon0; const double* lat0; const double* v0; const double* m0; const double* h_bl;
-    const double* ftab;                /* [n][n_steps][4] Fourier tables (k_fourier_table)    */
+    const double* ftab;                /* [n][n_steps][4] Fourier tables (k_fourier_table); NULL with a ring */
+    /* Fourier RING (tcr_run_years): instead of a full table per integrated seed, every track-pool row owns a ring of
+     * ring_nodes = 2 segments of nodes that the integrator fills on demand from the storm's coefficients, one segment ahead
+     * of the storm's clock -- storms use a quarter to a third of their table, and the table was 90 % of the per-slot workspace.
+     * A segment is longer than the nodes one RK attempt can span (max_step / t_step + 4: the host checks it), so an attempt
+     * never needs more than the two resident segments.                                                                      */
+    const double2* coef; double* ring; int ring_nodes;
+    int ring_cta;                      /* lock-stepped variants: requests served by the whole CTA (1) or by the lane's own warp (0) */
     double* track;                     /* [n][n_steps][4] lon,lat,v,m -- or, with track_row, a POOL of rows  */
     /* track pool (tcr_run_years): a storm writes its samples into the row its lane holds; a TC candidate
      * keeps the row (track_row[slot] = row) and the lane draws a fresh one, every other storm's row is
@@ -531,7 +605,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
     auto Ks = [&](int j, int i, double v) { if (in_smem(j)) ks[k_off(j, i)] = v; else Kr[j][i] = v; };
     const tcr_params& p = cx.p;
     const int lane = threadIdx.x & 31;
-    const double* ftab = nullptr;
+    const double* ftab = nullptr;       /* this storm's full table, or its row's ring */
+    const int fmask = A.ring ? A.ring_nodes - 1 : TCR_FTAB_FULL;
+    int have = 0;                       /* ring: nodes [0, have) of this storm have been tabulated */
     const int64_t n = A.n_dev ? (int64_t)*A.n_dev : A.n;
     const int ns = p.n_steps;
     const double t_bound = p.total_time, rtol = p.rtol, atol = p.atol, max_step = p.max_step;
@@ -604,6 +680,41 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
         mode = M_IDLE;
     };
 
+    /* tabulate ring segments until node need_idx of the lane's storm is resident (-1: nothing needed).  The warp serves its
+     * requests one at a time, all 32 lanes on one storm's segment.  Residency: after a fill, nodes [have - ring_nodes, have)
+     * are in the ring and have - seg <= need_idx; the lowest node a later evaluation of the same storm can ask for is the
+     * lower node of its clock, >= need_idx - 2 - (nodes one attempt spans) -- inside the ring because seg exceeds that span
+     * by 4 or more.  Callers pass need_idx one node high (ring_need: a stage time t + c h may round one ulp past t_new,
+     * onto a node). */
+    uint32_t ring_stage = 0;
+    if (HOMES) ring_stage = (uint32_t)__cvta_generic_to_shared(k_smem + (32 + 12) * THREADS + ((int)threadIdx.x & ~31));
+    /* CTA-wide service (lock-stepped variants): the lanes post their requests to a list in shared memory and the CTA's warps
+     * take them round-robin -- a warp that had to serve its own lanes one after the other kept its five partner warps
+     * waiting at the next slot barrier for as long as the unluckiest warp's requests took */
+    constexpr bool CTA_SERVE = HOMES && CTA_LOCKSTEP != 0;
+    __shared__ int rq_n[2], rq_par;
+    __shared__ int4 rq[CTA_SERVE ? THREADS : 1];
+    if (CTA_SERVE && A.ring) {
+        if (threadIdx.x < 2) rq_n[threadIdx.x] = 0;
+        if (threadIdx.x == 2) rq_par = 0;
+        __syncthreads();
+    }
+    auto ring_need = [&](int idx) { return idx < 0 ? idx : min(idx + 1, ns - 1); };
+    auto ring_serve = [&](int need_idx) {
+        for (;;) {
+            const unsigned req = __ballot_sync(TCR_FULL, need_idx >= have);
+            if (!req) break;
+            const int src = __ffs((int)req) - 1;
+            const long long sid_s = __shfl_sync(TCR_FULL, (long long)sid, src);
+            const int have_s = __shfl_sync(TCR_FULL, have, src);
+            const unsigned int row_s = __shfl_sync(TCR_FULL, row, src);
+            const int seg = A.ring_nodes >> 1;
+            tcr_ring_fill(cx, A.coef + (size_t)sid_s * TCR_N_PHASES, A.ring + (size_t)row_s * A.ring_nodes * 4, have_s, seg,
+                          A.ring_nodes - 1, ring_stage, (uint32_t)(THREADS * sizeof(double)));
+            if (lane == src) have += seg;
+        }
+    };
+
     for (;;) {
         /* ---- macro-step boundary: open the next RK attempt (RungeKutta._step_impl) ---- */
         if (mode == M_WAIT) { mode = M_RK; new_step = true; }
@@ -652,7 +763,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                         d[14 * THREADS] = __hiloint2double(ym, nfev);
                         d[15 * THREADS] = __hiloint2double(n_out, n_attempts);
                         d[16 * THREADS] = __hiloint2double(mode, (rejected ? 1 : 0) | (new_step ? 2 : 0) | (any_v ? 4 : 0));
-                        d[17 * THREADS] = __hiloint2double(0, (int)row);
+                        d[17 * THREADS] = __hiloint2double(have, (int)row);
                     }
                     __syncthreads();
                     if ((int)threadIdx.x < total) {
@@ -666,13 +777,41 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                         rejected = fl & 1; new_step = (fl & 2) != 0; any_v = (fl & 4) != 0;
                         status = 100;
                         row = (unsigned int)__double2loint(d[17 * THREADS]);
-                        ftab = A.ftab + (size_t)sid * ns * 4;
+                        have = __double2hiint(d[17 * THREADS]);
+                        ftab = A.ring ? A.ring + (size_t)row * A.ring_nodes * 4 : A.ftab + (size_t)sid * ns * 4;
                         trk = A.track + (A.track_row ? (size_t)row : (size_t)sid) * row_doubles;
                     } else {
                         mode = M_IDLE;             /* the queue is drained: this lane never needs a row again */
                     }
                     __syncthreads();                                     /* mailbox reusable by the next packing */
                 }
+            }
+        }
+        /* ---- idle lanes take the next storm from the queue.  Once per macro step: a storm ends where an RK attempt ends
+         * (only a storm that fails the ventilation pre-check frees its lane mid-step: 0.1-0.5 % of them), and a new storm's
+         * first ring segment has to be tabulated before its first evaluation ---- */
+        if (!drained) {
+            const unsigned need = __ballot_sync(TCR_FULL, mode == M_IDLE && lane < A.lane_cap);
+            if (need) {
+                const int cnt = __popc(need), leader = __ffs(need) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(A.queue, (unsigned long long)cnt);
+                base = __shfl_sync(TCR_FULL, base, leader);
+                if ((need >> lane) & 1u) {
+                    const int64_t my = (int64_t)base + __popc(need & ((1u << lane) - 1u));
+                    if (my < n) {
+                        sid = my;
+                        ym = A.ym[sid];
+                        Y(0) = A.lon0[sid]; Y(1) = A.lat0[sid]; Y(2) = A.v0[sid]; Y(3) = A.m0[sid];
+                        hbl = 0.5 * p.Ck / A.h_bl[sid];          /* storm-constant prefactor of dv/dt, dm/dt */
+                        ftab = A.ring ? A.ring + (size_t)row * A.ring_nodes * 4 : A.ftab + (size_t)sid * ns * 4;
+                        have = 0;
+                        trk = A.track + (A.track_row ? (size_t)row : (size_t)sid) * row_doubles;
+                        nfev = 0; n_out = 0; n_attempts = 0; any_v = false; t = 0.0; status = 100;
+                        mode = M_INIT0;
+                    }
+                }
+                if ((int64_t)base + cnt >= n) drained = true;
             }
         }
         if (mode == M_RK) {
@@ -692,32 +831,35 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 h_abs = fabs(h);
             }
         }
+        /* ---- Fourier ring: every stage time of this attempt lies in (t, t_new], so the highest node it can bracket is the
+         * upper node of t_new; a new storm's first evaluation (t = 0) brackets nodes 0 and 1 ---- */
+        if (A.ring) {
+            const int need = ring_need(mode == M_RK ? tcr_fs_index(cx, t_new) : (mode == M_INIT0 ? 1 : -1));
+            if (CTA_SERVE && A.ring_cta) {
+                const int par = rq_par;
+                if (need >= have) {              /* one segment is always enough here (a segment exceeds an attempt's span) */
+                    rq[atomicAdd(&rq_n[par], 1)] = make_int4((int)sid, (int)row, have, 0);
+                    have += A.ring_nodes >> 1;
+                }
+                __syncthreads();
+                const int nreq = rq_n[par];
+                if (threadIdx.x == 0) { rq_n[par ^ 1] = 0; rq_par = par ^ 1; }      /* the next macro step's list */
+                for (int i = (int)(threadIdx.x >> 5); i < nreq; i += THREADS / 32) {
+                    const int4 r = rq[i];
+                    tcr_ring_fill(cx, A.coef + (size_t)r.x * TCR_N_PHASES, A.ring + (size_t)(unsigned)r.y * A.ring_nodes * 4, r.z,
+                                  A.ring_nodes >> 1, A.ring_nodes - 1, ring_stage, (uint32_t)(THREADS * sizeof(double)));
+                }
+                /* the slot-0 barrier below orders these fills before the evaluations that read them */
+            }
+            ring_serve(need);                    /* free-running variants; with the CTA service nothing is left to do */
+        }
 
 #pragma unroll 1
         for (int slot = 0; slot < 6; ++slot) {
-            /* ---- idle lanes take the next storm from the queue ---- */
-            if (slot < 5 && !drained) {
-                const unsigned need = __ballot_sync(TCR_FULL, mode == M_IDLE && lane < A.lane_cap);
-                if (need) {
-                    const int cnt = __popc(need), leader = __ffs(need) - 1;
-                    unsigned long long base = 0;
-                    if (lane == leader) base = atomicAdd(A.queue, (unsigned long long)cnt);
-                    base = __shfl_sync(TCR_FULL, base, leader);
-                    if ((need >> lane) & 1u) {
-                        const int64_t my = (int64_t)base + __popc(need & ((1u << lane) - 1u));
-                        if (my < n) {
-                            sid = my;
-                            ym = A.ym[sid];
-                            Y(0) = A.lon0[sid]; Y(1) = A.lat0[sid]; Y(2) = A.v0[sid]; Y(3) = A.m0[sid];
-                            hbl = 0.5 * p.Ck / A.h_bl[sid];          /* storm-constant prefactor of dv/dt, dm/dt */
-                            ftab = A.ftab + (size_t)sid * ns * 4;
-                            trk = A.track + (A.track_row ? (size_t)row : (size_t)sid) * row_doubles;
-                            nfev = 0; n_out = 0; n_attempts = 0; any_v = false; t = 0.0; status = 100;
-                            mode = M_INIT0;
-                        }
-                    }
-                    if ((int64_t)base + cnt >= n) drained = true;
-                }
+            if (slot == 1 && A.ring) {
+                /* select_initial_step's second evaluation sits at t = h0, which is known only now: inside segment 0 in
+                 * practice (h0 is seconds to minutes), but nothing bounds it */
+                ring_serve(ring_need(mode == M_INIT1 ? tcr_fs_index(cx, 0.0 + h0) : -1));
             }
             if constexpr (CTA_LOCKSTEP != 0) {
                 /* all warps of the CTA enter every RHS evaluation together: the ~45 KB of RHS code
@@ -789,15 +931,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 if constexpr (FAST_RHS) {
                     /* straight-line evaluation (tcr_rhs_fast.cuh); an evaluation that left the common case of any
                      * of its operations is repeated by the specification form */
-                    if (tcr_rhs_fast(cx, ym, ftab, hbl, te, ye, dy, aux)) {
+                    const TcrFtab ft = {ftab, fmask};
+                    if (tcr_rhs_fast(cx, ym, ft, hbl, te, ye, dy, aux)) {
                         double yy[4] = {ye[0], ye[1], ye[2], ye[3]}, dd[4];
                         TcrRhsAux ax2;
-                        tcr_rhs_slow(cx, ym, ftab, hbl, te, yy, dd, &ax2);
+                        tcr_rhs_slow(cx, ym, ft, hbl, te, yy, dd, &ax2);
                         dy[0] = dd[0]; dy[1] = dd[1]; dy[2] = dd[2]; dy[3] = dd[3];
                         aux = ax2;
                     }
                 } else {
-                    tcr_rhs(cx, ym, ftab, hbl, te, ye, dy, aux);
+                    tcr_rhs(cx, ym, TcrFtab{ftab, fmask}, hbl, te, ye, dy, aux);
                 }
                 ++nfev;
             }
@@ -855,6 +998,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_integrate(const __grid_consta
                 if (max_step < hh) hh = max_step;
                 h_abs = hh;
                 { const double yl[4] = {Y(0), Y(1), Y(2), Y(3)}; g = tcr_event(p, yl); }
+                /* an initial-step probe beyond the ring's length has overwritten the nodes the integration starts from */
+                if (A.ring && have > A.ring_nodes) have = 0;
                 mode = M_WAIT;
             }
         }
@@ -959,7 +1104,7 @@ __global__ void __launch_bounds__(128) k_rhs_eval(const __grid_constant__ TcrCtx
     const double yi[4] = {y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]};
     double dy[4];
     TcrRhsAux aux = {0, 0, 0, {0, 0, 0, 0}};
-    tcr_rhs(cx, ym[i], ftab + (size_t)i * cx.p.n_steps * 4, 0.5 * cx.p.Ck / h_bl[i], t[i], yi, dy, aux);
+    tcr_rhs(cx, ym[i], TcrFtab{ftab + (size_t)i * cx.p.n_steps * 4, TCR_FTAB_FULL}, 0.5 * cx.p.Ck / h_bl[i], t[i], yi, dy, aux);
 #pragma unroll
     for (int k = 0; k < 4; ++k) { dydt[4 * i + k] = dy[k]; env[4 * i + k] = aux.wf[k]; }
 }
@@ -971,7 +1116,8 @@ __global__ void __launch_bounds__(128) k_rhs_eval(const __grid_constant__ TcrCtx
 /* ======================================================================================== */
 /* one output sample of a storm: env winds at the track point (util/compute.py:201-202), translation speed from the
  * neighbouring samples (util/sphere.py:58-83) and axi_to_max_wind (wind/tc_wind.py:6-21)                       */
-__device__ __forceinline__ double tcr_post_sample(const TcrCtx& cx, int ym, const double* __restrict__ ftab,
+/* ftab: the storm's full Fourier table, or NULL and coef: its 60 coefficient pairs (the nodes are then formed on the spot) */
+__device__ __forceinline__ double tcr_post_sample(const TcrCtx& cx, int ym, const double* __restrict__ ftab, const double2* __restrict__ coef,
                                                   const double* __restrict__ trk, int nt, int k, double w[4])
 {
     const tcr_params& p = cx.p;
@@ -982,7 +1128,8 @@ __device__ __forceinline__ double tcr_post_sample(const TcrCtx& cx, int ym, cons
     w[0] = w[1] = w[2] = w[3] = 0.0;
     if (!(tcr_isnan(lon) || tcr_isnan(tk))) {
         TcrFsNodes fsn;
-        tcr_fs_begin(cx, ftab, tk, fsn);
+        if (ftab) tcr_fs_begin(cx, TcrFtab{ftab, TCR_FTAB_FULL}, tk, fsn);
+        else tcr_fs_begin_coef(cx, coef, tk, fsn);
         TcrCell c;
         tcr_cell_at(cx.tab.lon, cx.tab.lat, lon, lat, c);
         tcr_env_winds_cell(cx, tcr_record(cx.tab, ym, c), c, fsn, tk, w);
@@ -1034,6 +1181,7 @@ struct PostArgs {
     int64_t n;                          /* storms if list == NULL */
     const int32_t* list; const unsigned int* list_count;
     const int32_t* ym; const double* ftab; const double* track;
+    const double2* coef;                /* [n][60] coefficient pairs, used when ftab == NULL (the integrator kept only rings) */
     const int32_t* track_row;           /* pool row of a candidate's track (NULL: track is indexed by storm) */
     const unsigned int* pool_ctl;       /* [1] != 0: the track pool overflowed, the wave is void             */
     const int32_t* n_time; const int32_t* status;
@@ -1059,10 +1207,11 @@ __global__ void __launch_bounds__(128) k_postprocess(const __grid_constant__ Tcr
         __syncthreads();
         const int ym = A.ym[sid];
         const double* trk = A.track + (size_t)(A.track_row ? (int64_t)A.track_row[sid] : sid) * ns * 4;
-        const double* ftab = A.ftab + (size_t)sid * ns * 4;
+        const double* ftab = A.ftab ? A.ftab + (size_t)sid * ns * 4 : nullptr;
+        const double2* coef = A.coef ? A.coef + (size_t)sid * TCR_N_PHASES : nullptr;
         for (int k = threadIdx.x; k < nt; k += blockDim.x) {
             double w[4];
-            const double vm = tcr_post_sample(cx, ym, ftab, trk, nt, k, w);
+            const double vm = tcr_post_sample(cx, ym, ftab, coef, trk, nt, k, w);
             if (A.env) {
                 double2* ed = reinterpret_cast<double2*>(A.env + ((size_t)sid * ns + k) * 4);
                 ed[0] = make_double2(w[0], w[1]);
@@ -1643,7 +1792,7 @@ __global__ void __launch_bounds__(128) k_select_finish(const SelectArgs A)
 struct GatherArgs {
     int n_years, n_tracks;
     const int32_t* row_slot; const int32_t* n_time;
-    const int32_t* ym; const double* ftab; const double* track; const int32_t* track_row;
+    const int32_t* ym; const double* ftab; const double2* coef; const double* track; const int32_t* track_row;
     const unsigned int* pool_ctl;
     double* o_lon; double* o_lat; double* o_v; double* o_m; double* o_vmax; double* o_env;
 };
@@ -1660,7 +1809,8 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ TcrCtx c
     const int nt = A.n_time[slot];
     const int ym = A.ym[slot];
     const double* trk = A.track + (size_t)A.track_row[slot] * ns * 4;
-    const double* ftab = A.ftab + (size_t)slot * ns * 4;
+    const double* ftab = A.ftab ? A.ftab + (size_t)slot * ns * 4 : nullptr;
+    const double2* coef = A.coef ? A.coef + (size_t)slot * TCR_N_PHASES : nullptr;
     const size_t o = (size_t)row * ns;
     const bool env_al16 = (reinterpret_cast<uintptr_t>(A.o_env) & 15) == 0;
     for (int k = lane; k < ns; k += 32) {
@@ -1670,7 +1820,7 @@ __global__ void __launch_bounds__(256) k_gather(const __grid_constant__ TcrCtx c
             a = *reinterpret_cast<const double2*>(trk + (size_t)k * 4);
             b = *reinterpret_cast<const double2*>(trk + (size_t)k * 4 + 2);
             double w[4];
-            vm = tcr_post_sample(cx, ym, ftab, trk, nt, k, w);
+            vm = tcr_post_sample(cx, ym, ftab, coef, trk, nt, k, w);
             e0 = make_double2(w[0], w[1]);
             e1 = make_double2(w[2], w[3]);
         }

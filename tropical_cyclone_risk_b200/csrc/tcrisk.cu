@@ -86,12 +86,13 @@ struct Workspace {
     int64_t pool_rows = 0;         /* rows of the track pool (tcr_run_years): lanes in flight + candidates   */
     bool mem_limited = false;      /* the capacities were set by the memory budget, not by the job            */
     int ns = 0;
+    int ring_nodes = 0;            /* nodes per Fourier ring (0: tcr_run_years tabulates full tables)         */
     DevBuf code, basin, month, att_slot, a_lon, a_lat, a_v0, a_m0;   /* per attempt */
     DevBuf blk_count, blk_off;                                       /* per 256-attempt seed block */
     DevBuf att_kept, wave_tot;                                       /* k_wave_stats: byte per attempt; per-year totals + histogram */
     DevBuf s_ym, s_lon, s_lat, s_v0, s_m0, s_hbl, s_att, s_key;       /* per slot */
     DevBuf n_time, status, nfev, flags, cand, track_row;
-    DevBuf coef, ftab, track, env, vmax;
+    DevBuf coef, ftab, ring, track, env, vmax;
     DevBuf counters;       /* [0] queue (u64), u32 @+8 n_slots, @+12 cand_count, @+16 n_pass, @+20 pool next, @+24 pool overflow */
     DevBuf year_i64;       /* wave_off [ny+1], k0 [ny], consumed [ny], used [ny] */
     DevBuf year_i32;       /* ym_base [ny], year_key [ny], nt [ny] */
@@ -101,10 +102,10 @@ struct Workspace {
     {
         DevBuf* all[] = {&code, &basin, &month, &att_slot, &a_lon, &a_lat, &a_v0, &a_m0, &blk_count, &blk_off, &att_kept, &wave_tot,
                          &s_ym, &s_lon, &s_lat, &s_v0, &s_m0, &s_hbl, &s_att, &s_key,
-                         &n_time, &status, &nfev, &flags, &cand, &track_row, &coef, &ftab, &track, &env, &vmax, &counters, &year_i64,
+                         &n_time, &status, &nfev, &flags, &cand, &track_row, &coef, &ftab, &ring, &track, &env, &vmax, &counters, &year_i64,
                          &year_i32, &row_slot, &stats, &out};
         for (DevBuf* b : all) b->release();
-        att_cap = slot_cap = full_cap = pool_rows = 0; mem_limited = false;
+        att_cap = slot_cap = full_cap = pool_rows = 0; mem_limited = false; ring_nodes = 0;
     }
 };
 
@@ -131,6 +132,8 @@ struct tcr_handle {
     bool have_static = false, have_masks = false;
     /* tuning */
     int integ_variant = 21, oversub_permille = 1020, interp_variant = 0;
+    int ftab_ring = -1;          /* tcr_run_years: Fourier rings filled by the integrator (1), full tables tabulated ahead of it (0), or
+                                  * by the length of the output grid (-1, default: ring_nodes_for) */
     /* within-year sharding (tcr_set_shard): rank r of `world` integrates the attempts k with k % world == r */
     int shard_rank = 0, shard_world = 1;
     tcr_allreduce_fn allreduce = nullptr;
@@ -261,16 +264,19 @@ int tcr_create(int device, const tcr_params* p, tcr_handle** out)
         const int v = atoi(iv);
         if (v >= 1 && v <= 32) h->integ_variant = v - 1;
     }
+    if (const char* fr = getenv("TCR_FTAB_RING")) h->ftab_ring = atoi(fr) < 0 ? -1 : atoi(fr) != 0;   /* A/B runs; a test runs both in one process */
     h->num_sms = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
     memset(&h->ctx, 0, sizeof h->ctx);
     h->ctx.p = *p;
     h->ctx.t_step = p->total_time / (double)(p->n_steps - 1);
     if (cudaMallocHost(&h->pinned, 1 << 16) != cudaSuccess) { delete h; return set_err("cudaMallocHost failed"); }
-    if (h->sincos.ensure((size_t)p->n_steps * TCR_N_HARM * sizeof(double2))) { cudaFreeHost(h->pinned); delete h; return -1; }
+    if (h->sincos.ensure((size_t)2 * p->n_steps * TCR_N_HARM * sizeof(double2))) { cudaFreeHost(h->pinned); delete h; return -1; }
     h->ctx.sc = h->sincos.as<double2>();
+    h->ctx.sct = h->ctx.sc + (size_t)p->n_steps * TCR_N_HARM;
     h->ctx.inv_t_step = 1.0 / h->ctx.t_step;
-    k_build_sincos<<<(p->n_steps + 127) / 128, 128, 0, h->stream>>>(h->ctx, h->sincos.as<double2>());
+    k_build_sincos<<<(p->n_steps + 127) / 128, 128, 0, h->stream>>>(h->ctx, h->sincos.as<double2>(),
+                                                                    h->sincos.as<double2>() + (size_t)p->n_steps * TCR_N_HARM);
     double* d_consts = reinterpret_cast<double*>(h->pinned);          /* pinned memory is device-accessible (UVA) */
     k_build_consts<<<1, 32, 0, h->stream>>>(p->earth_R, p->gen_lat_min, p->gen_lat_max, d_consts);
     cudaError_t e = cudaGetLastError();
@@ -586,19 +592,45 @@ int tcr_env_interp(tcr_handle* h, int64_t n, const int32_t* ym, const double* lo
 /* per integrated slot: 60 coefficient pairs, the Fourier table (32 B per node), ~100 B of scalars, and its share
  * of the track pool (one row per kPoolDiv slots: candidates are 2-3 % of the storms)                       */
 static const int kPoolDiv = 8;
-static size_t slot_bytes(int ns) { return 960 + (size_t)ns * 32 + 104 + (size_t)ns * 32 / kPoolDiv; }
+static size_t slot_bytes(int ns, int ring_nodes)
+{
+    return 960 + 104 + (ring_nodes ? (size_t)ring_nodes * 32 / kPoolDiv : (size_t)ns * 32) + (size_t)ns * 32 / kPoolDiv;
+}
+
+/* Fourier ring of tcr_run_years (IntegArgs::ring): nodes per ring, or 0 for full tables.  A segment (half a ring) must exceed
+ * the nodes one RK attempt can span by 4 (k_integrate, ring_serve).
+ * Default: the ring where the output grid is at least four rings long.  Measured on one box (profiles/r02_ring_ab.txt): a
+ * node tabulated inside the integrator costs about 3.6 x a node of the stand-alone DMMA kernel (two dependent L2 round trips and
+ * ~400 instructions per 64-node segment, issued by a warp whose CTA partners wait at the next slot barrier), and storms use
+ * 30-40 % of their table -- so at 361 hourly nodes (rings of 128) the ring loses (configs[1] 12.3 against 11.4 ms per step,
+ * configs[2] 737 against 726 ms although it runs in 3 waves instead of 9), at 1441 nodes (900-s output, rings of 256), where the
+ * tabulation kernel is 39 % of the step, it wins (300 against 345 ms).  TCR_FTAB_RING=1 / 0 at tcr_create forces either.    */
+static int ring_nodes_for(const tcr_handle* h)
+{
+    if (!h->ftab_ring) return 0;
+    const tcr_params& p = h->ctx.p;
+    if (!(p.max_step > 0.0) || !(h->ctx.t_step > 0.0)) return 0;
+    const double span = std::ceil(p.max_step / h->ctx.t_step) + 1.0;
+    int seg = 64;
+    while ((double)seg < span + 4.0 && seg < (1 << 20)) seg *= 2;
+    if (2 * seg >= p.n_steps) return 0;                     /* a ring as long as the table saves nothing */
+    if (h->ftab_ring < 0 && 8 * seg > p.n_steps) return 0;
+    return 2 * seg;
+}
 static const size_t kAttemptBytes = 56;
 static int64_t max_lanes(const tcr_handle* h) { return (int64_t)h->num_sms * 576; }   /* most threads per SM of any variant */
 
 /* full: every slot owns a track / env / vmax row (tcr_integrate returns them for every storm); otherwise tracks
  * live in the pool and env winds / vmax are never stored per slot (k_gather forms them for the rows it emits) */
 enum WsMode { WS_SLOTS = 0, WS_FULL = 1, WS_POOL = 2 };     /* slots only (coefficients, Fourier tables) / + per-slot rows / + track pool */
-static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_years, WsMode mode)
+static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_years, WsMode mode, int ring_nodes = 0)
 {
     const bool full = mode == WS_FULL;
     Workspace& w = h->ws;
     const int ns = h->ctx.p.n_steps;
     if (w.ns != ns) { w.release_all(); w.ns = ns; }
+    /* full Fourier tables for the slots THIS call asked for (a workspace grown by ring-mode years has none) */
+    if (!ring_nodes && w.ftab.ensure((size_t)std::max<int64_t>(slot_cap, 1) * ns * 32)) return -1;
     if (att_cap > w.att_cap) {
         const size_t c = (size_t)att_cap, nb = (c + 255) / 256;
         if (w.code.ensure(c * 4) || w.basin.ensure(c * 4) || w.month.ensure(c * 4) || w.att_slot.ensure(c * 4) ||
@@ -612,8 +644,7 @@ static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_yea
         if (w.s_ym.ensure(c * 4) || w.s_lon.ensure(c * 8) || w.s_lat.ensure(c * 8) || w.s_v0.ensure(c * 8) ||
             w.s_m0.ensure(c * 8) || w.s_hbl.ensure(c * 8) || w.s_att.ensure(c * 8) || w.s_key.ensure(c * 4) ||
             w.n_time.ensure(c * 4) || w.status.ensure(c * 4) || w.nfev.ensure(c * 4) || w.flags.ensure(c * 4) ||
-            w.cand.ensure(c * 4) || w.track_row.ensure(c * 4) || w.coef.ensure(c * TCR_N_PHASES * sizeof(double2)) ||
-            w.ftab.ensure(c * ns * 32))
+            w.cand.ensure(c * 4) || w.track_row.ensure(c * 4) || w.coef.ensure(c * TCR_N_PHASES * sizeof(double2)))
             return -1;
         w.slot_cap = slot_cap;
     }
@@ -631,6 +662,11 @@ static int ws_ensure(tcr_handle* h, int64_t att_cap, int64_t slot_cap, int n_yea
             w.full_cap = std::min<int64_t>(w.full_cap, (int64_t)(w.track.bytes / ((size_t)ns * 32)));
         }
         w.pool_rows = std::min<int64_t>((int64_t)(w.track.bytes / ((size_t)ns * 32)), 0x7fffffff);
+        if (ring_nodes) {
+            if (w.ring.ensure((size_t)w.pool_rows * ring_nodes * 32)) return -1;
+            w.pool_rows = std::min<int64_t>(w.pool_rows, (int64_t)(w.ring.bytes / ((size_t)ring_nodes * 32)));
+        }
+        w.ring_nodes = ring_nodes;
     }
     if (w.counters.ensure(64)) return -1;
     const size_t ny = (size_t)std::max(n_years, 1);
@@ -906,6 +942,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
      * bounded by a memory budget.  A workspace that already fits is reused without touching the
      * allocator (cudaMemGetInfo / cudaMalloc are millisecond-class host calls). */
     const size_t out_bytes = on_device ? 0 : rows * ns * 72 + rows * 12 + (size_t)n_years * 84 * 8;
+    const int ring_nodes = ring_nodes_for(h);
     {
         Workspace& w0 = h->ws;
         const bool hinted = h->hint_kept_rate > 0.0;
@@ -926,23 +963,24 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         /* a workspace that was sized by the memory budget is as large as it gets: asking the allocator again would only
          * re-derive the same capacity from a slightly different free-memory reading, and a one-percent growth means
          * freeing and re-allocating tens of gigabytes (measured: 150-350 ms per call, every call, at configs[3]'s shape) */
-        const bool fits = w0.ns == ns && (w0.att_cap >= want_att || w0.mem_limited) && (w0.slot_cap >= want_slot || w0.mem_limited) &&
+        const bool fits = w0.ns == ns && w0.ring_nodes == ring_nodes && (w0.att_cap >= want_att || w0.mem_limited) && (w0.slot_cap >= want_slot || w0.mem_limited) &&
                           (on_device || w0.out.bytes >= out_bytes + 256);
         if (!fits) {
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
-            size_t held = w0.ftab.bytes + w0.track.bytes + w0.env.bytes + w0.vmax.bytes + w0.coef.bytes + w0.out.bytes;
+            if (ring_nodes) w0.ftab.release(); else w0.ring.release();
+            size_t held = w0.ftab.bytes + w0.ring.bytes + w0.track.bytes + w0.env.bytes + w0.vmax.bytes + w0.coef.bytes + w0.out.bytes;
             size_t budget = std::min<size_t>((size_t)96 << 30, (size_t)((free_b + held) * 0.6));
             if (budget > out_bytes) budget -= out_bytes;
-            const int64_t cap_mem = (int64_t)((double)budget / ((double)kAttemptBytes + pass_est * (double)slot_bytes(ns)));
+            const int64_t cap_mem = (int64_t)((double)budget / ((double)kAttemptBytes + pass_est * (double)slot_bytes(ns, ring_nodes)));
             /* 25 % headroom so that the next call's slightly different estimate still fits */
             int64_t att_cap = std::max<int64_t>(std::max<int64_t>(4096, 512 * (int64_t)n_years), std::min(cap_mem, want_att + want_att / 4));
             w0.mem_limited = hinted && cap_mem < want_att + want_att / 4;     /* sized from measured survival rates: final */
             int64_t slot_cap = std::min(att_cap, std::max<int64_t>(4096, (int64_t)((double)att_cap * pass_est) + 1024));
             w0.env.release(); w0.vmax.release();                       /* only tcr_integrate keeps per-slot env / vmax rows */
             if (w0.full_cap > 0) { w0.track.release(); w0.full_cap = 0; w0.pool_rows = 0; }
-            if (ws_ensure(h, std::max(att_cap, w0.att_cap), std::max(slot_cap, w0.slot_cap), n_years, WS_POOL)) return -1;
-        } else if (ws_ensure(h, w0.att_cap, w0.slot_cap, n_years, WS_POOL)) {
+            if (ws_ensure(h, std::max(att_cap, w0.att_cap), std::max(slot_cap, w0.slot_cap), n_years, WS_POOL, ring_nodes)) return -1;
+        } else if (ws_ensure(h, w0.att_cap, w0.slot_cap, n_years, WS_POOL, ring_nodes)) {
             return -1;
         }
     }
@@ -1133,17 +1171,26 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         memset(&a, 0, sizeof a);
         a.n = 0; a.n_dev = d_nslots;
         a.ym = as.s_ym; a.lon0 = as.s_lon; a.lat0 = as.s_lat; a.v0 = as.s_v0; a.m0 = as.s_m0; a.h_bl = as.s_hbl;
-        a.ftab = w.ftab.as<double>(); a.track = w.track.as<double>();
+        a.track = w.track.as<double>();
+        if (ring_nodes) {
+            /* the integrator tabulates what its storms reach, segment by segment, into the rings of the track-pool rows;
+             * post-processing and the gather form the few nodes they need from the coefficients */
+            a.ftab = nullptr; a.coef = w.coef.as<double2>(); a.ring = w.ring.as<double>(); a.ring_nodes = ring_nodes;
+            { static const int cta_on = getenv("TCR_RING_CTA") ? atoi(getenv("TCR_RING_CTA")) : 1; a.ring_cta = cta_on; }
+        } else {
+            a.ftab = w.ftab.as<double>();
+        }
         a.n_time = w.n_time.as<int32_t>(); a.status = w.status.as<int32_t>(); a.nfev = w.nfev.as<int32_t>();
         a.flags = w.flags.as<uint32_t>();
         a.queue = d_queue; a.cand_list = w.cand.as<int32_t>(); a.cand_count = d_ncand;
         a.track_row = w.track_row.as<int32_t>(); a.pool_ctl = d_pool; a.pool_rows = (unsigned int)w.pool_rows;
-        if (launch_fourier_table(h, slots_upper, d_nslots) || launch_integrate(h, a, slots_upper)) return -1;
+        if (!ring_nodes && launch_fourier_table(h, slots_upper, d_nslots)) return -1;
+        if (launch_integrate(h, a, slots_upper)) return -1;
 
         PostArgs pa;
         memset(&pa, 0, sizeof pa);
         pa.n = 0; pa.list = w.cand.as<int32_t>(); pa.list_count = d_ncand;
-        pa.ym = a.ym; pa.ftab = a.ftab; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
+        pa.ym = a.ym; pa.ftab = a.ftab; pa.coef = a.coef; pa.track = a.track; pa.n_time = a.n_time; pa.status = a.status;
         pa.track_row = a.track_row; pa.pool_ctl = d_pool;
         pa.env = nullptr; pa.vmax = nullptr; pa.flags = a.flags;
         {
@@ -1211,7 +1258,7 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
         GatherArgs ga;
         memset(&ga, 0, sizeof ga);
         ga.n_years = n_years; ga.n_tracks = n_tracks; ga.row_slot = se.row_slot; ga.n_time = a.n_time;
-        ga.ym = a.ym; ga.ftab = a.ftab; ga.track = a.track; ga.track_row = a.track_row; ga.pool_ctl = d_pool;
+        ga.ym = a.ym; ga.ftab = a.ftab; ga.coef = a.coef; ga.track = a.track; ga.track_row = a.track_row; ga.pool_ctl = d_pool;
         ga.o_lon = d_lon; ga.o_lat = d_lat; ga.o_v = d_v; ga.o_m = d_m; ga.o_vmax = d_vmax; ga.o_env = d_env;
         {
             LaunchTimer lt_(h, TCR_K_GATHER);
