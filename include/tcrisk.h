@@ -302,6 +302,17 @@ int tcr_set_entropy_table(tcr_handle* h, int np, int ns, const double* p_look, c
 int tcr_thermo_month(tcr_handle* h, int64_t n_pts, int nlev, const double* p_env, const float* ta, const float* hus,
                      const double* sst, const double* psl, double ck_over_cd, int k_mid,
                      double* vmax, double* chi, double* rh_mid, int on_device);
+/* the same three fields for namelist.select_thermo = 2 (reversible thermodynamics: thermo.py:56-60, 71-75, 132-133):
+ * the inversion table is the three-dimensional one of thermo/entropy_table_reversible.npz (p [np] Pa, s [ns],
+ * rt [nrt] total water, T [np][ns][nrt]; thermo.py:279-284), read the way scipy.interpolate.interpn(method='linear',
+ * bounds_error=False, fill_value=nan) reads it (thermo.py:343-353): a level, entropy or water content outside its axis
+ * gives a NaN parcel temperature.  select_interp = 1 (BFGS inversion) exists only in the reference's unused scalar
+ * CAPE_PI (thermo.py:144-263); CAPE_PI_vectorized, the function calc_thermo.py:61 calls, has no such branch.        */
+int tcr_set_entropy_table_reversible(tcr_handle* h, int np, int ns, int nrt, const double* p_look, const double* s_look,
+                                     const double* rt_look, const double* T_lookup);
+int tcr_thermo_month_reversible(tcr_handle* h, int64_t n_pts, int nlev, const double* p_env, const float* ta, const float* hus,
+                                const double* sst, const double* psl, double ck_over_cd, int k_mid,
+                                double* vmax, double* chi, double* rh_mid, int on_device);
 
 /* page-locked host memory for the caller's input planes / result arrays (the reference's
  * NumPy arrays of util/compute.py:126-133 become views of this block): makes the host<->device

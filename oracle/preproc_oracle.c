@@ -5,7 +5,8 @@
  *
  * Follows thermo/thermo.py of the reference step by step, with the profile arrays written out
  * per level exactly as CAPE_PI_vectorized builds them (thermo.py:266-412), for the namelist
- * defaults select_thermo = 1 (pseudoadiabatic), select_interp = 2 (entropy look-up table):
+ * defaults select_thermo = 1 (pseudoadiabatic), select_interp = 2 (entropy look-up table), and, further down,
+ * for select_thermo = 2 (reversible; orc_thermo_rev):
  *   sat_thermo        thermo.py:29-39      conv_q_to_rh  thermo.py:42-47
  *   s_unsat / s_sat   thermo.py:50-76      sat_deficit   thermo.py:92-104
  *   get_LCL           thermo.py:107-127    (Romps 2017; scipy.special.lambertw branch -1)
@@ -200,6 +201,180 @@ static double th_pi_column(const th_table* tab, double cecd, double sst, double 
     double pi = sqrt(th_max(cecd * (sst / T_out_s) * cape_diff, 0));                             /* :411 */
     if (pi != pi) pi = 0;                                                                        /* :412 */
     return pi;
+}
+
+/* ============================================================================================== */
+/* select_thermo = 2 (reversible thermodynamics), select_interp = 2: the other branch of every function */
+/* above -- thermo.py:56-60, 71-75, 132-133 -- and the three-dimensional inversion table               */
+/* thermo/entropy_table_reversible.npz (p, s, rt) read through scipy.interpolate.interpn               */
+/* (thermo.py:279-284, 343-353).  Pinned against the unmodified reference with                          */
+/* namelist.select_thermo = 2 (oracle/make_golden_thermo.py -> tests/golden/ref_thermo_rev.npz).        */
+/* ============================================================================================== */
+#define TH_CPV 1870.0                  /* util/constants.py:14-17 */
+#define TH_CL 4190.0
+#define TH_LV 2.5e6
+
+typedef struct th_table3 { int np, ns, nr; const double* p; const double* s; const double* r; const double* T; } th_table3;
+
+/* thermo.py:50-60, select_thermo == 2 */
+static double th_s_unsat_rev(double T, double p, double r, double r_t)
+{
+    double es, rs;
+    th_sat(T, p, &es, &rs);
+    double rh = th_max(r / rs * (1 + rs / TH_EPS) / (1 + r / TH_EPS), 0);
+    double L = TH_LV - (TH_CPV - TH_CL) * (273.15 - T);
+    return (TH_CP + TH_CL * r_t) * tcr_log(T) - TH_RD * tcr_log(p - es * rh) + L * r / T - r * TH_RV * tcr_log(rh);
+}
+
+/* thermo.py:64-76, select_thermo == 2 (L uses the clamped T, as the reference's statement order has it) */
+static double th_s_sat_rev(double T, double p, double r_t)
+{
+    double es, rs;
+    th_sat(T, p, &es, &rs);
+    T = th_max(T, 1e-4);
+    double L = TH_LV - (TH_CPV - TH_CL) * (273.15 - T);
+    return (TH_CP + r_t * TH_CL) * tcr_log(T) - TH_RD * tcr_log(th_max(p - es, 1e-4)) + L * rs / T;
+}
+
+static double th_T_rho_rev(double T, double rv, double rt) { return T * (1 + rv / TH_EPS) / (1 + rt); }   /* thermo.py:132-133 */
+
+/* scipy.interpolate._rgi_cython.find_indices for one axis: the interval i with g[i] <= x < g[i+1] (the last one closed),
+ * clipped to [0, n-2]; norm distance y = (x - g[i]) / (g[i+1] - g[i]).  Returns 0 when x is NaN or outside the axis
+ * (RegularGridInterpolator(bounds_error=False, fill_value=nan): the result is NaN).                                   */
+static int th_rgi_cell(const double* g, int n, double x, int* i0, double* y)
+{
+    if (!(x >= g[0] && x <= g[n - 1])) return 0;
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (g[mid] <= x) lo = mid; else hi = mid;
+    }
+    if (lo > n - 2) lo = n - 2;
+    *i0 = lo;
+    *y = (x - g[lo]) / (g[lo + 1] - g[lo]);
+    return 1;
+}
+
+/* RegularGridInterpolator._evaluate_linear in three dimensions: the eight corners in itertools.product order (first axis
+ * slowest, lower corner first), weight = ((1 * w_p) * w_s) * w_rt with w = 1 - y at the lower and y at the upper node,
+ * value = value + T[corner] * weight starting from 0.                                                                  */
+static double th_lookup3(const th_table3* t, double p, double s, double r)
+{
+    int ip, is, ir; double yp, ys, yr;
+    if (!th_rgi_cell(t->p, t->np, p, &ip, &yp) || !th_rgi_cell(t->s, t->ns, s, &is, &ys) || !th_rgi_cell(t->r, t->nr, r, &ir, &yr))
+        return NAN;
+    const double wp[2] = {1 - yp, yp}, ws[2] = {1 - ys, ys}, wr[2] = {1 - yr, yr};
+    double value = 0.0;
+    for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+            for (int c = 0; c < 2; ++c) {
+                double weight = wp[a] * ws[b] * wr[c];
+                value = value + t->T[((size_t)(ip + a) * t->ns + (is + b)) * t->nr + (ir + c)] * weight;
+            }
+    return value;
+}
+
+/* test hook: th_lookup3 at n points (tests/test_preproc.py compares it bit for bit with scipy.interpolate.interpn) */
+void orc_entropy_lookup3(int64_t n, const double* p, const double* s, const double* r, int np, int ns, int nr,
+                         const double* p_look, const double* s_look, const double* r_look, const double* T_look, double* out)
+{
+    th_table3 tab = {np, ns, nr, p_look, s_look, r_look, T_look};
+    for (int64_t i = 0; i < n; ++i) out[i] = th_lookup3(&tab, p[i], s[i], r[i]);
+}
+
+/* CAPE_PI_vectorized for one column with select_thermo == 2 (thermo.py:266-412) */
+static double th_pi_column_rev(const th_table3* tab, double cecd, double sst, double p_surf, int nlev, const double* p_env,
+                               const double* dlnp, const float* T_env, const float* r_env, int64_t stride, double* w /* [7][nlev] scratch */)
+{
+    double* Te = w; double* Tre = w + nlev; double* Ta = w + 2 * nlev; double* ra = w + 3 * nlev;
+    double* Tra = w + 4 * nlev; double* Trs = w + 5 * nlev; double* Ts = w + 6 * nlev;
+    const double T_ns = (double)T_env[0], r_ns = (double)r_env[0], p_ns = p_env[0];             /* :289-291 */
+    double ess, rs;
+    th_sat(sst, p_surf, &ess, &rs);                                                              /* :293 */
+    const double rh = r_ns / rs * (1 + rs / TH_EPS) / (1 + r_ns / TH_EPS);                       /* :295 */
+    const double s_ns = th_s_unsat_rev(T_ns, p_ns, r_ns, r_ns);                                  /* :298 */
+    const double ss = th_s_sat_rev(sst, p_surf, rs);                                             /* :300 */
+    for (int k = 0; k < nlev; ++k) {
+        Te[k] = (double)T_env[k * stride];
+        Tre[k] = th_T_rho_rev(Te[k], (double)r_env[k * stride], (double)r_env[k * stride]);      /* :304 */
+    }
+    const double pLCL = th_lcl(p_ns, T_ns, r_ns, rh);                                            /* :315 */
+    int icond = nlev - 1;                                                                        /* :321-324 */
+    for (int k = 0; k < nlev; ++k) if (pLCL > p_env[k]) { icond = k; break; }
+    for (int k = 0; k < nlev; ++k) {
+        Ta[k] = T_ns * tcr_pow(p_env[k] / p_ns, TH_RD / TH_CP);                                  /* :328 */
+        ra[k] = r_ns;                                                                            /* :330 */
+    }
+    for (int k = icond; k < nlev; ++k) {                                                         /* :343-351 */
+        double es_;
+        Ta[k] = th_lookup3(tab, p_env[k], s_ns, r_ns);
+        th_sat(Ta[k], p_env[k], &es_, &ra[k]);
+    }
+    for (int k = 0; k < nlev; ++k) {
+        double es_, rsp;
+        Ts[k] = th_lookup3(tab, p_env[k], ss, rs);                                               /* :353 */
+        th_sat(Ts[k], p_env[k], &es_, &rsp);                                                     /* :355 */
+        Tra[k] = th_T_rho_rev(Ta[k], ra[k], r_ns);                                               /* :357 */
+        Trs[k] = th_T_rho_rev(Ts[k], rsp, rs);                                                   /* :358 */
+    }
+    int a_out = nlev - 1, s_out = nlev - 1;                                                      /* :361-362 */
+    for (int k = nlev - 1; k >= 0; --k) if (Tra[k] >= Tre[k]) { a_out = k; break; }
+    for (int k = nlev - 1; k >= 0; --k) if (Trs[k] >= Tre[k]) { s_out = k; break; }
+    double T_out_s = NAN, add_a = 0.0, add_s = 0.0;                                              /* :364-369 */
+    if (s_out < nlev - 1) {                                                                      /* :372-383 */
+        int k = s_out;
+        double dT1 = Trs[k] - Tre[k], dT2 = Trs[k + 1] - Tre[k + 1];
+        double p_out = (p_env[k] * dT2 - p_env[k + 1] * dT1) / (dT2 - dT1);
+        T_out_s = (Te[k] * (p_out - p_env[k + 1]) + Te[k + 1] * (p_env[k] - p_out)) / (p_env[k] - p_env[k + 1]);
+        add_s = TH_RD * dT1 * (p_env[k] - p_out) / (p_env[k] + p_out);
+    }
+    if (a_out < nlev - 1) {                                                                      /* :385-396 */
+        int k = a_out;
+        double dT1 = Tra[k] - Tre[k], dT2 = Tra[k + 1] - Tre[k + 1];
+        double p_out = (p_env[k] * dT2 - p_env[k + 1] * dT1) / (dT2 - dT1);
+        add_a = TH_RD * dT1 * (p_env[k] - p_out) / (p_env[k] + p_out);
+    }
+    double cape = 0.0, capes = 0.0;                                                              /* :398-404 */
+    for (int k = 0; k < nlev; ++k) {
+        if (k <= a_out) cape += TH_RD * (Tra[k] - Tre[k]) * -dlnp[k];
+        if (k <= s_out) capes += TH_RD * (Trs[k] - Tre[k]) * -dlnp[k];
+    }
+    cape += add_a;                                                                               /* :405-406 */
+    capes += add_s;
+    cape = th_max(cape, 0);                                                                      /* :408-409 */
+    if (cape != cape) cape = 0;
+    double cape_diff = capes - cape;
+    double pi = sqrt(th_max(cecd * (sst / T_out_s) * cape_diff, 0));                             /* :411 */
+    if (pi != pi) pi = 0;                                                                        /* :412 */
+    return pi;
+}
+
+/* orc_thermo with namelist.select_thermo = 2: table = (p [np], s [ns], rt [nr], T [np][ns][nr]) */
+void orc_thermo_rev(int64_t n_pts, int nlev, const double* p_env, const float* ta, const float* hus, const double* sst,
+                    const double* psl, int np, int ns, int nr, const double* p_look, const double* s_look, const double* r_look,
+                    const double* T_look, double cecd, int k_mid, double p_mid, double* vmax, double* chi, double* rh_mid)
+{
+    th_table3 tab = {np, ns, nr, p_look, s_look, r_look, T_look};
+    double* dlnp = (double*)malloc(sizeof(double) * (size_t)nlev * 9);
+    double* lnp = dlnp + nlev;
+    double* w = dlnp + 2 * nlev;
+    for (int k = 0; k < nlev; ++k) lnp[k] = tcr_log(p_env[k]);                                   /* thermo.py:302-303 */
+    for (int k = 0; k + 1 < nlev; ++k) dlnp[k] = lnp[k + 1] - lnp[k];
+    dlnp[nlev - 1] = (2 * lnp[nlev - 1] - lnp[nlev - 2]) - lnp[nlev - 1];
+    for (int64_t c = 0; c < n_pts; ++c) {
+        vmax[c] = th_pi_column_rev(&tab, cecd, sst[c], psl[c], nlev, p_env, dlnp, ta + c, hus + c, n_pts, w);
+        const double Tm = (double)ta[(size_t)k_mid * n_pts + c], qm = (double)hus[(size_t)k_mid * n_pts + c];
+        /* sat_deficit (thermo.py:92-104): all three entropies carry the MID-LEVEL mixing ratio as total water */
+        double sp = th_s_unsat_rev(Tm, p_mid, qm, qm);
+        double sps = th_s_sat_rev(Tm, p_mid, qm);
+        double spss = th_s_sat_rev(sst[c], psl[c], qm);
+        chi[c] = th_min(th_max((sps - sp) / (spss - sps), 0), 10);
+        double es, rs;
+        th_sat(Tm, p_mid, &es, &rs);                                                             /* conv_q_to_rh, thermo.py:42-47 */
+        double qs = rs / (1 + rs);
+        rh_mid[c] = th_min(th_max(qm / qs, 1e-5), 1);
+    }
+    free(dlnp);
 }
 
 /* One time sample of compute_thermo (calc_thermo.py:60-69): vmax, chi, rh_mid for n_pts columns.

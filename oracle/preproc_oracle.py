@@ -73,7 +73,10 @@ def wind_stats(series, group_start):
 def thermo(p_env, ta, hus, sst, psl, table, cecd, k_mid):
     """vmax (potential intensity), chi, rh_mid for every column -- one time sample of compute_thermo
     (thermo/calc_thermo.py:60-69).  ta, hus [nlev, n] float32 (lowest level first), p_env [nlev] Pa,
-    sst / psl [n]; table = (p_look, s_look, T_lookup) of thermo/entropy_table.npz."""
+    sst / psl [n]; table = (p_look, s_look, T_lookup) of thermo/entropy_table.npz (select_thermo = 1) or
+    (p_look, s_look, rt_look, T_lookup) of thermo/entropy_table_reversible.npz (select_thermo = 2)."""
+    if len(table) == 4:
+        return _thermo_rev(p_env, ta, hus, sst, psl, table, cecd, k_mid)
     import ctypes as C
     from oracle import tcr_oracle
     lib = tcr_oracle.lib()
@@ -95,3 +98,43 @@ def thermo(p_env, ta, hus, sst, psl, table, cecd, k_mid):
                    pl.size, sl.size, pl.ctypes.data, sl.ctypes.data, tl.ctypes.data, float(cecd), int(k_mid),
                    float(p_env[k_mid]), *[o.ctypes.data for o in out])
     return tuple(out)
+
+
+def _thermo_rev(p_env, ta, hus, sst, psl, table, cecd, k_mid):
+    import ctypes as C
+    from oracle import tcr_oracle
+    lib = tcr_oracle.lib()
+    p_env = np.ascontiguousarray(p_env, dtype=np.float64)
+    sst = np.ascontiguousarray(sst, dtype=np.float64).reshape(-1)
+    psl = np.ascontiguousarray(psl, dtype=np.float64).reshape(-1)
+    nlev, n = p_env.size, sst.size
+    ta = np.ascontiguousarray(ta, dtype=np.float32).reshape(nlev, n)
+    hus = np.ascontiguousarray(hus, dtype=np.float32).reshape(nlev, n)
+    pl, sl, rl, tl = (np.ascontiguousarray(a, dtype=np.float64) for a in table)
+    assert tl.shape == (pl.size, sl.size, rl.size)
+    out = [np.empty(n) for _ in range(3)]
+    vp = C.c_void_p
+    lib.orc_thermo_rev.restype = None
+    lib.orc_thermo_rev.argtypes = [C.c_int64, C.c_int, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_double,
+                                   C.c_int, C.c_double] + [vp] * 3
+    lib.orc_thermo_rev(n, nlev, p_env.ctypes.data, ta.ctypes.data, hus.ctypes.data, sst.ctypes.data, psl.ctypes.data,
+                       pl.size, sl.size, rl.size, pl.ctypes.data, sl.ctypes.data, rl.ctypes.data, tl.ctypes.data, float(cecd),
+                       int(k_mid), float(p_env[k_mid]), *[o.ctypes.data for o in out])
+    return tuple(out)
+
+
+def entropy_lookup3(p, s, r, table):
+    """T(p, s, rt) from the reversible inversion table the way scipy.interpolate.interpn(method='linear',
+    bounds_error=False, fill_value=nan) evaluates it (test hook of the restatement in preproc_oracle.c)."""
+    import ctypes as C
+    from oracle import tcr_oracle
+    lib = tcr_oracle.lib()
+    p, s, r = (np.ascontiguousarray(a, dtype=np.float64).reshape(-1) for a in (p, s, r))
+    pl, sl, rl, tl = (np.ascontiguousarray(a, dtype=np.float64) for a in table)
+    out = np.empty(p.size)
+    vp = C.c_void_p
+    lib.orc_entropy_lookup3.restype = None
+    lib.orc_entropy_lookup3.argtypes = [C.c_int64, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    lib.orc_entropy_lookup3(p.size, p.ctypes.data, s.ctypes.data, r.ctypes.data, pl.size, sl.size, rl.size,
+                            pl.ctypes.data, sl.ctypes.data, rl.ctypes.data, tl.ctypes.data, out.ctypes.data)
+    return out

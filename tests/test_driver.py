@@ -19,7 +19,7 @@ class OracleEngine:
         n = ua.shape[0]
         return po.wind_stats([a[:, k].reshape(n, -1) for k in (iu, il) for a in (ua, va)], gs)
 
-    def thermo_month(self, p_env, ta, hus, sst, psl, cecd, k_mid):
+    def thermo_month(self, p_env, ta, hus, sst, psl, cecd, k_mid, select_thermo=1):
         out = po.thermo(p_env, ta, hus, sst, psl, self.table, cecd, k_mid)
         return tuple(o.reshape(np.shape(sst)) for o in out)
 

@@ -228,6 +228,95 @@ def test_thermo_oracle_against_live_reference_if_present():
     _assert_close_to_reference(v, want.reshape(-1), 1e-11, 1e-11, "vmax")
 
 
+# ---- namelist.select_thermo = 2 (reversible thermodynamics, three-dimensional inversion table) ----
+def _thermo_rev_golden():
+    from conftest import golden
+    g = golden("ref_thermo_rev.npz")
+    return g, (g["table_p"], g["table_s"], g["table_rt"], g["table_T"])
+
+
+def test_thermo_reversible_oracle_matches_reference_golden():
+    """The same kind of soundings through the unmodified reference with namelist.select_thermo = 2
+    (oracle/make_golden_thermo.py --reversible): identical NaN / zero pattern, PI within 1e-10 relative."""
+    g, table = _thermo_rev_golden()
+    v, c, r = po.thermo(g["p"], g["ta"], g["hus"], g["sst"], g["psl"], table, float(g["cecd"]), int(g["k_mid"]))
+    _assert_close_to_reference(v, g["vmax"], 1e-10, 1e-10, "vmax")
+    assert np.array_equal(v == 0, g["vmax"] == 0)
+    _assert_close_to_reference(c, g["chi"], 1e-10, 1e-12, "chi")
+    _assert_close_to_reference(r, g["rh_mid"], 1e-13, 0, "rh_mid")
+    assert (g["vmax"] > 30).sum() > 500 and (g["vmax"] == 0).sum() > 50
+    # the two thermodynamics differ: this is not the pseudoadiabatic answer under another name
+    g1, t1 = _thermo_golden()
+    v1, _, _ = po.thermo(g["p"], g["ta"], g["hus"], g["sst"], g["psl"], t1, float(g["cecd"]), int(g["k_mid"]))
+    assert np.nanmax(np.abs(v1 - v)) > 1.0
+
+
+def test_entropy_lookup3_is_scipy_interpn_bit_for_bit():
+    """thermo.py:343-353 reads the reversible table through scipy.interpolate.interpn(method='linear', bounds_error=False,
+    fill_value=nan): the restatement (interval search, norm distances, corner order, weight products) against scipy itself on
+    random points, exact nodes, both ends of every axis, points outside and NaNs."""
+    from scipy.interpolate import interpn
+    _, table = _thermo_rev_golden()
+    pl, sl, rl, T = table
+    rng = np.random.default_rng(3)
+    n = 20000
+    p = rng.uniform(pl[0] - 2000.0, pl[-1] + 2000.0, n)
+    s = rng.uniform(sl[0] - 20.0, sl[-1] + 20.0, n)
+    r = rng.uniform(-0.001, rl[-1] + 0.002, n)
+    p[:40] = np.repeat(pl[[0, -1, 5, 17]], 10); s[:40:3] = sl[[0, -1, 9, 2, 30, 33, 1, 0, -1, 12, 4, 8, 20, 21]]
+    r[1:40:4] = rl[[0, -1, 3, 24, 0, 11, 12, 1, -1, 7]]
+    p[40], s[41], r[42] = np.nan, np.nan, np.nan
+    p[43], s[44], r[45] = np.inf, -np.inf, np.inf
+    want = interpn((pl, sl, rl), T, (p, s, r), method="linear", bounds_error=False, fill_value=np.nan)
+    got = po.entropy_lookup3(p, s, r, table)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.isnan(want).sum() > 1000 and (~np.isnan(want)).sum() > 10000
+
+
+def test_thermo_reversible_oracle_against_live_reference_if_present():
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference tree not present")
+    import tempfile
+    import warnings
+    from tropical_cyclone_risk_b200 import synth_thermo
+    ref = rh.load_reference()
+    nl = ref.namelist
+    _, table = _thermo_rev_golden()
+    p, ta, hus, sst, psl = synth_thermo.soundings(4096, seed=123)
+    shp = (64, 64)
+    saved = (nl.select_thermo, nl.src_directory)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "thermo"))
+        np.savez(os.path.join(tmp, "thermo", "entropy_table_reversible.npz"), p=table[0], s=table[1], rt=table[2], T=table[3])
+        nl.select_thermo, nl.src_directory = 2, tmp
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                want = ref.thermo.CAPE_PI_vectorized(sst.reshape(shp), psl.reshape(shp), p.copy(), ta.astype(np.float64).reshape((-1,) + shp),
+                                                     hus.astype(np.float64).reshape((-1,) + shp))
+        finally:
+            nl.select_thermo, nl.src_directory = saved
+    v, _, _ = po.thermo(p, ta, hus, sst, psl, table, nl.Ck / nl.Cd, 13)
+    _assert_close_to_reference(v, want.reshape(-1), 1e-10, 1e-10, "vmax")
+
+
+def test_compute_thermo_refuses_what_the_reference_cannot_run():
+    """select_interp = 1 has no branch in CAPE_PI_vectorized (thermo.py:266: the table is not loaded and f_lookup fails);
+    select_thermo outside {1, 2} leaves s undefined in s_unsat (thermo.py:53-60)."""
+    import types
+    from tropical_cyclone_risk_b200 import preproc
+    from tropical_cyclone_risk_b200 import namelist as nl
+    z = np.zeros((1, 2, 2, 2), dtype=np.float32)
+    bad = types.SimpleNamespace(**{k: getattr(nl, k) for k in dir(nl) if not k.startswith("__")})
+    bad.select_interp = 1
+    with pytest.raises(NotImplementedError):
+        preproc.compute_thermo(None, z[:, 0], z[:, 0], z, z, [1000, 900], bad)
+    bad.select_interp, bad.select_thermo = 2, 3
+    with pytest.raises(ValueError):
+        preproc.compute_thermo(None, z[:, 0], z[:, 0], z, z, [1000, 900], bad)
+
+
 def test_order_levels():
     from tropical_cyclone_risk_b200 import preproc
     ta = np.arange(2 * 3 * 2 * 2, dtype=np.float32).reshape(2, 3, 2, 2)
@@ -295,6 +384,60 @@ def test_gpu_compute_thermo_mirror(engine):
 
 
 @pytest.mark.gpu
+def test_gpu_thermo_reversible_bit_exact_vs_oracle_and_close_to_reference(engine):
+    """namelist.select_thermo = 2: k_thermo<true> against the oracle bit for bit and against the unmodified reference."""
+    g, table = _thermo_rev_golden()
+    engine.set_entropy_table_reversible(*table)
+    got = engine.thermo_month(g["p"], g["ta"], g["hus"], g["sst"], g["psl"], float(g["cecd"]), int(g["k_mid"]), select_thermo=2)
+    want = po.thermo(g["p"], g["ta"], g["hus"], g["sst"], g["psl"], table, float(g["cecd"]), int(g["k_mid"]))
+    for name, a, b in zip(("vmax", "chi", "rh_mid"), got, want):
+        assert np.array_equal(a, b, equal_nan=True), name
+    _assert_close_to_reference(got[0], g["vmax"], 1e-9, 1e-9, "vmax vs reference")
+    _assert_close_to_reference(got[1], g["chi"], 1e-9, 1e-12, "chi vs reference")
+    _assert_close_to_reference(got[2], g["rh_mid"], 1e-12, 0, "rh_mid vs reference")
+    # the pseudoadiabatic table of the same handle is untouched by the reversible one
+    g1, t1 = _thermo_golden()
+    engine.set_entropy_table(*t1)
+    a = engine.thermo_month(g1["p"], g1["ta"], g1["hus"], g1["sst"], g1["psl"], float(g1["cecd"]), int(g1["k_mid"]))
+    b = po.thermo(g1["p"], g1["ta"], g1["hus"], g1["sst"], g1["psl"], t1, float(g1["cecd"]), int(g1["k_mid"]))
+    assert np.array_equal(a[0], b[0], equal_nan=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nlev_cut", [(1, 0), (129, 0), (5000, 6), (40000, 0)])
+def test_gpu_thermo_reversible_other_shapes(engine, n, nlev_cut):
+    from tropical_cyclone_risk_b200 import synth_thermo
+    _, table = _thermo_rev_golden()
+    engine.set_entropy_table_reversible(*table)
+    p, ta, hus, sst, psl = synth_thermo.soundings(n, seed=1000 + n, edge_cases=n >= 64)
+    if nlev_cut:
+        p, ta, hus = p[:-nlev_cut], ta[:-nlev_cut], hus[:-nlev_cut]
+    got = engine.thermo_month(p, ta, hus, sst, psl, 0.9, 11, select_thermo=2)
+    want = po.thermo(p, ta, hus, sst, psl, table, 0.9, 11)
+    for name, a, b in zip(("vmax", "chi", "rh_mid"), got, want):
+        assert np.array_equal(a, b, equal_nan=True), name
+
+
+@pytest.mark.gpu
+def test_gpu_compute_thermo_mirror_reversible(engine):
+    """compute_thermo with a namelist that says select_thermo = 2."""
+    import types
+    from tropical_cyclone_risk_b200 import preproc, synth_thermo
+    from tropical_cyclone_risk_b200 import namelist as nl
+    nl2 = types.SimpleNamespace(**{k: getattr(nl, k) for k in dir(nl) if not k.startswith("__")})
+    nl2.select_thermo = 2
+    _, table = _thermo_rev_golden()
+    engine.set_entropy_table_reversible(*table)
+    nlat, nlon = 6, 10
+    p, ta, hus, sst, psl = synth_thermo.soundings(nlat * nlon, seed=6, edge_cases=False)
+    got = preproc.compute_thermo(engine, sst.reshape(1, nlat, nlon), psl.reshape(1, nlat, nlon), ta.reshape(1, -1, nlat, nlon),
+                                 hus.reshape(1, -1, nlat, nlon), p, nl2, "Pa", "K")
+    want = po.thermo(p, ta, hus, sst, psl, table, nl.Ck / nl.Cd, 13)
+    for a, b in zip(got, want):
+        assert np.array_equal(a[0].reshape(-1), b, equal_nan=True)
+
+
+@pytest.mark.gpu
 def test_gpu_thermo_rejects_bad_input(engine):
     from tropical_cyclone_risk_b200._lib import TcrError
     from tropical_cyclone_risk_b200 import synth_thermo
@@ -316,7 +459,7 @@ class _OracleEngine:
     def wind_stats(self, ua, va, iu, il, gs):
         return po.wind_stats(series_of(ua, va, iu, il), gs)
 
-    def thermo_month(self, p_env, ta, hus, sst, psl, cecd, k_mid):
+    def thermo_month(self, p_env, ta, hus, sst, psl, cecd, k_mid, select_thermo=1):
         _, table = _thermo_golden()
         out = po.thermo(p_env, ta, hus, sst, psl, table, cecd, k_mid)
         return tuple(o.reshape(np.shape(sst)) for o in out)

@@ -15,7 +15,7 @@ SYMBOLS = (
     "tcr_env_interp", "tcr_integrate", "tcr_run_years", "tcr_seed_attempts", "tcr_set_tuning",
     "tcr_launch_count", "tcr_set_interp_variant", "tcr_host_alloc", "tcr_host_free",
     "tcr_set_timing", "tcr_kernel_time", "tcr_poi_vmax", "tcr_exceedance", "tcr_prepare_month",
-    "tcr_wind_stats", "tcr_set_entropy_table", "tcr_thermo_month", "tcr_rhs_eval", "tcr_set_shard",
+    "tcr_wind_stats", "tcr_set_entropy_table", "tcr_thermo_month", "tcr_set_entropy_table_reversible", "tcr_thermo_month_reversible", "tcr_rhs_eval", "tcr_set_shard",
 )
 
 _lib = None
@@ -71,6 +71,8 @@ def load():
     lib.tcr_wind_stats.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, vp, vp, vp, vp, C.c_int, vp, vp, C.c_int]
     lib.tcr_set_entropy_table.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
     lib.tcr_thermo_month.argtypes = [vp, C.c_int64, C.c_int, vp, vp, vp, vp, vp, C.c_double, C.c_int, vp, vp, vp, C.c_int]
+    lib.tcr_set_entropy_table_reversible.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp]
+    lib.tcr_thermo_month_reversible.argtypes = lib.tcr_thermo_month.argtypes
     lib.tcr_rhs_eval.argtypes = [vp, C.c_int64] + [vp] * 7
     lib.tcr_set_shard.argtypes = [vp, C.c_int, C.c_int, ALLREDUCE_FN, vp]
     lib.tcr_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]

@@ -349,7 +349,7 @@ struct ThLevel {            /* per pressure level, column independent */
     double mdlnp;           /* -dlnp[k]                    (thermo.py:302-303, 401-404)  */
     double dry;             /* (p / p_ns)^(Rd/cp)          (thermo.py:328)               */
     double wp0, wp1;        /* table weights on the pressure axis                        */
-    int ip, pad;            /* table cell on the pressure axis                           */
+    int ip, pad;            /* table cell on the pressure axis; reversible table: pad = 1 when p lies inside the axis */
 };
 
 struct ThermoArgs {
@@ -361,6 +361,7 @@ struct ThermoArgs {
     ThLevel* lev;                             /* [nlev]                                   */
     int np, ns;
     const double* p_look; const double* s_look; const double* T_look;    /* entropy table [np][ns] */
+    int nr; const double* r_look;     /* select_thermo = 2: total-water axis, T_look [np][ns][nr] (0 / NULL: pseudoadiabatic) */
     double cecd, p_mid;
     double* vmax; double* chi; double* rh_mid;
 };
@@ -384,6 +385,25 @@ __device__ __forceinline__ void th_locate(const double* __restrict__ ax, int n, 
     w1 = f * (a - x0);
 }
 
+/* scipy.interpolate._rgi_cython.find_indices for one axis (the reversible table is read through interpn, thermo.py:343-353):
+ * interval i with g[i] <= x < g[i+1] (the last one closed), norm distance y = (x - g[i]) / (g[i+1] - g[i]); false when x is
+ * NaN or outside the axis (bounds_error=False, fill_value=nan) */
+__device__ __forceinline__ bool th_rgi_cell(const double* __restrict__ g, int n, double x, int& i0, double& y)
+{
+    i0 = 0; y = 0.0;
+    if (!(x >= __ldg(g) && x <= __ldg(g + n - 1))) return false;
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(g + mid) <= x) lo = mid; else hi = mid;
+    }
+    if (lo > n - 2) lo = n - 2;
+    const double x0 = __ldg(g + lo), x1 = __ldg(g + lo + 1);
+    i0 = lo;
+    y = (x - x0) / (x1 - x0);
+    return true;
+}
+
 __global__ void k_thermo_levels(const ThermoArgs A)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -397,8 +417,14 @@ __global__ void k_thermo_levels(const ThermoArgs A)
     L.p = p;
     L.mdlnp = -dlnp;
     L.dry = tcr_pow(p / A.p_env[0], TH_RD / TH_CP);
-    th_locate(A.p_look, A.np, p, L.ip, L.wp0, L.wp1);
     L.pad = 0;
+    if (A.nr > 0) {
+        double y;
+        L.pad = th_rgi_cell(A.p_look, A.np, p, L.ip, y) ? 1 : 0;
+        L.wp0 = 1 - y; L.wp1 = y;
+    } else {
+        th_locate(A.p_look, A.np, p, L.ip, L.wp0, L.wp1);
+    }
     A.lev[k] = L;
 }
 
@@ -437,6 +463,49 @@ __device__ __forceinline__ double th_s_sat(double T, double p)
     return TH_CP * tcr_log(T) - TH_RD * tcr_log(th_fmax(p - es, 1e-4)) + TH_L0 * rs / T;
 }
 
+/* select_thermo = 2 (reversible): thermo.py:56-60, 71-75, 132-133; util/constants.py:14-17 */
+#define TH_CPV 1870.0
+#define TH_CL 4190.0
+#define TH_LV 2.5e6
+__device__ __forceinline__ double th_s_unsat_rev(double T, double p, double r, double r_t)
+{
+    double es, rs;
+    th_sat(T, p, es, rs);
+    const double rh = th_fmax(r / rs * (1 + rs / TH_EPS) / (1 + r / TH_EPS), 0);
+    const double L = TH_LV - (TH_CPV - TH_CL) * (273.15 - T);
+    return (TH_CP + TH_CL * r_t) * tcr_log(T) - TH_RD * tcr_log(p - es * rh) + L * r / T - r * TH_RV * tcr_log(rh);
+}
+
+__device__ __forceinline__ double th_s_sat_rev(double T, double p, double r_t)
+{
+    double es, rs;
+    th_sat(T, p, es, rs);
+    T = th_fmax(T, 1e-4);
+    const double L = TH_LV - (TH_CPV - TH_CL) * (273.15 - T);
+    return (TH_CP + r_t * TH_CL) * tcr_log(T) - TH_RD * tcr_log(th_fmax(p - es, 1e-4)) + L * rs / T;
+}
+
+__device__ __forceinline__ double th_t_rho_rev(double T, double rv, double rt) { return T * (1 + rv / TH_EPS) / (1 + rt); }
+
+/* RegularGridInterpolator._evaluate_linear over (p, s, rt): eight corners in itertools.product order, weight =
+ * (w_p * w_s) * w_rt, value = value + T[corner] * weight from 0 */
+__device__ __forceinline__ double th_lookup3(const double* __restrict__ T, int ns, int nr, int ip, double wp0, double wp1,
+                                             int is, double ys, int ir, double yr)
+{
+    const double wp[2] = {wp0, wp1}, ws[2] = {1 - ys, ys}, wr[2] = {1 - yr, yr};
+    double value = 0.0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const double weight = wp[a] * ws[b] * wr[c];
+                value = value + __ldg(T + ((size_t)(ip + a) * ns + (is + b)) * nr + (ir + c)) * weight;
+            }
+    return value;
+}
+
 /* real branch -1 of the Lambert W function on [-1/e, 0): scipy.special.lambertw(z, -1) as get_LCL uses it
  * (thermo.py:124): first guess log(-z), Halley steps to the routine's default tolerance 1e-8 */
 __device__ __forceinline__ double th_lambertw_m1(double z)
@@ -471,6 +540,7 @@ struct ThParcel {
     }
 };
 
+template <bool REV>
 __global__ void __launch_bounds__(128) k_thermo(const ThermoArgs A)
 {
     __shared__ ThLevel lev[TH_MAX_LEVELS];
@@ -486,8 +556,8 @@ __global__ void __launch_bounds__(128) k_thermo(const ThermoArgs A)
     double ess, rs;
     th_sat(sst, p_surf, ess, rs);                                                       /* thermo.py:293 */
     const double rh = r_ns / rs * (1 + rs / TH_EPS) / (1 + r_ns / TH_EPS);              /* :295 */
-    const double s_ns = th_s_unsat(T_ns, p_ns, r_ns);                                   /* :298 */
-    const double ss = th_s_sat(sst, p_surf);                                            /* :300 */
+    const double s_ns = REV ? th_s_unsat_rev(T_ns, p_ns, r_ns, r_ns) : th_s_unsat(T_ns, p_ns, r_ns);   /* :298 */
+    const double ss = REV ? th_s_sat_rev(sst, p_surf, rs) : th_s_sat(sst, p_surf);      /* :300 */
     /* get_LCL (thermo.py:107-127) */
     double pLCL;
     {
@@ -504,8 +574,19 @@ __global__ void __launch_bounds__(128) k_thermo(const ThermoArgs A)
     /* entropy-axis cells of the two parcels */
     int is_a, is_s;
     double wa0, wa1, wsa0, wsa1;
-    th_locate(A.s_look, ns, s_ns, is_a, wa0, wa1);
-    th_locate(A.s_look, ns, ss, is_s, wsa0, wsa1);
+    int ir_a = 0, ir_s = 0;                    /* reversible table: total-water cells (r_ns for the boundary-layer parcel, rs for the */
+    double yr_a = 0.0, yr_s = 0.0;             /* saturated one, thermo.py:346-353), norm distances instead of FITPACK weights         */
+    bool ok_a = true, ok_s = true;
+    if constexpr (REV) {
+        ok_a = th_rgi_cell(A.s_look, ns, s_ns, is_a, wa1);
+        ok_a = th_rgi_cell(A.r_look, A.nr, r_ns, ir_a, yr_a) && ok_a;
+        ok_s = th_rgi_cell(A.s_look, ns, ss, is_s, wsa1);
+        ok_s = th_rgi_cell(A.r_look, A.nr, rs, ir_s, yr_s) && ok_s;
+        wa0 = wsa0 = 0.0;
+    } else {
+        th_locate(A.s_look, ns, s_ns, is_a, wa0, wa1);
+        th_locate(A.s_look, ns, ss, is_s, wsa0, wsa1);
+    }
 
     ThParcel pa, ps;
     pa.init(); ps.init();
@@ -525,7 +606,11 @@ __global__ void __launch_bounds__(128) k_thermo(const ThermoArgs A)
         cond = cond || (pLCL > L.p) || (k == nlev - 1);
         const double* t0 = A.T_look + (size_t)L.ip * ns;
         double Ta, ra;
-        if (cond) {                                                                      /* :333-340: moist adiabat from the table */
+        if (REV && cond) {                                                               /* :343-351 */
+            Ta = (L.pad && ok_a) ? th_lookup3(A.T_look, ns, A.nr, L.ip, L.wp0, L.wp1, is_a, wa1, ir_a, yr_a) : NAN;
+            double es_;
+            th_sat(Ta, L.p, es_, ra);
+        } else if (cond) {                                                               /* :333-340: moist adiabat from the table */
             const double* r0 = t0 + is_a;
             const double* r1 = r0 + ns;
             double sp = 0.0;
@@ -541,7 +626,11 @@ __global__ void __launch_bounds__(128) k_thermo(const ThermoArgs A)
             ra = r_ns;
         }
         double Ts, rsp;
-        {
+        if constexpr (REV) {                                                             /* :353 */
+            Ts = (L.pad && ok_s) ? th_lookup3(A.T_look, ns, A.nr, L.ip, L.wp0, L.wp1, is_s, wsa1, ir_s, yr_s) : NAN;
+            double es_;
+            th_sat(Ts, L.p, es_, rsp);
+        } else {
             const double* r0 = t0 + is_s;                                                /* :342 */
             const double* r1 = r0 + ns;
             double sp = 0.0;
@@ -553,8 +642,8 @@ __global__ void __launch_bounds__(128) k_thermo(const ThermoArgs A)
             double es_;
             th_sat(Ts, L.p, es_, rsp);                                                   /* :355 */
         }
-        pa.level(k, th_t_rho(Ta, ra), Tre, Te, L.mdlnp);                                 /* :357, 361, 401-402 */
-        ps.level(k, th_t_rho(Ts, rsp), Tre, Te, L.mdlnp);                                /* :358, 362, 403-404 */
+        pa.level(k, REV ? th_t_rho_rev(Ta, ra, r_ns) : th_t_rho(Ta, ra), Tre, Te, L.mdlnp);     /* :357, 361, 401-402 */
+        ps.level(k, REV ? th_t_rho_rev(Ts, rsp, rs) : th_t_rho(Ts, rsp), Tre, Te, L.mdlnp);      /* :358, 362, 403-404 */
     }
     /* outflow level by linear interpolation between `out` and the level above it (:372-396) */
     double T_out_s = NAN, add_a = 0.0, add_s = 0.0;
@@ -579,9 +668,10 @@ __global__ void __launch_bounds__(128) k_thermo(const ThermoArgs A)
     __stcs(A.vmax + c, pi);
 
     /* sat_deficit (thermo.py:92-104) clipped to [0, 10] (calc_thermo.py:68); conv_q_to_rh (thermo.py:42-47) */
-    const double sp_ = th_s_unsat(Tm, A.p_mid, qm);
-    const double sps = th_s_sat(Tm, A.p_mid);
-    const double spss = ss;                                                              /* s_sat(sst, psl): the same call as :300 */
+    /* reversible: all three entropies carry the mid-level mixing ratio as total water (thermo.py:97-101) */
+    const double sp_ = REV ? th_s_unsat_rev(Tm, A.p_mid, qm, qm) : th_s_unsat(Tm, A.p_mid, qm);
+    const double sps = REV ? th_s_sat_rev(Tm, A.p_mid, qm) : th_s_sat(Tm, A.p_mid);
+    const double spss = REV ? th_s_sat_rev(sst, p_surf, qm) : ss;                        /* pseudoadiabatic: s_sat(sst, psl), the same call as :300 */
     __stcs(A.chi + c, th_fmin(th_fmax((sps - sp_) / (spss - sps), 0), 10));
     double es, rsm;
     th_sat(Tm, A.p_mid, es, rsm);

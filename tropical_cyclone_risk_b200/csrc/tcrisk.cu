@@ -128,6 +128,8 @@ struct tcr_handle {
     DevBuf bathy, land, masks;
     DevBuf etab;                 /* entropy look-up table of the thermo kernel: p_look | s_look | T_lookup */
     int etab_np = 0, etab_ns = 0;
+    DevBuf etab3;                /* reversible table (select_thermo = 2): p_look | s_look | rt_look | T_lookup [np][ns][nr] */
+    int etab3_np = 0, etab3_ns = 0, etab3_nr = 0;
     AxisBuf ax_lon_b, ax_lat_b, ax_lon_l, ax_lat_l, ax_lon_m, ax_lat_m;
     bool have_static = false, have_masks = false;
     /* tuning */
@@ -1566,12 +1568,34 @@ int tcr_set_entropy_table(tcr_handle* h, int np, int ns, const double* p_look, c
     return 0;
 }
 
-int tcr_thermo_month(tcr_handle* h, int64_t n_pts, int nlev, const double* p_env, const float* ta, const float* hus,
-                     const double* sst, const double* psl, double ck_over_cd, int k_mid,
-                     double* vmax, double* chi, double* rh_mid, int on_device)
+int tcr_set_entropy_table_reversible(tcr_handle* h, int np, int ns, int nrt, const double* p_look, const double* s_look,
+                                     const double* rt_look, const double* T_lookup)
 {
     if (!h) return set_err("null handle");
-    if (!h->etab.p) return set_err("tcr_thermo_month: call tcr_set_entropy_table first");
+    if (np < 2 || ns < 2 || nrt < 2 || !p_look || !s_look || !rt_look || !T_lookup) return set_err("tcr_set_entropy_table_reversible: bad argument");
+    for (int i = 1; i < np; ++i) if (!(p_look[i] > p_look[i - 1])) return set_err("tcr_set_entropy_table_reversible: pressure axis must ascend");
+    for (int i = 1; i < ns; ++i) if (!(s_look[i] > s_look[i - 1])) return set_err("tcr_set_entropy_table_reversible: entropy axis must ascend");
+    for (int i = 1; i < nrt; ++i) if (!(rt_look[i] > rt_look[i - 1])) return set_err("tcr_set_entropy_table_reversible: total-water axis must ascend");
+    CK(cudaSetDevice(h->device));
+    const size_t nT = (size_t)np * ns * nrt, n = (size_t)np + ns + nrt + nT;
+    if (h->etab3.ensure(n * sizeof(double))) return -1;
+    double* d = h->etab3.as<double>();
+    CK(cudaMemcpyAsync(d, p_look, (size_t)np * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + np, s_look, (size_t)ns * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + np + ns, rt_look, (size_t)nrt * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d + np + ns + nrt, T_lookup, nT * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->etab3_np = np; h->etab3_ns = ns; h->etab3_nr = nrt;
+    return 0;
+}
+
+static int thermo_month_impl(tcr_handle* h, bool rev, int64_t n_pts, int nlev, const double* p_env, const float* ta, const float* hus,
+                             const double* sst, const double* psl, double ck_over_cd, int k_mid,
+                             double* vmax, double* chi, double* rh_mid, int on_device)
+{
+    if (!h) return set_err("null handle");
+    if (!rev && !h->etab.p) return set_err("tcr_thermo_month: call tcr_set_entropy_table first");
+    if (rev && !h->etab3.p) return set_err("tcr_thermo_month_reversible: call tcr_set_entropy_table_reversible first");
     if (n_pts <= 0 || nlev < 2 || nlev > TH_MAX_LEVELS || k_mid < 0 || k_mid >= nlev) return set_err("tcr_thermo_month: bad shape (2..%d levels)", TH_MAX_LEVELS);
     if (!p_env || !ta || !hus || !sst || !psl || !vmax || !chi || !rh_mid) return set_err("tcr_thermo_month: null argument");
     for (int k = 1; k < nlev; ++k)
@@ -1586,8 +1610,13 @@ int tcr_thermo_month(tcr_handle* h, int64_t n_pts, int nlev, const double* p_env
     ThermoArgs a;
     memset(&a, 0, sizeof a);
     a.n_pts = n_pts; a.nlev = nlev; a.k_mid = k_mid; a.p_env = d_p; a.lev = lv.as<ThLevel>();
-    a.np = h->etab_np; a.ns = h->etab_ns;
-    a.p_look = h->etab.as<double>(); a.s_look = a.p_look + a.np; a.T_look = a.s_look + a.ns;
+    if (rev) {
+        a.np = h->etab3_np; a.ns = h->etab3_ns; a.nr = h->etab3_nr;
+        a.p_look = h->etab3.as<double>(); a.s_look = a.p_look + a.np; a.r_look = a.s_look + a.ns; a.T_look = a.r_look + a.nr;
+    } else {
+        a.np = h->etab_np; a.ns = h->etab_ns;
+        a.p_look = h->etab.as<double>(); a.s_look = a.p_look + a.np; a.T_look = a.s_look + a.ns;
+    }
     a.cecd = ck_over_cd; a.p_mid = p_env[k_mid];
     if (on_device) {
         a.ta = ta; a.hus = hus; a.sst = sst; a.psl = psl; a.vmax = vmax; a.chi = chi; a.rh_mid = rh_mid;
@@ -1606,7 +1635,8 @@ int tcr_thermo_month(tcr_handle* h, int64_t n_pts, int nlev, const double* p_env
     {
         LaunchTimer lt_(h, TCR_K_THERMO);
         k_thermo_levels<<<1, TH_MAX_LEVELS, 0, s>>>(a);
-        k_thermo<<<(unsigned)((n_pts + 127) / 128), 128, 0, s>>>(a);
+        if (rev) k_thermo<true><<<(unsigned)((n_pts + 127) / 128), 128, 0, s>>>(a);
+        else k_thermo<false><<<(unsigned)((n_pts + 127) / 128), 128, 0, s>>>(a);
     }
     CKK(h);
     h->launches++;
@@ -1618,6 +1648,20 @@ int tcr_thermo_month(tcr_handle* h, int64_t n_pts, int nlev, const double* p_env
     CK(cudaStreamSynchronize(s));
     lv.release(); in.release(); o.release();
     return 0;
+}
+
+int tcr_thermo_month(tcr_handle* h, int64_t n_pts, int nlev, const double* p_env, const float* ta, const float* hus,
+                     const double* sst, const double* psl, double ck_over_cd, int k_mid,
+                     double* vmax, double* chi, double* rh_mid, int on_device)
+{
+    return thermo_month_impl(h, false, n_pts, nlev, p_env, ta, hus, sst, psl, ck_over_cd, k_mid, vmax, chi, rh_mid, on_device);
+}
+
+int tcr_thermo_month_reversible(tcr_handle* h, int64_t n_pts, int nlev, const double* p_env, const float* ta, const float* hus,
+                                const double* sst, const double* psl, double ck_over_cd, int k_mid,
+                                double* vmax, double* chi, double* rh_mid, int on_device)
+{
+    return thermo_month_impl(h, true, n_pts, nlev, p_env, ta, hus, sst, psl, ck_over_cd, k_mid, vmax, chi, rh_mid, on_device);
 }
 
 }  // extern "C"

@@ -299,7 +299,10 @@ def make_engine(nl, reference_root, device=0):
     from .engine import Engine
     from .params import params_from_namelist
     eng = Engine(params_from_namelist(nl, "GL"), device=device)
-    eng.set_entropy_table(*preproc.load_entropy_table(os.path.join(reference_root, "thermo", "entropy_table.npz")))
+    if getattr(nl, "select_thermo", 1) == 2:                             # thermo.py:279-284
+        eng.set_entropy_table_reversible(*preproc.load_entropy_table(os.path.join(reference_root, "thermo", "entropy_table_reversible.npz")))
+    else:
+        eng.set_entropy_table(*preproc.load_entropy_table(os.path.join(reference_root, "thermo", "entropy_table.npz")))
     return eng
 
 

@@ -315,9 +315,22 @@ class Engine:
             raise ValueError("T_lookup must be [len(p), len(s)]")
         _lib.check(self.lib.tcr_set_entropy_table(self._h, p_look.size, s_look.size, _ptr(p_look), _ptr(s_look), _ptr(T_lookup)))
 
-    def thermo_month(self, p_env, ta, hus, sst, psl, ck_over_cd, k_mid):
+    def set_entropy_table_reversible(self, p_look, s_look, rt_look, T_lookup):
+        """The three-dimensional inversion table of thermo/entropy_table_reversible.npz (thermo.py:279-284), for
+        namelist.select_thermo = 2."""
+        p_look, s_look, rt_look, T_lookup = (_arr(a, np.float64) for a in (p_look, s_look, rt_look, T_lookup))
+        if T_lookup.shape != (p_look.size, s_look.size, rt_look.size):
+            raise ValueError("T_lookup must be [len(p), len(s), len(rt)]")
+        _lib.check(self.lib.tcr_set_entropy_table_reversible(self._h, p_look.size, s_look.size, rt_look.size, _ptr(p_look),
+                                                             _ptr(s_look), _ptr(rt_look), _ptr(T_lookup)))
+
+    def thermo_month(self, p_env, ta, hus, sst, psl, ck_over_cd, k_mid, select_thermo=1):
         """vmax, chi, rh_mid of one time sample (thermo/calc_thermo.py:60-69); ta, hus [nlev, ...grid] float32,
-        lowest model level first; returns three float64 arrays shaped like sst."""
+        lowest model level first; returns three float64 arrays shaped like sst.  select_thermo as in the namelist:
+        1 pseudoadiabatic (set_entropy_table), 2 reversible (set_entropy_table_reversible)."""
+        if select_thermo not in (1, 2):
+            raise ValueError("select_thermo must be 1 or 2 (namelist.py:59)")
+        fn = self.lib.tcr_thermo_month if select_thermo == 1 else self.lib.tcr_thermo_month_reversible
         p_env = _arr(p_env, np.float64)
         ta, hus = _arr(ta, np.float32), _arr(hus, np.float32)
         sst, psl = _arr(sst, np.float64), _arr(psl, np.float64)
@@ -325,15 +338,16 @@ class Engine:
         if ta.shape[0] != p_env.size or ta.size != p_env.size * n or hus.shape != ta.shape or psl.size != n:
             raise ValueError("inconsistent shapes")
         out = [np.empty(sst.shape) for _ in range(3)]
-        _lib.check(self.lib.tcr_thermo_month(self._h, n, p_env.size, _ptr(p_env), _ptr(ta), _ptr(hus), _ptr(sst), _ptr(psl),
-                                             float(ck_over_cd), int(k_mid), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), 0))
+        _lib.check(fn(self._h, n, p_env.size, _ptr(p_env), _ptr(ta), _ptr(hus), _ptr(sst), _ptr(psl),
+                      float(ck_over_cd), int(k_mid), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), 0))
         return tuple(out)
 
-    def thermo_month_dev(self, n_pts, p_env, d_ta, d_hus, d_sst, d_psl, ck_over_cd, k_mid, d_vmax, d_chi, d_rh):
+    def thermo_month_dev(self, n_pts, p_env, d_ta, d_hus, d_sst, d_psl, ck_over_cd, k_mid, d_vmax, d_chi, d_rh, select_thermo=1):
         p_env = _arr(p_env, np.float64)
         vp = C.c_void_p
-        _lib.check(self.lib.tcr_thermo_month(self._h, int(n_pts), p_env.size, _ptr(p_env), vp(d_ta), vp(d_hus), vp(d_sst), vp(d_psl),
-                                             float(ck_over_cd), int(k_mid), vp(d_vmax), vp(d_chi), vp(d_rh), 1))
+        fn = self.lib.tcr_thermo_month if select_thermo == 1 else self.lib.tcr_thermo_month_reversible
+        _lib.check(fn(self._h, int(n_pts), p_env.size, _ptr(p_env), vp(d_ta), vp(d_hus), vp(d_sst), vp(d_psl),
+                      float(ck_over_cd), int(k_mid), vp(d_vmax), vp(d_chi), vp(d_rh), 1))
 
     def poi_vmax(self, lon, lat, vmax, poi_lon, poi_lat, radius_km=100.0, r_earth_m=6378000.0):
         """Per-track maximum of vmax while within radius_km of (poi_lon, poi_lat); NaN if never."""

@@ -36,8 +36,8 @@ p_midlevel = 60000                    # Pa, mid-level of the saturation deficit
 PI_reduc = 0.80
 Ck = 1.2e-3
 Cd = 1.2e-3
-select_thermo = 1                     # 1 pseudoadiabatic (the only mode the device kernel implements)
-select_interp = 2                     # 2 entropy look-up table (ditto)
+select_thermo = 1                     # 1 pseudoadiabatic, 2 reversible (k_thermo<false> / k_thermo<true>)
+select_interp = 2                     # 2 entropy look-up table (the only mode CAPE_PI_vectorized, thermo.py:266, has)
 
 # --- track / intensity constants (reference namelist.py:70-94) --------------
 steering_levels = [250, 850]

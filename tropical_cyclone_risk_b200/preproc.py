@@ -92,9 +92,11 @@ def calc_wnd_stat(engine, ua, va, times, levels, dt, level_units="hPa", group_su
 # thermodynamics: thermo/calc_thermo.py:24-72 (compute_thermo) on the device
 # ---------------------------------------------------------------------------------------------
 def load_entropy_table(path):
-    """thermo/entropy_table.npz of a reference checkout (thermo.py:274-278): (p_look, s_look, T_lookup)."""
+    """thermo/entropy_table.npz of a reference checkout (thermo.py:274-278): (p_look, s_look, T_lookup); for
+    thermo/entropy_table_reversible.npz (thermo.py:279-284): (p_look, s_look, rt_look, T_lookup)."""
     with np.load(path) as t:
-        return np.array(t["p"], dtype=np.float64), np.array(t["s"], dtype=np.float64), np.array(t["T"], dtype=np.float64)
+        keys = ("p", "s", "rt", "T") if "rt" in t.files else ("p", "s", "T")
+        return tuple(np.array(t[k], dtype=np.float64) for k in keys)
 
 
 def order_levels(levels, level_units, ta, hus, p_midlevel_pa):
@@ -117,10 +119,16 @@ def compute_thermo(engine, sst, psl, ta, hus, levels, namelist, level_units="hPa
     sst (time, lat_s, lon_s), psl (time, lat, lon), ta / hus (time, level, lat, lon).  When the SST grid
     differs from the atmospheric grid pass both axis pairs: the SST is regridded like
     mat.interp_2d_grid(nan_to_num(sst)) (calc_thermo.py:38-40).  Returns (vmax, chi, rh_mid), each
-    (time, lat, lon) float64.  engine.set_entropy_table must have been called."""
+    (time, lat, lon) float64.  engine.set_entropy_table (namelist.select_thermo = 1) or
+    engine.set_entropy_table_reversible (select_thermo = 2) must have been called.  select_interp = 1 (BFGS inversion of
+    the entropy, thermo.py:223-233) exists only in the reference's scalar CAPE_PI, which nothing calls: CAPE_PI_vectorized,
+    the function calc_thermo.py:61 runs, reads the look-up table whatever select_interp says (and fails with a NameError
+    when it is not 2); it is refused here."""
     from . import fields
-    if namelist.select_thermo != 1 or namelist.select_interp != 2:
-        raise NotImplementedError("the device kernel implements select_thermo = 1, select_interp = 2 (the namelist defaults)")
+    if namelist.select_thermo not in (1, 2):
+        raise ValueError("namelist.select_thermo must be 1 (pseudoadiabatic) or 2 (reversible)")
+    if namelist.select_interp != 2:
+        raise NotImplementedError("select_interp = 1: CAPE_PI_vectorized (thermo.py:266) has no computed-inversion branch either")
     sst, psl = np.asarray(sst), np.asarray(psl)
     p_env, k_mid, ta, hus = order_levels(levels, level_units, np.asarray(ta), np.asarray(hus), float(namelist.p_midlevel))
     n_time = psl.shape[0]
@@ -131,7 +139,7 @@ def compute_thermo(engine, sst, psl, ta, hus, levels, namelist, level_units="hPa
             s = fields.regrid(sst_lon, sst_lat, s, lon, lat)
         if "C" in sst_units:                                           # calc_thermo.py:41-42
             s = s + 273.15
-        v, c, r = engine.thermo_month(p_env, ta[i], hus[i], s, psl[i], namelist.Ck / namelist.Cd, k_mid)
+        v, c, r = engine.thermo_month(p_env, ta[i], hus[i], s, psl[i], namelist.Ck / namelist.Cd, k_mid, namelist.select_thermo)
         out[0][i], out[1][i], out[2][i] = v, c, r
     return tuple(out)
 
