@@ -972,7 +972,10 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
             CK(cudaMemGetInfo(&free_b, &total_b));
             if (ring_nodes) w0.ftab.release(); else w0.ring.release();
             size_t held = w0.ftab.bytes + w0.ring.bytes + w0.track.bytes + w0.env.bytes + w0.vmax.bytes + w0.coef.bytes + w0.out.bytes;
-            size_t budget = std::min<size_t>((size_t)96 << 30, (size_t)((free_b + held) * 0.6));
+            /* share of the free memory a wave's workspace may take, and its cap (TCR_WS_FRAC, TCR_WS_CAP_GB: A/B runs) */
+            static const double ws_frac = getenv("TCR_WS_FRAC") ? atof(getenv("TCR_WS_FRAC")) : 0.6;
+            static const size_t ws_cap = (size_t)(getenv("TCR_WS_CAP_GB") ? atoi(getenv("TCR_WS_CAP_GB")) : 96) << 30;
+            size_t budget = std::min<size_t>(ws_cap, (size_t)((free_b + held) * ws_frac));
             if (budget > out_bytes) budget -= out_bytes;
             const int64_t cap_mem = (int64_t)((double)budget / ((double)kAttemptBytes + pass_est * (double)slot_bytes(ns, ring_nodes)));
             /* 25 % headroom so that the next call's slightly different estimate still fits */
