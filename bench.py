@@ -59,9 +59,11 @@ NCU_INTEGRATE = {
                        "l1_data_pipe_wavefronts_pct": 31.2},
     # a launch of this workload touches tens of gigabytes of workspace: `--set full` (about 40 replays with memory save /
     # restore) is not practical, the DRAM counters alone were collected over nine consecutive launches = one step
+    # per STEP (the number of launches per step depends on the workspace budget: nine waves when this was measured; the bench
+    # line divides by the launches per step of its own run)
     "GL_40_5000_361": {"source": "profiles/r02_integrate_cfg2_dram.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, "
-                                 "nine consecutive launches = one step; average per launch)",
-                       "traffic": 27.85e9 + 13.46e9, "l2_hit_pct": 74.2},
+                                 "nine consecutive launches = one step; summed over the step, divided by this run's launches per step)",
+                       "traffic_per_step": 9 * (27.85e9 + 13.46e9), "l2_hit_pct": 74.2},
 }
 
 
@@ -307,6 +309,11 @@ def run_gpu_arm(args):
     wl.upload(eng)
     if args.integ_variant:
         eng.set_tuning(integ_variant=args.integ_variant)
+    if world == 1:
+        # one process, nothing but this bench's own result blocks and roofline legs (< 20 GB) allocated after the workspace is
+        # sized: configs[2] then runs in fewer, larger waves (7 instead of 9 at 0.8: +1 %, profiles/r02_ring_ab.txt).  Under torchrun every rank also
+        # holds the peer-copy blocks of the whole world, so the library default (0.6 of the free memory) stays.
+        eng.set_workspace_budget(0.75, 150 << 30)
     ym_base = np.arange(ny, dtype=np.int32) * 12
     year_key = np.asarray(years, dtype=np.int32)
 
@@ -476,14 +483,18 @@ def run_gpu_arm(args):
         cfg_key = "%s_%d_%d_%d" % (args.basin, args.years, args.tracks, ns)
         ncu = NCU_INTEGRATE.get(cfg_key)
         roof = {"kernel": "k_integrate", "bound": "hbm", "achieved": ki_ach, "peak": peak, "unit": "GB/s",
-                "frac": ki_ach / peak, "traffic": ncu["traffic"] if ncu else None,
+                "frac": ki_ach / peak,
+                "traffic": (ncu["traffic"] if "traffic" in ncu else ncu["traffic_per_step"] / max(ki_n / K, 1)) if ncu else None,
                 "algorithmic_bytes_per_launch": ki_bytes / max(ki_n, 1), "peak_source": peak_src,
                 "launches": ki_n, "avg_launch_ms": ki_ms / max(ki_n, 1),
                 "share_of_step": ki_ms / ms, "rhs_per_s": rhs_all / (ki_ms * 1e-3) if ki_ms > 0 else 0.0}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, ns),
+            "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args, ns), fourier_series=(
+                "rings of %d nodes per track-pool row, filled by k_integrate on demand" % eng.fourier_ring_nodes
+                if eng.fourier_ring_nodes else "full tables ahead of the integrator (k_fourier_table_mma, FP64 tensor cores)")),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e_max / K},
             "gpu_launches": launches_all,

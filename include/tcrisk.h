@@ -238,6 +238,16 @@ int tcr_seed_attempts(tcr_handle* h, int ym_base, int32_t year_key, uint32_t run
  * kernels); only speed and the amount of discarded work do.                                  */
 int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int64_t max_wave_slots,
                    int oversub_permille);
+/* How tcr_run_years tabulates the storms' Fourier series for this handle's output grid: 0 = full tables ahead of the
+ * integrator (k_fourier_table_mma), n > 0 = rings of n nodes per track-pool row that k_integrate fills on demand
+ * (the default where the grid is at least four rings long, i.e. on 900-s output; TCR_FTAB_RING=0 / 1 at tcr_create
+ * forces either).  Results never depend on it.                                                                   */
+int tcr_fourier_ring_nodes(tcr_handle* h);
+/* memory the per-wave workspace of tcr_run_years may take: a fraction of the device memory that is free when the
+ * workspace is sized (default 0.6) and an absolute cap (default 96 GiB).  A larger budget means fewer, larger waves
+ * (configs[2]: 9 waves at 0.6, 7 at 0.8: +1 %); what it leaves must hold whatever the caller allocates afterwards.
+ * Results never depend on it.                                                                                    */
+int tcr_set_workspace_budget(tcr_handle* h, double fraction_of_free, int64_t cap_bytes);
 /* number of kernels launched by this handle so far (bench.py's gpu_launches)               */
 int64_t tcr_launch_count(tcr_handle* h);
 /* device-time accounting: with timing enabled every launch of a kernel class is bracketed by

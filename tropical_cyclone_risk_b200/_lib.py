@@ -15,7 +15,7 @@ SYMBOLS = (
     "tcr_env_interp", "tcr_integrate", "tcr_run_years", "tcr_seed_attempts", "tcr_set_tuning",
     "tcr_launch_count", "tcr_set_interp_variant", "tcr_host_alloc", "tcr_host_free",
     "tcr_set_timing", "tcr_kernel_time", "tcr_poi_vmax", "tcr_exceedance", "tcr_prepare_month",
-    "tcr_wind_stats", "tcr_set_entropy_table", "tcr_thermo_month", "tcr_set_entropy_table_reversible", "tcr_thermo_month_reversible", "tcr_rhs_eval", "tcr_set_shard",
+    "tcr_wind_stats", "tcr_set_entropy_table", "tcr_thermo_month", "tcr_set_entropy_table_reversible", "tcr_thermo_month_reversible", "tcr_set_workspace_budget", "tcr_fourier_ring_nodes", "tcr_rhs_eval", "tcr_set_shard",
 )
 
 _lib = None
@@ -60,6 +60,8 @@ def load():
     lib.tcr_run_years.argtypes = [vp, C.c_int, vp, vp, C.c_uint32, C.c_int] + [vp] * 9 + [C.POINTER(TcrYearStats), C.c_int]
     lib.tcr_seed_attempts.argtypes = [vp, C.c_int, C.c_int32, C.c_uint32, C.c_int64, C.c_int64] + [vp] * 8
     lib.tcr_set_tuning.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, C.c_int]
+    lib.tcr_set_workspace_budget.argtypes = [vp, C.c_double, C.c_int64]
+    lib.tcr_fourier_ring_nodes.argtypes = [vp]
     lib.tcr_launch_count.argtypes = [vp]
     lib.tcr_launch_count.restype = C.c_int64
     lib.tcr_set_interp_variant.argtypes = [vp, C.c_int]

@@ -134,6 +134,7 @@ struct tcr_handle {
     bool have_static = false, have_masks = false;
     /* tuning */
     int integ_variant = 21, oversub_permille = 1020, interp_variant = 0;
+    double ws_frac = 0.6; size_t ws_cap = (size_t)96 << 30;   /* tcr_set_workspace_budget */
     int ftab_ring = -1;          /* tcr_run_years: Fourier rings filled by the integrator (1), full tables tabulated ahead of it (0), or
                                   * by the length of the output grid (-1, default: ring_nodes_for) */
     /* within-year sharding (tcr_set_shard): rank r of `world` integrates the attempts k with k % world == r */
@@ -339,6 +340,24 @@ int tcr_set_tuning(tcr_handle* h, int integ_variant, int64_t max_wave_cands, int
     if (max_wave_cands > 0) h->max_wave = max_wave_cands;
     if (max_wave_slots > 0) h->max_slots = max_wave_slots;
     if (oversub_permille > 0) h->oversub_permille = oversub_permille;
+    return 0;
+}
+
+static int ring_nodes_for(const tcr_handle* h);
+int tcr_fourier_ring_nodes(tcr_handle* h)
+{
+    if (!h) return set_err("null handle");
+    return ring_nodes_for(h);
+}
+
+int tcr_set_workspace_budget(tcr_handle* h, double fraction_of_free, int64_t cap_bytes)
+{
+    if (!h) return set_err("null handle");
+    if (!(fraction_of_free > 0.0 && fraction_of_free <= 0.95) || cap_bytes <= 0)
+        return set_err("tcr_set_workspace_budget: fraction in (0, 0.95], cap_bytes > 0");
+    h->ws_frac = fraction_of_free;
+    h->ws_cap = (size_t)cap_bytes;
+    h->ws.mem_limited = false;                       /* the next tcr_run_years sizes its workspace again */
     return 0;
 }
 
@@ -972,9 +991,12 @@ int tcr_run_years(tcr_handle* h, int n_years, const int32_t* ym_base, const int3
             CK(cudaMemGetInfo(&free_b, &total_b));
             if (ring_nodes) w0.ftab.release(); else w0.ring.release();
             size_t held = w0.ftab.bytes + w0.ring.bytes + w0.track.bytes + w0.env.bytes + w0.vmax.bytes + w0.coef.bytes + w0.out.bytes;
-            /* share of the free memory a wave's workspace may take, and its cap (TCR_WS_FRAC, TCR_WS_CAP_GB: A/B runs) */
-            static const double ws_frac = getenv("TCR_WS_FRAC") ? atof(getenv("TCR_WS_FRAC")) : 0.6;
-            static const size_t ws_cap = (size_t)(getenv("TCR_WS_CAP_GB") ? atoi(getenv("TCR_WS_CAP_GB")) : 96) << 30;
+            /* share of the free memory a wave's workspace may take, and its cap (tcr_set_workspace_budget; TCR_WS_FRAC,
+             * TCR_WS_CAP_GB override both for A/B runs) */
+            static const double env_frac = getenv("TCR_WS_FRAC") ? atof(getenv("TCR_WS_FRAC")) : 0.0;
+            static const size_t env_cap = (size_t)(getenv("TCR_WS_CAP_GB") ? atoi(getenv("TCR_WS_CAP_GB")) : 0) << 30;
+            const double ws_frac = env_frac > 0.0 ? env_frac : h->ws_frac;
+            const size_t ws_cap = env_cap ? env_cap : h->ws_cap;
             size_t budget = std::min<size_t>(ws_cap, (size_t)((free_b + held) * ws_frac));
             if (budget > out_bytes) budget -= out_bytes;
             const int64_t cap_mem = (int64_t)((double)budget / ((double)kAttemptBytes + pass_est * (double)slot_bytes(ns, ring_nodes)));

@@ -80,6 +80,18 @@ class Engine:
         (x1000).  Results never depend on these."""
         _lib.check(self.lib.tcr_set_tuning(self._h, integ_variant, max_wave, max_slots, oversub_permille))
 
+    @property
+    def fourier_ring_nodes(self):
+        """0: run_years tabulates full Fourier tables ahead of the integrator; n: rings of n nodes filled inside it."""
+        n = self.lib.tcr_fourier_ring_nodes(self._h)
+        if n < 0:
+            _lib.check(n)
+        return int(n)
+
+    def set_workspace_budget(self, fraction_of_free=0.6, cap_bytes=96 << 30):
+        """Memory the per-wave workspace of run_years may take (tcr_set_workspace_budget): fewer, larger waves with more."""
+        _lib.check(self.lib.tcr_set_workspace_budget(self._h, float(fraction_of_free), int(cap_bytes)))
+
     def set_shard(self, rank, world, allreduce=None):
         """Within-year sharding (tcr_set_shard): run_years becomes collective over `world` engines; this one integrates
         the attempts k with k % world == rank.  allreduce(ptr, count, dtype, op, stream) -> None performs the in-place
