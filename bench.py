@@ -53,17 +53,19 @@ NCU_TRAFFIC = {"k_env_interp": 10.152e9 + 5.609e9, "k_wind_stats": 1.030e9 + 0.1
                "k_poi_vmax": 2.003e9 + 0.0065e9}
 # k_integrate, keyed by workload (basin_years_tracks_steps): the committed ncu capture of THAT workload
 NCU_INTEGRATE = {
-    "NA_10_1000_361": {"source": "profiles/r02_prof_integrate_summary.txt (ncu --set full, one launch)", "traffic": 2.079e9 + 1.828e9,
-                       "fp64_pipe_pct_of_peak": 31.7, "issue_slots_busy_pct": 36.9, "lanes_per_instruction": 23.3,
-                       "l2_hit_pct": 83.0, "dram_pct_of_peak": 5.9, "registers": 168, "warps_per_sm": 12,
+    "NA_10_1000_361": {"source": "profiles/r02_prof_integrate_summary.txt (ncu --set full, one launch)", "traffic": 2.073e9 + 1.829e9,
+                       "fp64_pipe_pct_of_peak": 32.2, "issue_slots_busy_pct": 38.0, "lanes_per_instruction": 23.3,
+                       "l2_hit_pct": 82.9, "dram_pct_of_peak": 5.9, "registers": 168, "warps_per_sm": 12,
                        "l1_data_pipe_wavefronts_pct": 31.2},
     # a launch of this workload touches tens of gigabytes of workspace: `--set full` (about 40 replays with memory save /
     # restore) is not practical, the DRAM counters alone were collected over nine consecutive launches = one step
-    # per STEP (the number of launches per step depends on the workspace budget: nine waves when this was measured; the bench
-    # line divides by the launches per step of its own run)
-    "GL_40_5000_361": {"source": "profiles/r02_integrate_cfg2_dram.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, "
-                                 "nine consecutive launches = one step; summed over the step, divided by this run's launches per step)",
-                       "traffic_per_step": 9 * (27.85e9 + 13.46e9), "l2_hit_pct": 74.2},
+    # per STEP (the number of launches per step depends on the workspace budget; the bench line divides by the launches per
+    # step of its own run): a step of seven waves = six full ones (37.57 GB read + 18.81 GB written each, 80.2 ms) and the
+    # last, partial one (21.09 + 9.30 GB, 41.8 ms); the nine-wave step of the earlier capture summed to 371.8 GB
+    "GL_40_5000_361": {"source": "profiles/r02_integrate_cfg2_dram.csv (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,"
+                                 "gpu__time_duration.sum,lts__t_sector_hit_rate.pct over consecutive launches of the default "
+                                 "command; summed over one step, divided by this run's launches per step)",
+                       "traffic_per_step": 6 * (37.57e9 + 18.81e9) + (21.09e9 + 9.30e9), "l2_hit_pct": 75.8},
 }
 
 
