@@ -261,3 +261,38 @@ def test_the_reference_namelist_is_accepted_unchanged():
     assert driver.get_env_wnd_fn(nl).endswith("env_wnd_era5_201601_202112.nc")
     assert driver.get_fn_thermo(nl).endswith("thermo_era5_201601_202112.nc")
     assert nl.var_keys[nl.dataset_type]["mslp"] == "sp" and nl.select_thermo == 1 and nl.select_interp == 2
+
+
+def test_make_engine_loads_the_table_the_namelist_selects(tmp_path, monkeypatch):
+    """driver.make_engine: thermo/entropy_table.npz for select_thermo = 1, thermo/entropy_table_reversible.npz for 2
+    (thermo.py:274-284), through preproc.load_entropy_table."""
+    import types
+    from tropical_cyclone_risk_b200 import driver, engine, preproc
+    from tropical_cyclone_risk_b200 import namelist as nl
+    root = tmp_path / "ref"
+    (root / "thermo").mkdir(parents=True)
+    p, s, rt = np.linspace(2500.0, 105000.0, 5), np.linspace(2300.0, 3600.0, 4), np.linspace(0.0, 0.04, 3)
+    np.savez(root / "thermo" / "entropy_table.npz", p=p, s=s, T=np.arange(20.0).reshape(5, 4))
+    np.savez(root / "thermo" / "entropy_table_reversible.npz", p=p, s=s, rt=rt, T=np.arange(60.0).reshape(5, 4, 3))
+    t2 = preproc.load_entropy_table(str(root / "thermo" / "entropy_table.npz"))
+    t3 = preproc.load_entropy_table(str(root / "thermo" / "entropy_table_reversible.npz"))
+    assert [a.shape for a in t2] == [(5,), (4,), (5, 4)] and [a.shape for a in t3] == [(5,), (4,), (3,), (5, 4, 3)]
+    calls = []
+
+    class FakeEngine:
+        def __init__(self, params, device=0):
+            calls.append(("create", device))
+
+        def set_entropy_table(self, *table):
+            calls.append(("pseudo", [np.shape(a) for a in table]))
+
+        def set_entropy_table_reversible(self, *table):
+            calls.append(("reversible", [np.shape(a) for a in table]))
+
+    monkeypatch.setattr(engine, "Engine", FakeEngine)
+    for sel, want in ((1, "pseudo"), (2, "reversible")):
+        nl2 = types.SimpleNamespace(**{k: getattr(nl, k) for k in dir(nl) if not k.startswith("__")})
+        nl2.select_thermo = sel
+        del calls[:]
+        driver.make_engine(nl2, str(root), device=3)
+        assert calls[0] == ("create", 3) and calls[1][0] == want and len(calls) == 2
